@@ -1,0 +1,149 @@
+/*
+ * ggufb200.h -- C-ABI of libggufb200.so, the B200 (sm_100a) compute library of the GGUF decode engine.
+ *
+ * What this replaces.  The reference (zepfu/llama-gguf-inference) contains no native code: its compute is
+ * the third-party `/app/llama-server` process that scripts/start.sh:473-480,516 spawns and that
+ * scripts/gateway.py:699-804 proxies to.  The process/HTTP contract of that binary is re-implemented by the
+ * python host in this repository (llama-gguf-inference_b200/server.py, cli.py); this header is the boundary
+ * between that host and the hand-written CUDA kernels -- the place where, in the reference's backend,
+ * llama.cpp calls into ggml / ggml-cuda [UPSTREAM-MEM].  Each entry point names the ggml operation it
+ * stands in for.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types, no exceptions across the boundary;
+ *   - every function returns 0 on success or a negative GGB_ERR_* code; ggb_last_error() returns the
+ *     thread-local message of the last failure on the calling thread;
+ *   - device pointers are caller-owned (the host allocates with torch); the library never frees them and
+ *     keeps no hidden device state besides cached device attributes;
+ *   - every launch takes the caller's CUDA stream (cudaStream_t passed as void*), performs no host
+ *     synchronisation and no allocation, so all entry points are CUDA-graph capturable;
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef GGUFB200_H
+#define GGUFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGB_ABI_VERSION 1
+
+/* ggml tensor type ids (gguf/constants.py:4059-4093) */
+#define GGB_TYPE_F32 0
+#define GGB_TYPE_F16 1
+#define GGB_TYPE_Q8_0 8
+#define GGB_TYPE_Q4_K 12
+#define GGB_TYPE_Q5_K 13
+#define GGB_TYPE_Q6_K 14
+
+#define GGB_OK 0
+#define GGB_ERR_ARG (-1)     /* bad argument (null pointer, unsupported type, misaligned or ragged size) */
+#define GGB_ERR_CUDA (-2)    /* a CUDA runtime call or launch failed */
+#define GGB_ERR_UNSUPPORTED (-3)
+
+int ggb_abi_version(void);
+const char* ggb_last_error(void);
+/* name / SM count / compute capability / total memory of the current device */
+int ggb_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- K0: dequantisation (ggml dequantize_row_q8_0 / q4_K / q5_K / q6_K; bit-exact)
+ * `w` holds n elements in CANONICAL GGUF block layout; out = n floats. */
+int ggb_dequant(int type, const void* w, float* out, int64_t n, void* stream);
+
+/* ---- load-time repack: canonical GGUF rows -> tile-SoA rows (csrc/layout.cuh).  Same byte count per row
+ * up to a 16-byte round-up of the row stride.  k must be a multiple of 256. */
+int64_t ggb_repacked_row_stride(int type, int64_t k);
+int ggb_repack(int type, const void* canon, void* dst, int64_t rows, int64_t k, void* stream);
+/* inverse check / get_rows on repacked weights: out[rows][k] floats, bit-exact with ggb_dequant */
+int ggb_dequant_repacked(int type, const void* w, float* out, int64_t rows, int64_t k, void* stream);
+
+/* ---- activation quantisation (ggml quantize_row_q8_K / quantize_row_q8_0), m rows of k floats.
+ * Q8_K: qs[m][k] int8, d[m][k/256] f32, bsums[m][k/16] int16.   Q8_0: qs[m][k] int8, d[m][k/32] f16 bits. */
+int ggb_quantize_q8_K(const float* x, int8_t* qs, float* d, int16_t* bsums, int64_t k, int m, void* stream);
+int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m, void* stream);
+
+/* ---- K1: fused dequant-GEMV  y = W.x  (ggml mul_mat with one activation column: quantize_row_q8_K +
+ * ggml_vec_dot_q*_K_q8_K).  One launch covers up to GGB_MAX_SEG weight matrices that share the input vector.
+ *
+ *   prologue (how the K-vector the CTAs quantise is produced)
+ *     GGB_PRO_PLAIN     x
+ *     GGB_PRO_RMSNORM   rms_norm(x, eps) * norm_w                     (ggml_rms_norm + ggml_mul)
+ *   epilogue
+ *     GGB_EPI_STORE     y_s[r] = dot
+ *     GGB_EPI_RESIDUAL  y_0[r] = residual[r] + dot                    (ggml_add; y_0 may alias residual)
+ *     GGB_EPI_SWIGLU    y_0[r] = silu(dot_0[r]) * dot_1[r]            (segments 0 = gate, 1 = up)
+ *     GGB_EPI_ROPE_KV   segments 0,1,2 = q,k,v: rope(q) -> y_0 (f32); rope(k) -> f16 kcache[pos]; v -> f16
+ *                       vcache[pos]  (ggml_rope NORM mode + ggml_cpy into the KV cache); pos is read from
+ *                       device memory so a captured graph can be replayed for every position
+ *     GGB_EPI_ARGMAX    y_0[r] = dot and per-CTA (max, first index) partials for the greedy sampler
+ */
+#define GGB_MAX_SEG 3
+#define GGB_PRO_PLAIN 0
+#define GGB_PRO_RMSNORM 1
+#define GGB_EPI_STORE 0
+#define GGB_EPI_RESIDUAL 1
+#define GGB_EPI_SWIGLU 2
+#define GGB_EPI_ROPE_KV 3
+#define GGB_EPI_ARGMAX 4
+
+typedef struct ggb_gemv_seg {
+    const void* w;   /* tile-SoA weights [rows][row_stride] */
+    int32_t type;    /* GGB_TYPE_Q4_K / Q5_K / Q6_K / Q8_0 */
+    int32_t rows;
+    float* y;        /* output vector of this segment (f32) or NULL when the epilogue consumes it */
+} ggb_gemv_seg;
+
+typedef struct ggb_gemv_args {
+    int32_t n_seg;
+    int32_t k;                 /* shared inner dimension, multiple of 256 */
+    ggb_gemv_seg seg[GGB_MAX_SEG];
+    int32_t prologue;
+    int32_t epilogue;
+    const float* x;            /* [k] input */
+    const float* norm_w;       /* [k] RMSNorm gain (GGB_PRO_RMSNORM) */
+    float eps;
+    int32_t use_pdl;           /* launch with programmatic stream serialisation */
+    const float* residual;     /* GGB_EPI_RESIDUAL */
+    /* GGB_EPI_ROPE_KV */
+    const int32_t* pos_dev;    /* device scalar: position of this token */
+    const float* rope_tab;     /* [n_ctx][n_rot/2][2] cos,sin */
+    int32_t n_rot, head_dim;
+    uint16_t* kcache;          /* [n_ctx][rows_k] f16 bits */
+    uint16_t* vcache;          /* [n_ctx][rows_v] f16 bits */
+    /* GGB_EPI_ARGMAX */
+    float* part_val;           /* [grid] */
+    int32_t* part_idx;         /* [grid] */
+    int32_t grid;              /* 0 = library default (a multiple of the SM count) */
+} ggb_gemv_args;
+
+int ggb_gemv(const ggb_gemv_args* args, void* stream);
+/* number of CTAs ggb_gemv will launch for these args (size of part_val/part_idx) */
+int ggb_gemv_grid(const ggb_gemv_args* args);
+
+/* ---- small fused glue */
+/* embedding gather (ggml get_rows on canonical token_embd): x[k] = dequant(row tok) ; tok read from device */
+int ggb_embed_row(int type, const void* token_embd, int64_t k, const int32_t* tok_dev, float* x, void* stream);
+/* reduce the GEMV's argmax partials to the token id (first index of the maximum), append it to
+ * out_tokens[*step_dev], advance *pos_dev and *step_dev, and gather the next embedding row into x */
+int ggb_argmax_next(const float* part_val, const int32_t* part_idx, int n_part, int32_t* tok_dev,
+                    int32_t* pos_dev, int32_t* step_dev, int32_t* out_tokens, int32_t out_cap,
+                    int emb_type, const void* token_embd, int64_t k, float* x, void* stream);
+/* plain ops, exported for tests and for the prefill path */
+int ggb_rms_norm(const float* x, const float* w, float* y, int64_t k, int m, float eps, void* stream);
+int ggb_swiglu(const float* g, const float* u, float* out, int64_t n, void* stream);
+int ggb_argmax(const float* x, int64_t n, int32_t* out_idx, void* stream);
+
+/* ---- KV-cache attention, one query token (ggml flash_attn_ext / soft_max path, GQA)
+ * q [n_head*hd] f32 (already rotated); caches [n_ctx][n_kv*hd] f16; attends positions 0..*pos_dev inclusive.
+ * ws: workspace of ggb_attn_decode_ws_bytes() bytes.  out [n_head*hd] f32. */
+size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim);
+int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
+                    int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGUFB200_H */

@@ -1,0 +1,190 @@
+// attn.cu -- K6: KV-cache attention for one query token (decode), grouped-query heads, f16 cache.
+// Stands in for ggml's flash_attn_ext / soft_max + mul_mat path on the CPU backend [UPSTREAM-MEM]:
+//   q is rounded to f16 (the CPU path converts the K.Q operand to the cache type), scores = q.k / sqrt(hd),
+//   softmax in f32, out = P.V normalised at the end.
+//
+// One thread-block CLUSTER of 8 CTAs per query head (B200: distributed shared memory + cluster barrier):
+//   pass 1  every CTA scores its slice of positions (f16 x f16 products are exact in f32; summed in f64) and
+//           keeps them in shared memory; the slice maxima are exchanged through DSMEM -> global max M;
+//   pass 2  e = exp_ref(s - M); per-CTA f64 partial sums of e and of e*v; rank 0 gathers the eight partials
+//           through DSMEM in rank order and writes out = (float)(sum_ev / sum_e).
+// A true two-pass softmax (one global max) in a single launch: no split-KV merge kernel, no running-max
+// rescaling, and -- because every sum is an f64 sum of f32 terms -- the result does not depend on how the
+// positions are split, so it is bit-identical with the oracle's gref_attn_decode_canon.
+// The grid does not depend on the position (read from device memory): the launch replays inside a CUDA graph.
+#include <cooperative_groups.h>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define ATTN_CL 8      /* CTAs per cluster = position slices per head */
+#define ATTN_WARPS 4
+
+template <int HD>
+__global__ void __cluster_dims__(ATTN_CL, 1, 1) __launch_bounds__(ATTN_WARPS * 32)
+attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
+                   const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out) {
+    constexpr int LPG = HD / 8;        // lanes per position (each lane owns 8 consecutive dims = one 16-byte load)
+    constexpr int PPW = 32 / LPG;      // positions per warp step
+    constexpr int SLOTS = ATTN_WARPS * PPW;
+    extern __shared__ __align__(16) float s_scores[];   // this CTA's slice of scores
+    __shared__ double sm_acc[SLOTS][HD];
+    __shared__ double sm_sum[SLOTS];
+    __shared__ float sm_max[ATTN_WARPS];
+    __shared__ float cl_max;            // read by the other CTAs of the cluster
+    __shared__ double cl_acc[HD];       // read by rank 0
+    __shared__ double cl_sum;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int head = blockIdx.x / ATTN_CL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPG, li = lane % LPG;
+    const int kvh = head / (n_head / n_kv);
+    const int64_t kv_stride = (int64_t)n_kv * HD;
+
+    pdl_wait();
+    const int n = *pos_dev + 1;
+    int chunk = (n + ATTN_CL - 1) / ATTN_CL;
+    chunk = (chunk + 7) & ~7;
+    const int p_begin = min(n, crank * chunk), p_end = min(n, p_begin + chunk);
+
+    float qr[8];
+    {
+        const float4 a = *reinterpret_cast<const float4*>(q + (int64_t)head * HD + li * 8);
+        const float4 b = *reinterpret_cast<const float4*>(q + (int64_t)head * HD + li * 8 + 4);
+        const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) qr[i] = h2f(f2h(t[i]));
+    }
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
+
+    // ---- pass 1: scores of my slice + slice maximum
+    float mx = -INFINITY;
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += SLOTS) {
+        const int p = p0 + sub;
+        const bool live = p < p_end;
+        const uint4 kraw = *reinterpret_cast<const uint4*>(kc + (live ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+        const uint32_t kw[4] = {kraw.x, kraw.y, kraw.z, kraw.w};
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            s += (double)__fmul_rn(h2f((uint16_t)(kw[i] & 0xFFFF)), qr[2 * i]);      // exact products
+            s += (double)__fmul_rn(h2f((uint16_t)(kw[i] >> 16)), qr[2 * i + 1]);
+        }
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float sf = __fmul_rn((float)s, scale);
+        if (live) {
+            if (li == 0) s_scores[p - p_begin] = sf;
+            mx = fmaxf(mx, sf);
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) sm_max[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = sm_max[0];
+#pragma unroll
+        for (int w = 1; w < ATTN_WARPS; w++) m = fmaxf(m, sm_max[w]);
+        cl_max = m;
+    }
+    cluster.sync();
+    float M = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < ATTN_CL; r++) M = fmaxf(M, *cluster.map_shared_rank(&cl_max, r));
+
+    // ---- pass 2: e = exp_ref(s - M), f64 partial sums
+    double acc[8], sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0;
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += SLOTS) {
+        const int p = p0 + sub;
+        if (p < p_end) {
+            const float e = exp_ref(__fsub_rn(s_scores[p - p_begin], M));
+            const uint4 vraw = *reinterpret_cast<const uint4*>(vc + p * kv_stride + (int64_t)kvh * HD + li * 8);
+            const uint32_t vw[4] = {vraw.x, vraw.y, vraw.z, vraw.w};
+            sum += (double)e;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[2 * i] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] & 0xFFFF)));
+                acc[2 * i + 1] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] >> 16)));
+            }
+        }
+    }
+    const int slot = warp * PPW + sub;
+    if (li == 0) sm_sum[slot] = sum;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm_acc[slot][li * 8 + i] = acc[i];
+    __syncthreads();
+    for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+        double a = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < SLOTS; s2++) a += sm_acc[s2][d];
+        cl_acc[d] = a;
+    }
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < SLOTS; s2++) t += sm_sum[s2];
+        cl_sum = t;
+    }
+    cluster.sync();
+    if (crank == 0) {
+        double S = 0.0;
+#pragma unroll
+        for (int r = 0; r < ATTN_CL; r++) S += *cluster.map_shared_rank(&cl_sum, r);
+        for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < ATTN_CL; r++) a += cluster.map_shared_rank(cl_acc, r)[d];
+            out[(int64_t)head * HD + d] = (float)(a / S);
+        }
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
+    (void)n_head; (void)head_dim;
+    return 16; /* the cluster kernel needs no global workspace; kept in the ABI for split-KV variants */
+}
+
+template <int HD>
+static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
+                       int n_ctx, float* out, int use_pdl, cudaStream_t st) {
+    int chunk_max = (n_ctx + ATTN_CL - 1) / ATTN_CL;
+    chunk_max = (chunk_max + 7) & ~7;
+    const size_t smem = (size_t)chunk_max * sizeof(float);
+    if (smem > 96 * 1024) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: n_ctx=%d too large for the cluster kernel", n_ctx);
+    static size_t attr = 0;
+    if (smem > attr) {
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = 96 * 1024;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_head * ATTN_CL);
+    cfg.blockDim = dim3(ATTN_WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD>, q, kc, vc, pos_dev, n_head, n_kv, out));
+    return GGB_OK;
+}
+
+extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
+                               int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream) {
+    (void)ws;
+    if (!q || !kcache || !vcache || !pos_dev || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: null pointer");
+    if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
+    if (n_ctx <= 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_ctx must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) return launch_attn<128>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 64) return launch_attn<64>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: head_dim=%d (supported: 64, 128)", head_dim);
+}

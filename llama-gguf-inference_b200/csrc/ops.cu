@@ -1,0 +1,178 @@
+// ops.cu -- standalone activation quantisation and the small element-wise / reduction ops
+// (ggml quantize_row_q8_K, quantize_row_q8_0, rms_norm+mul, silu*mul, argmax [UPSTREAM-MEM]).
+// The decode path uses the fused forms inside gemv.cu; these entry points serve the prefill path and the
+// parity tests, and share the same device code (actquant.cuh).
+#include <float.h>
+
+#include "actquant.cuh"
+#include "common.cuh"
+
+// one warp per 256-block
+__global__ void quantize_q8_K_kernel(const float* __restrict__ x, int8_t* __restrict__ qs, float* __restrict__ d,
+                                     int16_t* __restrict__ bsums, int64_t nblocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const float4* p = reinterpret_cast<const float4*>(x + b * 256 + lane * 8);
+    const float4 v0 = p[0], v1 = p[1];
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float dd;
+    const Q8Codes c = warp_quantize_q8_K(v, lane, dd);
+    *reinterpret_cast<uint2*>(qs + b * 256 + lane * 8) = c.q;
+    const int s16 = c.sum8 + __shfl_xor_sync(0xffffffffu, c.sum8, 1);
+    if (!(lane & 1)) bsums[b * 16 + (lane >> 1)] = (int16_t)s16;
+    if (lane == 0) d[b] = dd;
+}
+
+__global__ void quantize_q8_0_kernel(const float* __restrict__ x, int8_t* __restrict__ qs, uint16_t* __restrict__ d, int64_t nchunks8) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; /* one thread per 8 elements */
+    const bool live = i < nchunks8;
+    const int64_t ii = live ? i : nchunks8 - 1; /* keep the whole warp in the shuffles */
+    const float4* p = reinterpret_cast<const float4*>(x + ii * 8);
+    const float4 v0 = p[0], v1 = p[1];
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float df;
+    uint16_t db;
+    const Q8Codes c = warp_quantize_q8_0(v, df, db);
+    if (!live) return;
+    *reinterpret_cast<uint2*>(qs + i * 8) = c.q;
+    if (!(i & 3)) d[i >> 2] = db;
+}
+
+extern "C" int ggb_quantize_q8_K(const float* x, int8_t* qs, float* d, int16_t* bsums, int64_t k, int m, void* stream) {
+    if (k < 0 || (k % 256) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_quantize_q8_K: k=%lld must be a multiple of 256", (long long)k);
+    const int64_t nb = k / 256 * m;
+    if (nb == 0) return GGB_OK;
+    if (!x || !qs || !d || !bsums) GGB_FAIL(GGB_ERR_ARG, "ggb_quantize_q8_K: null pointer");
+    quantize_q8_K_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, qs, d, bsums, nb);
+    GGB_CHECK_LAUNCH("ggb_quantize_q8_K");
+    return GGB_OK;
+}
+
+extern "C" int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m, void* stream) {
+    if (k < 0 || (k % 32) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_quantize_q8_0: k=%lld must be a multiple of 32", (long long)k);
+    const int64_t n8 = k / 8 * m;
+    if (n8 == 0) return GGB_OK;
+    if (!x || !qs || !d) GGB_FAIL(GGB_ERR_ARG, "ggb_quantize_q8_0: null pointer");
+    quantize_q8_0_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, qs, d, n8);
+    GGB_CHECK_LAUNCH("ggb_quantize_q8_0");
+    return GGB_OK;
+}
+
+// ------------------------------------------------------------------ rms_norm (+gain): one CTA per row
+// squares in f32, sum in f64 (as ggml's ggml_float accumulator), scale = 1/sqrtf(mean+eps) in f32.
+__global__ void rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int64_t k, float eps) {
+    __shared__ double red[32];
+    const float* xr = x + (int64_t)blockIdx.x * k;
+    float* yr = y + (int64_t)blockIdx.x * k;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) { const float v = xr[i]; s += (double)__fmul_rn(v, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float mean = (float)(red[0] / (double)k);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(mean + eps));
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const float v = __fmul_rn(xr[i], scale);
+        yr[i] = w ? __fmul_rn(v, w[i]) : v;
+    }
+}
+
+extern "C" int ggb_rms_norm(const float* x, const float* w, float* y, int64_t k, int m, float eps, void* stream) {
+    if (k <= 0 || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_rms_norm: bad shape");
+    if (m == 0) return GGB_OK;
+    if (!x || !y) GGB_FAIL(GGB_ERR_ARG, "ggb_rms_norm: null pointer");
+    rms_norm_kernel<<<m, 512, 0, (cudaStream_t)stream>>>(x, w, y, k, eps);
+    GGB_CHECK_LAUNCH("ggb_rms_norm");
+    return GGB_OK;
+}
+
+__global__ void swiglu_kernel(const float* __restrict__ g, const float* __restrict__ u, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = silu_mul_ref(g[i], u[i]);
+}
+extern "C" int ggb_swiglu(const float* g, const float* u, float* out, int64_t n, void* stream) {
+    if (n < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_swiglu: negative size");
+    if (n == 0) return GGB_OK;
+    if (!g || !u || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_swiglu: null pointer");
+    swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, u, out, n);
+    GGB_CHECK_LAUNCH("ggb_swiglu");
+    return GGB_OK;
+}
+
+// ------------------------------------------------------------------ argmax (first index of the maximum), single CTA
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__global__ void argmax_kernel(const float* __restrict__ x, int64_t n, int32_t* __restrict__ out) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float v = -FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) argmax_combine(v, idx, x[i], (int)i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -FLT_MAX;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+        if (threadIdx.x == 0) *out = idx;
+    }
+}
+extern "C" int ggb_argmax(const float* x, int64_t n, int32_t* out_idx, void* stream) {
+    if (n <= 0 || !x || !out_idx) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax: bad argument");
+    argmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out_idx);
+    GGB_CHECK_LAUNCH("ggb_argmax");
+    return GGB_OK;
+}
+
+// ------------------------------------------------------------------ greedy sampler tail: reduce GEMV partials, emit token,
+// advance position/step, gather next embedding row.  One CTA.
+__global__ void argmax_next_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int n_part,
+                                   int32_t* tok, int32_t* pos, int32_t* step, int32_t* out_tokens, int32_t out_cap) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    pdl_wait();
+    float v = -FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) argmax_combine(v, idx, part_val[i], part_idx[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -FLT_MAX;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+        if (threadIdx.x == 0) {
+            *tok = idx;
+            const int s = *step;
+            if (s < out_cap) out_tokens[s] = idx;
+            *step = s + 1;
+            *pos = *pos + 1;
+        }
+    }
+}
+
+extern "C" int ggb_argmax_next(const float* part_val, const int32_t* part_idx, int n_part, int32_t* tok_dev,
+                               int32_t* pos_dev, int32_t* step_dev, int32_t* out_tokens, int32_t out_cap,
+                               int emb_type, const void* token_embd, int64_t k, float* x, void* stream) {
+    if (!part_val || !part_idx || n_part <= 0 || !tok_dev || !pos_dev || !step_dev || !out_tokens)
+        GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_next: bad argument");
+    argmax_next_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(part_val, part_idx, n_part, tok_dev, pos_dev, step_dev, out_tokens, out_cap);
+    GGB_CHECK_LAUNCH("ggb_argmax_next");
+    if (token_embd) return ggb_embed_row(emb_type, token_embd, k, tok_dev, x, stream);
+    return GGB_OK;
+}

@@ -1,0 +1,371 @@
+"""Decode engine: GGUF file -> HBM-resident tile-SoA weights -> CUDA-graph-replayed decode steps.
+
+Replaces the model-execution core of the reference's backend process (`/app/llama-server -m MODEL -c CTX
+-ngl NGL`, /root/reference/scripts/start.sh:473-480).  PyTorch is used for device memory, streams and graph
+capture only; every arithmetic operation is a kernel of libggufb200.so reached through cabi.py.
+
+Per decoded token the engine enqueues, per layer, five launches (see csrc/gemv.cu):
+    QKV   : rms_norm*attn_norm -> Q8_K -> {Wq,Wk,Wv} GEMV -> RoPE(q,k) -> f16 KV-cache write
+    ATTN  : 8-CTA cluster per head, two-pass softmax over the cache through distributed shared memory
+    O     : Q8_K(attn) -> Wo GEMV -> + residual
+    GATEUP: rms_norm*ffn_norm -> Q8_K -> {Wgate,Wup} GEMV -> silu(g)*u
+    DOWN  : Q8_K(h) -> Wdown GEMV -> + residual
+then  HEAD: rms_norm*output_norm -> Q8_K -> Woutput GEMV -> arg-max partials -> token, pos+1, next embedding.
+Position, token and step counters live in device memory, so one captured graph serves every step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import cabi
+from . import gguf_reader as G
+
+QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q6_K, G.GGML_Q8_0)
+
+
+@dataclass
+class HParams:
+    n_layer: int
+    d: int
+    ff: int
+    n_head: int
+    n_kv: int
+    head_dim: int
+    n_rot: int
+    eps: float
+    rope_base: float
+    vocab: int
+    ctx_train: int
+
+    @classmethod
+    def from_gguf(cls, f: G.GGUFFile) -> "HParams":
+        arch = f.get("general.architecture")
+        if arch != "llama":
+            raise G.GGUFError(f"unsupported architecture {arch!r} (this engine implements the llama graph)")
+        a = lambda k, d=None: f.get(f"{arch}.{k}", d)  # noqa: E731
+        d = int(a("embedding_length"))
+        n_head = int(a("attention.head_count"))
+        hd = int(a("attention.key_length", d // n_head))
+        emb = f.tensors["token_embd.weight"]
+        return cls(n_layer=int(a("block_count")), d=d, ff=int(a("feed_forward_length")), n_head=n_head,
+                   n_kv=int(a("attention.head_count_kv", n_head)), head_dim=hd, n_rot=int(a("rope.dimension_count", hd)),
+                   eps=float(a("attention.layer_norm_rms_epsilon", 1e-5)), rope_base=float(a("rope.freq_base", 10000.0)),
+                   vocab=int(emb.ne[1]), ctx_train=int(a("context_length", 4096)))
+
+
+def rope_table(n_ctx: int, n_rot: int, base: float, freq_factors: np.ndarray | None = None) -> np.ndarray:
+    """[n_ctx, n_rot/2, 2] (cos, sin) in f32, the way ggml's rope cache is filled [UPSTREAM-MEM: ggml-cpu/ops.cpp]:
+    theta_0 = pos, theta_{i+1} = theta_i * base^(-2/n_rot), every step rounded to f32."""
+    scale = np.float32(np.power(np.float64(np.float32(base)), np.float64(np.float32(-2.0) / np.float32(n_rot))))
+    theta = np.empty((n_ctx, n_rot // 2), dtype=np.float32)
+    theta[:, 0] = np.arange(n_ctx, dtype=np.float32)
+    for i in range(1, n_rot // 2):
+        theta[:, i] = theta[:, i - 1] * scale
+    if freq_factors is not None:
+        theta = (theta / freq_factors.astype(np.float32)[None, :]).astype(np.float32)
+    t64 = theta.astype(np.float64)
+    return np.stack([np.cos(t64), np.sin(t64)], axis=-1).astype(np.float32)
+
+
+class Weight:
+    """One 2-D weight in HBM, tile-SoA layout."""
+
+    def __init__(self, tensor, qtype: int, rows: int, k: int):
+        self.t, self.type, self.rows, self.k = tensor, qtype, rows, k
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+
+class Engine:
+    def __init__(self, path: str, n_ctx: int = 4096, device: int = 0, use_graph: bool = True, use_pdl: bool = True,
+                 max_new: int = 65536, verbose: bool = False):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise cabi.GGBError("no CUDA device: the GGUF engine has no CPU fallback")
+        self.torch = torch
+        self.lib = cabi.lib()
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        self.use_graph, self.use_pdl = use_graph, int(bool(use_pdl))
+        self.file = G.GGUFFile(path)
+        self.hp = HParams.from_gguf(self.file)
+        self.n_ctx = int(n_ctx)
+        self.max_new = max_new
+        self.stream = torch.cuda.Stream(device=self.dev)
+        t0 = time.time()
+        self._load_weights()
+        self.load_seconds = time.time() - t0
+        self._alloc_state()
+        self._graphs = {}
+        if verbose:
+            print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
+
+    # ------------------------------------------------------------------ loading
+    def _sptr(self) -> int:
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _upload(self, name: str):
+        torch = self.torch
+        raw = self.file.data(name)
+        return torch.from_numpy(np.asarray(raw)).to(self.dev, non_blocking=False)
+
+    def _load_matrix(self, name: str) -> Weight:
+        torch = self.torch
+        ti = self.file.tensors[name]
+        if ti.ggml_type not in QUANT_TYPES:
+            raise G.GGUFError(f"{name}: tensor type {ti.type_name} is not supported by the GEMV path (supported: Q4_K, Q6_K, Q8_0)")
+        k, rows = ti.ne[0], ti.ne[1]
+        if k % 256:
+            raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
+        canon = self._upload(name)
+        stride = self.lib.ggb_repacked_row_stride(ti.ggml_type, k)
+        dst = torch.empty(rows * stride, dtype=torch.uint8, device=self.dev)
+        cabi.check(self.lib.ggb_repack(ti.ggml_type, canon.data_ptr(), dst.data_ptr(), rows, k, self._sptr()), f"repack {name}")
+        torch.cuda.current_stream().synchronize()
+        del canon
+        self.weight_bytes += ti.nbytes
+        return Weight(dst, ti.ggml_type, rows, k)
+
+    def _load_f32(self, name: str):
+        torch = self.torch
+        ti = self.file.tensors[name]
+        raw = self._upload(name)
+        out = torch.empty(ti.n_elements, dtype=torch.float32, device=self.dev)
+        cabi.check(self.lib.ggb_dequant(ti.ggml_type, raw.data_ptr(), out.data_ptr(), ti.n_elements, self._sptr()), f"dequant {name}")
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def _load_weights(self):
+        hp, f = self.hp, self.file
+        self.weight_bytes = 0
+        emb = f.tensors["token_embd.weight"]
+        self.emb_type = emb.ggml_type
+        self.emb_canon = self._upload("token_embd.weight")  # canonical layout: get_rows reads one row
+        self.layers = []
+        for i in range(hp.n_layer):
+            p = f"blk.{i}."
+            self.layers.append({
+                "attn_norm": self._load_f32(p + "attn_norm.weight"),
+                "wq": self._load_matrix(p + "attn_q.weight"),
+                "wk": self._load_matrix(p + "attn_k.weight"),
+                "wv": self._load_matrix(p + "attn_v.weight"),
+                "wo": self._load_matrix(p + "attn_output.weight"),
+                "ffn_norm": self._load_f32(p + "ffn_norm.weight"),
+                "wg": self._load_matrix(p + "ffn_gate.weight"),
+                "wu": self._load_matrix(p + "ffn_up.weight"),
+                "wd": self._load_matrix(p + "ffn_down.weight"),
+            })
+        self.out_norm = self._load_f32("output_norm.weight")
+        out_name = "output.weight" if "output.weight" in f.tensors else "token_embd.weight"
+        self.w_out = self._load_matrix(out_name)
+        ff = None
+        if "rope_freqs.weight" in f.tensors:
+            ff = self._load_f32("rope_freqs.weight").cpu().numpy()
+        self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
+
+    # ------------------------------------------------------------------ state
+    def _alloc_state(self):
+        torch, hp = self.torch, self.hp
+        dev = self.dev
+        kvd = hp.n_kv * hp.head_dim
+        self.kc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
+        self.vc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
+        f32 = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
+        self.x = f32(hp.d)
+        self.q = f32(hp.n_head * hp.head_dim)
+        self.attn = f32(hp.n_head * hp.head_dim)
+        self.h = f32(hp.ff)
+        self.logits = f32(hp.vocab)
+        self.attn_ws = torch.zeros(self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim), dtype=torch.uint8, device=dev)
+        i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)  # noqa: E731
+        self.tok_dev, self.pos_dev, self.step_dev = i32(1), i32(1), i32(1)
+        self.out_tokens = i32(self.max_new)
+        # arg-max partials: one per GEMV CTA
+        a = self._head_args()
+        self.n_part = self.lib.ggb_gemv_grid(C.byref(a))
+        self.part_val, self.part_idx = f32(self.n_part), i32(self.n_part)
+        self.host_i32 = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    # ------------------------------------------------------------------ launch descriptions
+    def _head_args(self):
+        hp = self.hp
+        return cabi.make_gemv_args(
+            [(self.w_out.ptr, self.w_out.type, self.w_out.rows, self.logits.data_ptr())], hp.d, self.x.data_ptr(),
+            prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ARGMAX, norm_w=self.out_norm.data_ptr(), eps=hp.eps,
+            use_pdl=self.use_pdl, part_val=getattr(self, "part_val", self.x).data_ptr(),
+            part_idx=getattr(self, "part_idx", self.x).data_ptr())
+
+    def _build_args(self):
+        hp = self.hp
+        self._layer_args = []
+        for i, L in enumerate(self.layers):
+            qkv = cabi.make_gemv_args(
+                [(L["wq"].ptr, L["wq"].type, L["wq"].rows, self.q.data_ptr()),
+                 (L["wk"].ptr, L["wk"].type, L["wk"].rows, 0),
+                 (L["wv"].ptr, L["wv"].type, L["wv"].rows, 0)],
+                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ROPE_KV,
+                norm_w=L["attn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, pos_dev=self.pos_dev.data_ptr(),
+                rope_tab=self.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
+                kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
+            o = cabi.make_gemv_args(
+                [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.x.data_ptr())], L["wo"].k, self.attn.data_ptr(),
+                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+            gu = cabi.make_gemv_args(
+                [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
+                 (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
+                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_SWIGLU,
+                norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
+            dn = cabi.make_gemv_args(
+                [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.x.data_ptr())], L["wd"].k, self.h.data_ptr(),
+                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+            self._layer_args.append((qkv, o, gu, dn))
+        self._head = self._head_args()
+
+    def launches_per_step(self) -> int:
+        """kernels of libggufb200 launched by one decode step (layers + head)."""
+        return self.hp.n_layer * 5 + 3
+
+    # ------------------------------------------------------------------ enqueue
+    def _enqueue_embed(self, s: int):
+        cabi.check(self.lib.ggb_embed_row(self.emb_type, self.emb_canon.data_ptr(), self.hp.d, self.tok_dev.data_ptr(),
+                                          self.x.data_ptr(), s), "embed_row")
+
+    def _enqueue_layers(self, s: int):
+        hp, lib = self.hp, self.lib
+        for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
+            cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
+            cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                                           self.pos_dev.data_ptr(), hp.n_head, hp.n_kv, hp.head_dim, self.n_ctx,
+                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self.use_pdl, s), "attn_decode")
+            cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
+            cabi.check(lib.ggb_gemv(C.byref(gu), s), "gemv gate/up")
+            cabi.check(lib.ggb_gemv(C.byref(dn), s), "gemv down")
+
+    def _enqueue_head(self, s: int):
+        lib = self.lib
+        cabi.check(lib.ggb_gemv(C.byref(self._head), s), "gemv head")
+        cabi.check(lib.ggb_argmax_next(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
+                                       self.tok_dev.data_ptr(), self.pos_dev.data_ptr(), self.step_dev.data_ptr(),
+                                       self.out_tokens.data_ptr(), self.max_new, self.emb_type,
+                                       self.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
+
+    def _run(self, kind: str):
+        """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head)."""
+        torch = self.torch
+        if not hasattr(self, "_layer_args"):
+            self._build_args()
+
+        def body(s):
+            if kind != "decode":
+                self._enqueue_embed(s)
+            self._enqueue_layers(s)
+            if kind != "prompt":
+                self._enqueue_head(s)
+
+        if not self.use_graph:
+            body(self.stream.cuda_stream)
+            return
+        g = self._graphs.get(kind)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                body(torch.cuda.current_stream().cuda_stream)
+            self._graphs[kind] = g
+            return self._run_graph_after_capture(g)
+        g.replay()
+
+    def _run_graph_after_capture(self, g):
+        g.replay()  # capture does not execute; run it once for real
+
+    # ------------------------------------------------------------------ public API
+    def reset(self):
+        with self.torch.cuda.stream(self.stream):
+            self.pos_dev.zero_()
+            self.step_dev.zero_()
+
+    def _set_tok_pos(self, tok: int, pos: int):
+        self.host_i32[0] = tok
+        self.host_i32[1] = pos
+        self.tok_dev.copy_(self.host_i32[0:1], non_blocking=True)
+        self.pos_dev.copy_(self.host_i32[1:2], non_blocking=True)
+
+    def warmup(self):
+        """Run every graph once (sets kernel attributes, captures graphs), then clear the state."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            graph = self.use_graph
+            self.use_graph = False
+            self._set_tok_pos(0, 0)
+            self._run("prompt_last")
+            self.stream.synchronize()
+            self.use_graph = graph
+            if graph:
+                for kind in ("prompt", "prompt_last", "decode"):
+                    self._set_tok_pos(0, 0)
+                    self._run(kind)
+                self.stream.synchronize()
+        self.reset()
+
+    def prefill(self, tokens: list[int], start_pos: int = 0):
+        """Feed the prompt (v1: token by token through the decode kernels); the last token also runs the head,
+        which emits the first generated token and leaves pos = start_pos + len(tokens)."""
+        if not tokens:
+            raise ValueError("empty prompt")
+        if start_pos + len(tokens) >= self.n_ctx:
+            raise ValueError(f"prompt of {len(tokens)} tokens does not fit the context ({self.n_ctx})")
+        with self.torch.cuda.stream(self.stream):
+            for i, t in enumerate(tokens):
+                self._set_tok_pos(int(t), start_pos + i)
+                self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
+                self.stream.synchronize()  # host_i32 is reused for the next token
+
+    def decode(self, n_steps: int):
+        """Enqueue n decode steps (no host synchronisation); tokens land in out_tokens."""
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(n_steps):
+                self._run("decode")
+
+    def read_last_token(self) -> int:
+        """Device -> pinned host read of the newest token (what a streaming server does per step)."""
+        with self.torch.cuda.stream(self.stream):
+            self.host_tok.copy_(self.tok_dev, non_blocking=True)
+        self.stream.synchronize()
+        return int(self.host_tok[0])
+
+    def tokens(self, n: int) -> list[int]:
+        self.stream.synchronize()
+        return self.out_tokens[:n].cpu().tolist()
+
+    def generate(self, prompt: list[int], n_new: int, stream_cb=None) -> list[int]:
+        """Greedy generation.  With stream_cb the newest token is read back after every step (streaming);
+        otherwise all steps are enqueued back-to-back and read once."""
+        if len(prompt) + n_new >= self.n_ctx:
+            raise ValueError("prompt + n_new exceeds the context window")
+        self.reset()
+        self.prefill(prompt)
+        if stream_cb is None:
+            self.decode(n_new - 1)
+            return self.tokens(n_new)
+        out = [self.read_last_token()]
+        stream_cb(out[-1])
+        for _ in range(n_new - 1):
+            self.decode(1)
+            out.append(self.read_last_token())
+            stream_cb(out[-1])
+        return out
+
+    def last_logits(self) -> np.ndarray:
+        self.stream.synchronize()
+        return self.logits.cpu().numpy()
+
+    def close(self):
+        self._graphs.clear()
+        self.file.close()

@@ -515,3 +515,222 @@ int64_t gref_argmax(const float *x, int64_t n) {
     for (int64_t i = 1; i < n; i++) if (x[i] > x[best]) best = i;
     return best;
 }
+
+/* ==================================================================================================
+ * ORDER-INDEPENDENT ("canon") VARIANTS
+ *
+ * ggml's f32 accumulation order is an implementation detail that differs between its own generic, AVX2,
+ * AVX-512 and NEON kernels, so no single order is "the" reference.  The functions above restate the generic
+ * order.  The functions below compute THE SAME integer dot products and the same per-unit f32 terms but add
+ * them in f64, which makes the result independent of summation order (up to a 2^-53 effect that survives the
+ * final rounding to f32 with probability ~1e-8 per output).  The CUDA kernels implement exactly this
+ * definition, so GPU and oracle agree bit-for-bit and greedy-token parity is decided by logic, not by
+ * rounding luck.  tests/ additionally bound canon against the generic order (<= 1e-5 relative per matvec).
+ *
+ * exp(): libm and CUDA expf differ by ulps, so canon uses gref_exp_ref(), a fixed sequence of IEEE
+ * operations (rint, fma, multiply by a power of two) that both sides evaluate identically.
+ * ================================================================================================== */
+
+float gref_exp_ref(float x) {
+    if (x < -103.0f) return 0.0f;
+    if (x > 88.0f) x = 88.0f;
+    const float n = rintf(x * 1.44269504088896341f);
+    float r = fmaf(n, -0.693145751953125f, x);
+    r = fmaf(n, -1.42860682030941723212e-6f, r);
+    float p = 1.0f / 5040.0f;
+    p = fmaf(p, r, 1.0f / 720.0f);
+    p = fmaf(p, r, 1.0f / 120.0f);
+    p = fmaf(p, r, 1.0f / 24.0f);
+    p = fmaf(p, r, 1.0f / 6.0f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    int ni = (int)n;
+    if (ni < -126) { p *= 5.42101086242752217e-20f; /* 2^-64, exact */ ni += 64; }
+    uint32_t bits = (uint32_t)(ni + 127) << 23;
+    float s;
+    memcpy(&s, &bits, 4);
+    return p * s;
+}
+
+/* per "unit" (64 consecutive elements: a pair of 32-element sub-blocks) one f32 term, summed in f64 */
+float gref_vec_dot_q4_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+    const blk_q4_K *w = (const blk_q4_K *)vw;
+    const blk_q8_K *a = (const blk_q8_K *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK_K; b++) {
+        const float d = gref_fp16_to_fp32(w[b].d) * a[b].d, dmin = gref_fp16_to_fp32(w[b].dmin) * a[b].d;
+        for (int g = 0; g < 4; g++) {
+            const uint8_t *q = w[b].qs + 32 * g;
+            const int8_t *x = a[b].qs + 64 * g;
+            int32_t dlo = 0, dhi = 0;
+            for (int l = 0; l < 32; l++) { dlo += (q[l] & 0xF) * x[l]; dhi += (q[l] >> 4) * x[32 + l]; }
+            uint8_t s0, m0, s1, m1;
+            k4_scale_min(2 * g, w[b].scales, &s0, &m0);
+            k4_scale_min(2 * g + 1, w[b].scales, &s1, &m1);
+            const int32_t isum = s0 * dlo + s1 * dhi;
+            const int32_t msum = m0 * (a[b].bsums[4 * g] + a[b].bsums[4 * g + 1]) + m1 * (a[b].bsums[4 * g + 2] + a[b].bsums[4 * g + 3]);
+            const float term = d * (float)isum - dmin * (float)msum; /* -ffp-contract=off: mul, mul, sub */
+            acc += (double)term;
+        }
+    }
+    return (float)acc;
+}
+
+float gref_vec_dot_q5_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+    const blk_q5_K *w = (const blk_q5_K *)vw;
+    const blk_q8_K *a = (const blk_q8_K *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK_K; b++) {
+        const float d = gref_fp16_to_fp32(w[b].d) * a[b].d, dmin = gref_fp16_to_fp32(w[b].dmin) * a[b].d;
+        for (int g = 0; g < 4; g++) {
+            const uint8_t *q = w[b].qs + 32 * g, *qh = w[b].qh;
+            const int8_t *x = a[b].qs + 64 * g;
+            int32_t dlo = 0, dhi = 0;
+            for (int l = 0; l < 32; l++) {
+                dlo += ((q[l] & 0xF) + (((qh[l] >> (2 * g)) & 1) << 4)) * x[l];
+                dhi += ((q[l] >> 4) + (((qh[l] >> (2 * g + 1)) & 1) << 4)) * x[32 + l];
+            }
+            uint8_t s0, m0, s1, m1;
+            k4_scale_min(2 * g, w[b].scales, &s0, &m0);
+            k4_scale_min(2 * g + 1, w[b].scales, &s1, &m1);
+            const int32_t isum = s0 * dlo + s1 * dhi;
+            const int32_t msum = m0 * (a[b].bsums[4 * g] + a[b].bsums[4 * g + 1]) + m1 * (a[b].bsums[4 * g + 2] + a[b].bsums[4 * g + 3]);
+            const float term = d * (float)isum - dmin * (float)msum;
+            acc += (double)term;
+        }
+    }
+    return (float)acc;
+}
+
+/* unit = (half n, column t): elements 128n + 32r + 16t + (0..15), r = 0..3 */
+float gref_vec_dot_q6_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+    const blk_q6_K *w = (const blk_q6_K *)vw;
+    const blk_q8_K *a = (const blk_q8_K *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK_K; b++) {
+        const float d = gref_fp16_to_fp32(w[b].d) * a[b].d;
+        for (int n = 0; n < 2; n++)
+            for (int t = 0; t < 2; t++) {
+                const uint8_t *ql = w[b].ql + 64 * n, *qh = w[b].qh + 32 * n;
+                int32_t isum = 0;
+                for (int r = 0; r < 4; r++) {
+                    int32_t v = 0;
+                    for (int i = 0; i < 16; i++) {
+                        const int l = 16 * t + i;
+                        const uint8_t qb = ql[32 * (r & 1) + l];
+                        const int lo = (r & 2) ? (qb >> 4) : (qb & 0xF);
+                        const int q = (lo | (((qh[l] >> (2 * r)) & 3) << 4)) - 32;
+                        v += q * a[b].qs[128 * n + 32 * r + l];
+                    }
+                    isum += (int32_t)w[b].scales[8 * n + 2 * r + t] * v;
+                }
+                acc += (double)(d * (float)isum);
+            }
+    }
+    return (float)acc;
+}
+
+float gref_vec_dot_q8_0_q8_0_canon(int64_t k, const void *vw, const void *va) {
+    const blk_q8_0 *w = (const blk_q8_0 *)vw;
+    const blk_q8_0 *a = (const blk_q8_0 *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        int32_t s = 0;
+        for (int j = 0; j < QK8_0; j++) s += w[b].qs[j] * a[b].qs[j];
+        acc += (double)((float)s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d)));
+    }
+    return (float)acc;
+}
+
+/* mode 0 = generic ggml order, 1 = canon */
+int gref_matmul_mode(int type, const void *W, int64_t rows, int64_t k, const float *X, int64_t m, float *Y, int nthreads, int mode) {
+    if (!mode) return gref_matmul(type, W, rows, k, X, m, Y, nthreads);
+    const int64_t wrow = gref_row_bytes(type, k);
+    const int64_t arow = gref_act_row_bytes(type, k);
+    if (wrow <= 0 || type == GREF_F32 || type == GREF_F16) return -1;
+    uint8_t *act = (uint8_t *)malloc((size_t)(arow * m));
+    if (!act) return -2;
+    for (int64_t j = 0; j < m; j++) gref_quantize_act(type, X + j * k, act + j * arow, k);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; r++) {
+        const uint8_t *wr = (const uint8_t *)W + r * wrow;
+        for (int64_t j = 0; j < m; j++) {
+            const void *ar = act + j * arow;
+            float v;
+            switch (type) {
+                case GREF_Q4_K: v = gref_vec_dot_q4_K_q8_K_canon(k, wr, ar); break;
+                case GREF_Q5_K: v = gref_vec_dot_q5_K_q8_K_canon(k, wr, ar); break;
+                case GREF_Q6_K: v = gref_vec_dot_q6_K_q8_K_canon(k, wr, ar); break;
+                default: v = gref_vec_dot_q8_0_q8_0_canon(k, wr, ar); break;
+            }
+            Y[j * rows + r] = v;
+        }
+    }
+    free(act);
+    return 0;
+}
+
+void gref_swiglu_canon(const float *g, const float *u, float *out, int64_t n) {
+    for (int64_t i = 0; i < n; i++) out[i] = (g[i] / (1.0f + gref_exp_ref(-g[i]))) * u[i];
+}
+
+/* rope table through f64 cos/sin rounded once to f32 (what the engine's host code builds with numpy) */
+void gref_rope_table_canon(int32_t pos, int n_rot, float freq_base, const float *freq_factors, float *out) {
+    const float theta_scale = (float)pow((double)freq_base, (double)(-2.0f / (float)n_rot));
+    float theta = (float)pos;
+    for (int i = 0; i < n_rot / 2; i++) {
+        const float t = freq_factors ? theta / freq_factors[i] : theta;
+        out[2 * i] = (float)cos((double)t);
+        out[2 * i + 1] = (float)sin((double)t);
+        theta *= theta_scale;
+    }
+}
+
+void gref_rope_apply(float *x, int n_heads, int head_dim, int n_rot, const float *tab) {
+    for (int h = 0; h < n_heads; h++) {
+        float *v = x + (int64_t)h * head_dim;
+        for (int i = 0; i < n_rot / 2; i++) {
+            const float c = tab[2 * i], s = tab[2 * i + 1];
+            const float x0 = v[2 * i], x1 = v[2 * i + 1];
+            v[2 * i] = x0 * c - x1 * s;
+            v[2 * i + 1] = x0 * s + x1 * c;
+        }
+    }
+}
+
+/* attention, canon: s_p = (float)(sum_f64 k.q) * scale ; M = max ; e_p = exp_ref(s_p - M) ;
+ * out_d = (float)( sum_f64 fl(e_p * v_pd) / sum_f64 e_p )   (normalised at the end, like flash attention) */
+void gref_attn_decode_canon(const float *q, const uint16_t *kc, const uint16_t *vc, float *out,
+                            int n_head, int n_kv, int hd, int n_pos, int64_t kv_stride) {
+    const int group = n_head / n_kv;
+    const float scale = 1.0f / sqrtf((float)hd);
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < n_head; h++) {
+        const int kvh = h / group;
+        float *sc = (float *)malloc(sizeof(float) * (size_t)n_pos);
+        float *qh = (float *)malloc(sizeof(float) * (size_t)hd);
+        double *o = (double *)calloc((size_t)hd, sizeof(double));
+        for (int i = 0; i < hd; i++) qh[i] = gref_fp16_to_fp32(gref_fp32_to_fp16(q[(int64_t)h * hd + i]));
+        float mx = -INFINITY;
+        for (int p = 0; p < n_pos; p++) {
+            const uint16_t *kr = kc + p * kv_stride + (int64_t)kvh * hd;
+            double s = 0.0;
+            for (int i = 0; i < hd; i++) s += (double)(gref_fp16_to_fp32(kr[i]) * qh[i]);
+            sc[p] = (float)s * scale;
+            if (sc[p] > mx) mx = sc[p];
+        }
+        double sum = 0.0;
+        for (int p = 0; p < n_pos; p++) {
+            const float e = gref_exp_ref(sc[p] - mx);
+            sum += (double)e;
+            const uint16_t *vr = vc + p * kv_stride + (int64_t)kvh * hd;
+            for (int i = 0; i < hd; i++) o[i] += (double)(e * gref_fp16_to_fp32(vr[i]));
+        }
+        for (int i = 0; i < hd; i++) out[(int64_t)h * hd + i] = (float)(o[i] / sum);
+        free(sc); free(qh); free(o);
+    }
+}

@@ -61,6 +61,13 @@ def lib() -> C.CDLL:
         L.gref_fp32_to_fp16_row.argtypes = [vp, vp, i64]; L.gref_fp32_to_fp16_row.restype = None
         L.gref_fp16_to_fp32_row.argtypes = [vp, vp, i64]; L.gref_fp16_to_fp32_row.restype = None
         L.gref_num_threads.argtypes = []; L.gref_num_threads.restype = i32
+        # order-independent ("canon") variants, see ggml_ref.c
+        L.gref_matmul_mode.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32, i32]; L.gref_matmul_mode.restype = i32
+        L.gref_exp_ref.argtypes = [f32]; L.gref_exp_ref.restype = f32
+        L.gref_swiglu_canon.argtypes = [vp, vp, vp, i64]; L.gref_swiglu_canon.restype = None
+        L.gref_rope_table_canon.argtypes = [i32, i32, f32, vp, vp]; L.gref_rope_table_canon.restype = None
+        L.gref_rope_apply.argtypes = [vp, i32, i32, i32, vp]; L.gref_rope_apply.restype = None
+        L.gref_attn_decode_canon.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i64]; L.gref_attn_decode_canon.restype = None
         _lib = L
     return _lib
 
@@ -111,7 +118,10 @@ def quantize_q8_0(x: np.ndarray) -> np.ndarray:
     return out
 
 
-def matmul(qtype: int, w_raw: np.ndarray, rows: int, k: int, x: np.ndarray, nthreads: int = 0) -> np.ndarray:
+GGML, CANON = "ggml", "canon"  # f32 accumulation in ggml's generic order | order-independent f64 accumulation
+
+
+def matmul(qtype: int, w_raw: np.ndarray, rows: int, k: int, x: np.ndarray, nthreads: int = 0, mode: str = GGML) -> np.ndarray:
     """Y[m, rows] = W[rows, k] . X[m, k] through activation quantisation + integer vec_dot (CPU mul_mat)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     m = 1 if x.ndim == 1 else x.shape[0]
@@ -119,7 +129,7 @@ def matmul(qtype: int, w_raw: np.ndarray, rows: int, k: int, x: np.ndarray, nthr
     w_raw = np.ascontiguousarray(w_raw, dtype=np.uint8).reshape(-1)
     assert w_raw.size == rows * row_bytes(qtype, k)
     y = np.empty((m, rows), dtype=np.float32)
-    rc = lib().gref_matmul(qtype, _p(w_raw), rows, k, _p(x), m, _p(y), nthreads)
+    rc = lib().gref_matmul_mode(qtype, _p(w_raw), rows, k, _p(x), m, _p(y), nthreads, 1 if mode == CANON else 0)
     assert rc == 0
     return y[0] if x.ndim == 1 else y
 
@@ -147,11 +157,29 @@ def rope_table(pos: int, n_rot: int, freq_base: float, freq_factors: np.ndarray 
     return out
 
 
-def swiglu(g: np.ndarray, u: np.ndarray) -> np.ndarray:
+def swiglu(g: np.ndarray, u: np.ndarray, mode: str = GGML) -> np.ndarray:
     g = np.ascontiguousarray(g, dtype=np.float32); u = np.ascontiguousarray(u, dtype=np.float32)
     out = np.empty_like(g)
-    lib().gref_swiglu(_p(g), _p(u), _p(out), g.size)
+    (lib().gref_swiglu_canon if mode == CANON else lib().gref_swiglu)(_p(g), _p(u), _p(out), g.size)
     return out
+
+
+def exp_ref(x: float) -> float:
+    return float(lib().gref_exp_ref(float(np.float32(x))))
+
+
+def rope_table_canon(pos: int, n_rot: int, freq_base: float, freq_factors: np.ndarray | None = None) -> np.ndarray:
+    out = np.empty((n_rot // 2, 2), dtype=np.float32)
+    ff = _p(np.ascontiguousarray(freq_factors, dtype=np.float32)) if freq_factors is not None else None
+    lib().gref_rope_table_canon(pos, n_rot, freq_base, ff, _p(out))
+    return out
+
+
+def rope_apply(x: np.ndarray, n_heads: int, head_dim: int, n_rot: int, tab: np.ndarray) -> np.ndarray:
+    y = np.ascontiguousarray(x, dtype=np.float32).copy()
+    tab = np.ascontiguousarray(tab, dtype=np.float32)
+    lib().gref_rope_apply(_p(y), n_heads, head_dim, n_rot, _p(tab))
+    return y
 
 
 def fp32_to_fp16(x: np.ndarray) -> np.ndarray:
@@ -161,12 +189,14 @@ def fp32_to_fp16(x: np.ndarray) -> np.ndarray:
     return out
 
 
-def attn_decode(q: np.ndarray, kc: np.ndarray, vc: np.ndarray, n_head: int, n_kv: int, hd: int, n_pos: int) -> np.ndarray:
+def attn_decode(q: np.ndarray, kc: np.ndarray, vc: np.ndarray, n_head: int, n_kv: int, hd: int, n_pos: int,
+                mode: str = GGML) -> np.ndarray:
     """q f32 [n_head*hd]; kc, vc uint16 (f16 bits) [ctx, n_kv*hd]; attends positions [0, n_pos)."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     assert kc.dtype == np.uint16 and vc.dtype == np.uint16 and kc.flags.c_contiguous and vc.flags.c_contiguous
     out = np.empty(n_head * hd, dtype=np.float32)
-    lib().gref_attn_decode(_p(q), _p(kc), _p(vc), _p(out), n_head, n_kv, hd, n_pos, n_kv * hd)
+    fn = lib().gref_attn_decode_canon if mode == CANON else lib().gref_attn_decode
+    fn(_p(q), _p(kc), _p(vc), _p(out), n_head, n_kv, hd, n_pos, n_kv * hd)
     return out
 
 
@@ -187,7 +217,13 @@ class OracleLlama:
         logits = Woutput ( rms_norm(x)*output_norm )        (output.weight falls back to token_embd)
     """
 
-    def __init__(self, path: str, n_ctx: int = 512, nthreads: int = 0):
+    def __init__(self, path: str, n_ctx: int = 512, nthreads: int = 0, mode: str = GGML):
+        """mode="ggml": f32 accumulation in ggml's generic order, libm expf/cosf (the restatement of the
+        reference's CPU path).  mode="canon": identical integers and per-unit f32 terms, f64 accumulation,
+        gref_exp_ref, f64-rounded rope table -- the order-independent definition the CUDA kernels implement
+        bit-for-bit (see ggml_ref.c)."""
+        assert mode in (GGML, CANON)
+        self.mode = mode
         from gguf import GGUFReader  # upstream's reader, on purpose (see module docstring)
 
         rd = GGUFReader(path)
@@ -218,6 +254,7 @@ class OracleLlama:
             shape = [int(s) for s in t.shape]  # ne order: ne0 (innermost) first
             self.t[t.name] = (int(t.tensor_type), shape, np.asarray(t.data).reshape(-1).view(np.uint8))
         self.vocab = self.t["token_embd.weight"][1][1]
+        self._norm_cache = {}
         self.freq_factors = None
         if "rope_freqs.weight" in self.t:
             self.freq_factors = self._f32("rope_freqs.weight")
@@ -227,6 +264,11 @@ class OracleLlama:
         qt, shape, raw = self.t[name]
         return dequantize(raw, qt, int(np.prod(shape)))
 
+    def _norm(self, name):
+        if name not in self._norm_cache:
+            self._norm_cache[name] = self._f32(name)
+        return self._norm_cache[name]
+
     def reset(self):
         kvd = self.n_kv * self.hd
         self.kc = np.zeros((self.n_layer, self.n_ctx, kvd), dtype=np.uint16)
@@ -235,37 +277,49 @@ class OracleLlama:
     def _mm(self, name, x):
         qt, shape, raw = self.t[name]
         k, rows = shape[0], shape[1]
-        return matmul(qt, raw, rows, k, x, self.nthreads)
+        return matmul(qt, raw, rows, k, x, self.nthreads, self.mode)
 
     def embed(self, tok: int) -> np.ndarray:
         qt, shape, raw = self.t["token_embd.weight"]
         rb = row_bytes(qt, shape[0])
         return dequantize(raw[tok * rb:(tok + 1) * rb], qt, shape[0])
 
-    def forward(self, tok: int, pos: int, return_hidden: bool = False) -> np.ndarray:
-        assert pos < self.n_ctx
-        x = self.embed(tok)
-        for l in range(self.n_layer):
-            p = f"blk.{l}."
-            h = rms_norm(x, self._f32(p + "attn_norm.weight"), self.eps)
-            q = self._mm(p + "attn_q.weight", h)
-            k = self._mm(p + "attn_k.weight", h)
-            v = self._mm(p + "attn_v.weight", h)
+    def layer(self, l: int, x: np.ndarray, pos: int) -> np.ndarray:
+        """One transformer block on the residual stream x at position pos (writes the KV cache)."""
+        p = f"blk.{l}."
+        h = rms_norm(x, self._norm(p + "attn_norm.weight"), self.eps)
+        q = self._mm(p + "attn_q.weight", h)
+        k = self._mm(p + "attn_k.weight", h)
+        v = self._mm(p + "attn_v.weight", h)
+        if self.mode == CANON:
+            tab = rope_table_canon(pos, self.n_rot, self.freq_base, self.freq_factors)
+            q = rope_apply(q, self.n_head, self.hd, self.n_rot, tab)
+            k = rope_apply(k, self.n_kv, self.hd, self.n_rot, tab)
+        else:
             q = rope_norm(q, self.n_head, self.hd, self.n_rot, pos, self.freq_base, self.freq_factors)
             k = rope_norm(k, self.n_kv, self.hd, self.n_rot, pos, self.freq_base, self.freq_factors)
-            self.kc[l, pos] = fp32_to_fp16(k)
-            self.vc[l, pos] = fp32_to_fp16(v)
-            a = attn_decode(q, self.kc[l], self.vc[l], self.n_head, self.n_kv, self.hd, pos + 1)
-            x = x + self._mm(p + "attn_output.weight", a)
-            h = rms_norm(x, self._f32(p + "ffn_norm.weight"), self.eps)
-            g = self._mm(p + "ffn_gate.weight", h)
-            u = self._mm(p + "ffn_up.weight", h)
-            x = x + self._mm(p + "ffn_down.weight", swiglu(g, u))
-        h = rms_norm(x, self._f32("output_norm.weight"), self.eps)
+        self.kc[l, pos] = fp32_to_fp16(k)
+        self.vc[l, pos] = fp32_to_fp16(v)
+        a = attn_decode(q, self.kc[l], self.vc[l], self.n_head, self.n_kv, self.hd, pos + 1, self.mode)
+        x = x + self._mm(p + "attn_output.weight", a)
+        h = rms_norm(x, self._norm(p + "ffn_norm.weight"), self.eps)
+        g = self._mm(p + "ffn_gate.weight", h)
+        u = self._mm(p + "ffn_up.weight", h)
+        return x + self._mm(p + "ffn_down.weight", swiglu(g, u, self.mode))
+
+    def head(self, x: np.ndarray, return_hidden: bool = False) -> np.ndarray:
+        h = rms_norm(x, self._norm("output_norm.weight"), self.eps)
         if return_hidden:
             return h
         out_name = "output.weight" if "output.weight" in self.t else "token_embd.weight"
         return self._mm(out_name, h)
+
+    def forward(self, tok: int, pos: int, return_hidden: bool = False) -> np.ndarray:
+        assert pos < self.n_ctx
+        x = self.embed(tok)
+        for l in range(self.n_layer):
+            x = self.layer(l, x, pos)
+        return self.head(x, return_hidden)
 
     def greedy(self, prompt: list[int], n_new: int, return_logits: bool = False):
         """Feed the prompt token by token, then generate n_new tokens by argmax."""

@@ -1,0 +1,216 @@
+"""CPU tests of the oracle (oracle/ggml_ref.c + oracle/oracle.py): pinned against the committed gguf-py golden
+vectors, against gguf-py live when it is importable, and through domain properties for the parts that no
+upstream artefact on this machine can pin (Q8_K quantisation, integer vec_dot, block glue)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rand_blocks
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = {"q8_0": 8, "q4_k": 12, "q5_k": 13, "q6_k": 14}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", list(NAMES))
+def test_dequant_matches_gguf_py_golden(oracle, name):
+    g = np.load(os.path.join(GOLD, f"dequant_{name}.npz"))
+    qt = NAMES[name]
+    raw = g["raw"]
+    out = oracle.dequantize(raw, qt, raw.shape[0] * oracle.BLOCK[qt][0])
+    a, b = _bits(out), g["out_bits"]
+    nan_both = np.isnan(out) & np.isnan(b.view(np.float32))
+    assert np.all((a == b) | nan_both)
+
+
+@pytest.mark.parametrize("name", list(NAMES))
+def test_dequant_matches_gguf_py_live(oracle, name):
+    gguf = pytest.importorskip("gguf")
+    T = gguf.GGMLQuantizationType
+    gt = {"q8_0": T.Q8_0, "q4_k": T.Q4_K, "q5_k": T.Q5_K, "q6_k": T.Q6_K}[name]
+    qt = NAMES[name]
+    rng = np.random.default_rng(5)
+    raw = rand_blocks(qt, 512, rng)
+    ref = gguf.quants.dequantize(raw.reshape(-1), gt).reshape(-1)
+    assert np.array_equal(_bits(ref), _bits(oracle.dequantize(raw, qt, 512 * oracle.BLOCK[qt][0])))
+
+
+def test_dequant_empty(oracle):
+    for qt in NAMES.values():
+        assert oracle.dequantize(np.zeros(0, np.uint8), qt, 0).size == 0
+
+
+def test_quantize_q8_0_matches_gguf_py_golden(oracle):
+    g = np.load(os.path.join(GOLD, "quantize_q8_0.npz"))
+    assert np.array_equal(oracle.quantize_q8_0(g["x"]), g["packed"])
+
+
+def test_fp16_conversions_exhaustive(oracle):
+    allh = np.arange(65536, dtype=np.uint16)
+    out = np.empty(65536, np.float32)
+    oracle.lib().gref_fp16_to_fp32_row(oracle._p(allh), oracle._p(out), 65536)
+    assert np.array_equal(_bits(out), _bits(allh.view(np.float16).astype(np.float32)))
+    finite = np.isfinite(out)
+    assert np.array_equal(oracle.fp32_to_fp16(out[finite]), allh[finite])  # round trip
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(200000) * np.exp(rng.uniform(-20, 12, 200000))).astype(np.float32)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(oracle.fp32_to_fp16(x), x.astype(np.float16).view(np.uint16))
+
+
+def test_quantize_q8_K_properties(oracle):
+    """No upstream vector exists for Q8_K on this machine (gguf-py cannot quantise it): check its definition."""
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal(256 * 40) * np.exp(rng.uniform(-3, 3, 256 * 40))).astype(np.float32)
+    x[:256] = 0
+    d, qs, bs = oracle.q8_K_fields(oracle.quantize_q8_K(x))
+    xb = x.reshape(-1, 256)
+    assert d[0] == 0 and not qs[0].any()
+    for b in range(1, xb.shape[0]):
+        i = int(np.argmax(np.abs(xb[b])))
+        assert qs[b, i] == -127                       # the extreme element maps to -127 (iscale = -127/max)
+        assert np.isclose(d[b], -xb[b, i] / 127, rtol=1e-6)
+        assert np.abs(qs[b].astype(np.float32) * d[b] - xb[b]).max() <= abs(d[b]) * 0.5001
+        assert np.array_equal(bs[b], qs[b].reshape(16, 16).sum(axis=1))
+    assert qs.max() <= 127 and qs.min() >= -127
+
+
+@pytest.mark.parametrize("name", ["q4_k", "q5_k", "q6_k", "q8_0"])
+def test_vec_dot_equals_exact_integer_formula_and_bounds_float(oracle, name):
+    """vec_dot == (dequantised weights) . (dequantised activations) up to f32 summation, and is within the
+    activation-quantisation error of the f32 matvec."""
+    qt = NAMES[name]
+    rng = np.random.default_rng(qt)
+    rows, k = 32, 2048
+    be, _ = oracle.BLOCK[qt]
+    raw = rand_blocks(qt, rows * k // be, rng)
+    x = rng.standard_normal(k).astype(np.float32)
+    y = oracle.matmul(qt, raw, rows, k, x)
+    W = oracle.dequantize(raw, qt, rows * k).reshape(rows, k).astype(np.float64)
+    if qt == 8:
+        p = oracle.quantize_q8_0(x).reshape(-1, 34)
+        xq = (p[:, 2:].copy().view(np.int8).astype(np.float64) * p[:, :2].copy().view(np.float16).astype(np.float64)).reshape(-1)
+    else:
+        d, qs, _ = oracle.q8_K_fields(oracle.quantize_q8_K(x))
+        xq = (qs.astype(np.float64) * d[:, None].astype(np.float64)).reshape(-1)
+    exact = W @ xq
+    assert np.abs(y - exact).max() <= 1e-5 * np.abs(exact).max()
+    assert np.abs(y - W @ x.astype(np.float64)).max() <= 2e-2 * np.abs(exact).max()
+
+
+def test_matmul_batch_equals_columns_and_is_linear_in_scale(oracle):
+    rng = np.random.default_rng(4)
+    rows, k = 16, 512
+    raw = rand_blocks(12, rows * k // 256, rng)
+    X = rng.standard_normal((3, k)).astype(np.float32)
+    Y = oracle.matmul(12, raw, rows, k, X)
+    for j in range(3):
+        assert np.array_equal(Y[j], oracle.matmul(12, raw, rows, k, X[j]))
+    # scaling the input by a power of two scales the output exactly (quantisation is scale-equivariant)
+    assert np.array_equal(oracle.matmul(12, raw, rows, k, X[0] * 4), Y[0] * 4)
+
+
+def test_block_glue_against_float64(oracle):
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(1024).astype(np.float32) * 3
+    w = rng.standard_normal(1024).astype(np.float32)
+    ref = x.astype(np.float64) / np.sqrt(np.mean(x.astype(np.float64) ** 2) + 1e-5) * w
+    assert np.abs(oracle.rms_norm(x, w, 1e-5) - ref).max() < 1e-5
+    g, u = x[:512], x[512:]
+    ref = g.astype(np.float64) / (1 + np.exp(-g.astype(np.float64))) * u
+    assert np.abs(oracle.swiglu(g, u) - ref).max() < 1e-5
+    # rope: rotation by pos * base^(-2i/d) of adjacent pairs, norm preserving
+    q = rng.standard_normal(4 * 64).astype(np.float32)
+    r = oracle.rope_norm(q, 4, 64, 64, 9, 10000.0)
+    th = 9 * 10000.0 ** (-np.arange(32) * 2 / 64)
+    qq = q.reshape(4, 32, 2).astype(np.float64)
+    ref = np.stack([qq[..., 0] * np.cos(th) - qq[..., 1] * np.sin(th), qq[..., 0] * np.sin(th) + qq[..., 1] * np.cos(th)], -1)
+    assert np.abs(r.reshape(4, 32, 2) - ref).max() < 1e-4
+    assert np.array_equal(oracle.rope_norm(q, 4, 64, 64, 0, 10000.0), q)
+    # attention against a float64 softmax
+    n_ctx, n_head, n_kv, hd, n = 40, 4, 2, 64, 33
+    kc = rng.standard_normal((n_ctx, n_kv * hd)).astype(np.float16)
+    vc = rng.standard_normal((n_ctx, n_kv * hd)).astype(np.float16)
+    qv = rng.standard_normal(n_head * hd).astype(np.float32)
+    out = oracle.attn_decode(qv, kc.view(np.uint16), vc.view(np.uint16), n_head, n_kv, hd, n)
+    for h in range(n_head):
+        kh = kc[:n, (h // 2) * hd:(h // 2 + 1) * hd].astype(np.float64)
+        vh = vc[:n, (h // 2) * hd:(h // 2 + 1) * hd].astype(np.float64)
+        s = kh @ qv[h * hd:(h + 1) * hd].astype(np.float16).astype(np.float64) / np.sqrt(hd)
+        p = np.exp(s - s.max()); p /= p.sum()
+        assert np.abs(out[h * hd:(h + 1) * hd] - p @ vh).max() < 1e-5
+    v = np.array([1, 5, 5, 2], dtype=np.float32)
+    assert oracle.argmax(v) == 1
+
+
+@pytest.mark.parametrize("ftype", ["Q4_K_M", "Q8_0"])
+def test_oracle_end_to_end_regression(oracle, model_dir, ftype):
+    """Seeded tiny model: greedy tokens and logits equal the committed vector (detects drift of the oracle or of
+    the synthetic generator); the logits are also bounded by an independent numpy f32 forward over gguf-py
+    dequantised weights."""
+    from ggufb200 import synth
+    g = np.load(os.path.join(GOLD, f"oracle_tiny_{ftype}.npz"))
+    path = os.path.join(model_dir, f"tiny-{ftype}.gguf")
+    synth.write_gguf(path, "tiny", ftype, seed=0xB200)
+    m = oracle.OracleLlama(path, n_ctx=64)
+    toks, logits = m.greedy(list(g["prompt"]), len(g["tokens"]), return_logits=True)
+    assert toks == list(g["tokens"])
+    assert np.allclose(logits[0], g["first_logits"], rtol=0, atol=1e-5)
+    assert np.allclose(logits[-1], g["last_logits"], rtol=0, atol=1e-5)
+
+
+def test_oracle_logits_bounded_by_float_forward(oracle, model_dir):
+    gguf = pytest.importorskip("gguf")
+    from ggufb200 import synth
+    path = os.path.join(model_dir, "tiny-f.gguf")
+    synth.write_gguf(path, "tiny", "Q4_K_M", seed=7)
+    m = oracle.OracleLlama(path, n_ctx=16)
+    rd = gguf.GGUFReader(path)
+    W = {t.name: gguf.quants.dequantize(np.asarray(t.data), t.tensor_type).astype(np.float64) for t in rd.tensors}
+    cfg = synth.PRESETS["tiny"]
+
+    def rms(x, w):
+        return x / np.sqrt(np.mean(x * x) + cfg.eps) * w
+
+    def fwd(tokens):
+        ks = [[] for _ in range(cfg.n_layer)]
+        vs = [[] for _ in range(cfg.n_layer)]
+        for pos, tok in enumerate(tokens):
+            x = W["token_embd.weight"][tok]
+            for l in range(cfg.n_layer):
+                p = f"blk.{l}."
+                h = rms(x, W[p + "attn_norm.weight"])
+                q, k, v = W[p + "attn_q.weight"] @ h, W[p + "attn_k.weight"] @ h, W[p + "attn_v.weight"] @ h
+                th = pos * cfg.rope_base ** (-np.arange(cfg.head_dim // 2) * 2 / cfg.head_dim)
+
+                def rope(t, nh):
+                    t = t.reshape(nh, -1, 2)
+                    return np.stack([t[..., 0] * np.cos(th) - t[..., 1] * np.sin(th), t[..., 0] * np.sin(th) + t[..., 1] * np.cos(th)], -1).reshape(-1)
+                q, k = rope(q, cfg.n_head), rope(k, cfg.n_kv)
+                ks[l].append(k); vs[l].append(v)
+                K, V = np.array(ks[l]), np.array(vs[l])
+                a = np.zeros(cfg.n_head * cfg.head_dim)
+                for hh in range(cfg.n_head):
+                    kv = hh // (cfg.n_head // cfg.n_kv)
+                    sl = slice(kv * cfg.head_dim, (kv + 1) * cfg.head_dim)
+                    s = K[:, sl] @ q[hh * cfg.head_dim:(hh + 1) * cfg.head_dim] / np.sqrt(cfg.head_dim)
+                    pr = np.exp(s - s.max()); pr /= pr.sum()
+                    a[hh * cfg.head_dim:(hh + 1) * cfg.head_dim] = pr @ V[:, sl]
+                x = x + W[p + "attn_output.weight"] @ a
+                h = rms(x, W[p + "ffn_norm.weight"])
+                g_, u_ = W[p + "ffn_gate.weight"] @ h, W[p + "ffn_up.weight"] @ h
+                x = x + W[p + "ffn_down.weight"] @ (g_ / (1 + np.exp(-g_)) * u_)
+        return W["output.weight"] @ rms(x, W["output_norm.weight"])
+
+    toks = [1, 300, 301]
+    m.reset()
+    for i, t in enumerate(toks):
+        lo = m.forward(t, i)
+    lf = fwd(toks)
+    # int8 activation quantisation + f16 KV: a few percent of the logit scale at most
+    assert np.abs(lo - lf).max() <= 0.05 * np.abs(lf).max()
+    assert np.corrcoef(lo, lf)[0, 1] > 0.999
