@@ -53,11 +53,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/... wrappers; let nvcc use the distro host compiler
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    extra = os.environ.get("GGB_NVCC_EXTRA", "").split()
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *ccbin, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc, *ccbin, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)))
     log = []
     failed = False

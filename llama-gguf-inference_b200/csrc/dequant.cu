@@ -125,6 +125,15 @@ __global__ void repack_kernel(int type, const uint8_t* __restrict__ src, uint8_t
         const int64_t so = ggb_repacked_to_canon(type, k, o);
         if (so >= 0) {
             v = (uint16_t)(srow[so] | (srow[so + 1] << 8));
+        } else if (so == -2) { /* Q4_K/Q5_K header: regrouped 6-bit scales/mins (layout.cuh) */
+            const int sbb = ggb_sb_bytes(type);
+            const int64_t tile_full = (int64_t)sbb * GGB_TILE_SB;
+            const int t = (int)(o / tile_full);
+            const int nsb = ggb_tile_nsb(k, t);
+            const int o3 = (int)(o - t * tile_full) - (type == GGB_TYPE_Q5_K ? 40 : 32) * 4 * nsb; /* offset inside HDR */
+            const int sb = o3 >> 4, i = (o3 & 15) - 4;
+            const uint8_t* sc = srow + ((int64_t)t * GGB_TILE_SB + sb) * sbb + 4;
+            v = (uint16_t)(ggb_hdr2_byte(sc, i) | (ggb_hdr2_byte(sc, i + 1) << 8));
         } else { /* Q5_K QHU: gather the fifth bits of 16 elements of one sub-block into two bytes */
             const int64_t tile_full = (int64_t)176 * GGB_TILE_SB;
             const int t = (int)(o / tile_full);
@@ -181,7 +190,7 @@ __device__ float deq_repacked(int type, const uint8_t* row, int64_t k, int64_t e
             q += ((bits >> l) & 1) << 4;
         }
         int sc, mn;
-        k4_scale_min(j, hdr + 4, sc, mn);
+        ggb_hdr2_scale_min(hdr, j, &sc, &mn);
         const float d = h2f(ld_u16(hdr)), dmin = h2f(ld_u16(hdr + 2));
         return __fsub_rn(__fmul_rn(__fmul_rn(d, (float)sc), (float)q), __fmul_rn(dmin, (float)mn));
     }

@@ -4,30 +4,46 @@
 // [UPSTREAM-MEM: ggml-quants.c, ggml-cpu/quants.c], plus the element-wise ops either side of it
 // (rms_norm*gain in front; residual add, SwiGLU, RoPE + KV-cache write, arg-max partials behind).
 //
-// Shape of the kernel (one launch = one "phase" of the layer, up to 3 weight matrices sharing the input):
-//   grid  = one CTA per SM (x ctas_per_sm), 512 threads; CTA c owns rows [rows*c/G, rows*(c+1)/G) of every
-//           segment, i.e. ONE contiguous byte range of each weight matrix -> HBM is streamed exactly once;
-//   prologue: every CTA redundantly normalises + quantises the K-vector into shared memory (int8 codes in a
-//           bank-swizzled order, per-block scales, per-16 sums).  K <= 28672 floats come from L2; doing it per
-//           CTA removes a whole launch + grid-wide dependency per phase;
-//   main loop: a warp takes (row, K-tile) items; lane u owns unit u of the tile (64 weights): 2-4 coalesced
-//           128-bit streaming loads (ld.global.nc.L1::no_allocate) issued one item ahead, in-register
-//           unpacking of the 6-bit scales/mins, dp4a integer dots against the int8 activations (identical
-//           integers to the CPU path), one f32 term per unit, f64 warp-shuffle reduction per item;
-//   epilogue: per-row f64 sum of the tile partials, ONE rounding to f32, then the fused op.
-// Accumulating the f32 terms in f64 makes the result independent of summation order, so the kernel agrees
-// bit-for-bit with the oracle's "canon" vec_dot (oracle/ggml_ref.c) -- greedy parity is then decided by
-// logic, not by which int8 code a 1-ulp difference happens to flip.  Cost: 1 F2D + 6 DADD per 2048 weights.
-// Programmatic dependent launch: the kernel calls griddepcontrol.wait only before it reads the previous
-// phase's output, so its launch latency and setup overlap the tail of the previous phase.
+// Shape of the kernel (one launch = one "phase" of a layer, up to 3 weight matrices sharing the input):
+//   grid   one CTA per SM, 16 warps.  CTA c owns rows [rows*c/G, rows*(c+1)/G) of every segment, i.e. ONE
+//          contiguous byte range of each weight matrix: HBM is streamed exactly once, in order.
+//   ring   every warp owns a private ring of tile slots in shared memory and is its own producer: one lane
+//          issues cp.async.bulk (TMA bulk copy, global -> shared, mbarrier complete_tx) for the tiles the
+//          warp will consume, several tiles ahead.  Weights do not depend on the previous phase, so the
+//          ring is filled BEFORE griddepcontrol.wait: with programmatic dependent launch the next phase's
+//          CTA is co-resident (<= 110 KB of shared memory, 64 registers) and its first ~80 KB per SM stream
+//          from HBM while the current phase is still computing -- HBM never idles across phase boundaries.
+//   prologue  every CTA redundantly normalises + quantises the K-vector into shared memory (int8 codes in a
+//          bank-swizzled order, per-block scales, per-16 sums); K <= 28672 floats come from L2.  Doing it
+//          per CTA removes a launch and a grid-wide dependency per phase.
+//   main loop  a warp walks PAIRS of rows; for each K-tile it loads the 64 int8 activations of its unit once
+//          (4 x LDS.128) and applies them to both rows: per row 3 x LDS.128 of packed weights from the ring,
+//          in-register unpacking of the 6-bit scales/mins, 16 dp4a, one f32 term, added to an f64 lane sum.
+//   reduce one butterfly per row pair (f64 shuffles), ONE rounding to f32 per output.
+//   epilogue  the fused element-wise op on the CTA's rows.
+// The f64 accumulation makes the result independent of summation order, so the kernel agrees bit-for-bit
+// with the oracle's "canon" vec_dot (oracle/ggml_ref.c): greedy parity is decided by logic, not rounding.
 #include <float.h>
+#include <stdlib.h>
 
 #include "actquant.cuh"
 #include "common.cuh"
 #include "layout.cuh"
 
-#define GEMV_NW 16
+#ifndef GEMV_NW
+#define GEMV_NW 8                          /* warps per CTA */
+#endif
 #define GEMV_THREADS (GEMV_NW * 32)
+#define GEMV_MAX_R 4
+// Per launch shape: R = rows a warp processes together (they share the activation registers), STEPS = ring stages
+// per warp (a stage = K-tile t of the R rows of a group, one mbarrier).  Chosen so that the ring of one CTA stays
+// <= ~80 KB and two CTAs (this phase and the next, launched early through PDL) fit one SM:
+//   Q4_K only        R=4 STEPS=2   8 warps x 8 x 1152 B = 72 KB
+//   Q6_K only        R=4 STEPS=2   8 warps x 8 x 1680 B = 105 KB (measured: the wider group beats co-residency here)
+//   Q4_K + Q6_K      R=2 STEPS=3   8 warps x 6 x 1680 B = 79 KB
+//   Q8_0             R=2 STEPS=2   8 warps x 4 x 2176 B = 68 KB
+#define GEMV_MIN_CTAS (GEMV_THREADS <= 256 ? 2 : (GEMV_THREADS <= 512 ? 2 : 1))
+#define RING_MAX_SLOTS 8
 
 struct SegK {
     const uint8_t* w;
@@ -42,6 +58,12 @@ struct GemvK {
     int n_seg, k, T;
     int pro, epi;
     int act_q8_0;
+    int slot_bytes, n_slots;   /* ring geometry (host-computed from the largest tile of the launch) */
+    int ring_bytes;            /* per warp = n_slots * slot_bytes: 4.5 KB (Q4_K) .. 8.5 KB (Q8_0) -> 72..136 KB per CTA */
+    int rowv_off;              /* byte offset of the per-row results in dynamic shared memory */
+    unsigned tl_slot;
+    int l2_prefetch;
+    int rq[GGB_MAX_SEG], rr[GGB_MAX_SEG];   /* rows = rq*grid + rr: CTA c starts at c*rq + min(c, rr) (no division on the device) */
     const float* x;
     const float* norm_w;
     float eps;
@@ -55,186 +77,337 @@ struct GemvK {
     int32_t* part_idx;
 };
 
+// ------------------------------------------------------------------ optional in-kernel timeline (debug builds only)
+#ifdef GGB_TIMELINE
+__device__ unsigned long long ggb_tl[8 * 1024 * 8];   /* [launch slot][cta][stamp] */
+__device__ unsigned int ggb_tl_launch;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_STAMP(i) do { if (threadIdx.x == 0) ggb_tl[((tl_slot & 7) * 1024 + (blockIdx.x & 1023)) * 8 + (i)] = gtime(); } while (0)
+#else
+#define TL_STAMP(i) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------ mbarrier / bulk-copy primitives (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared::cta, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // bank swizzle of 16-byte activation chunks: conflict-free LDS.128 for both the Q4_K/Q8_0 unit pattern
 // (chunks 4u+i) and the Q6_K pattern (chunks 16sb+8n+2r+t) -- see DESIGN.md "activation staging".
 __device__ __forceinline__ int swz(int c) { return c ^ ((c >> 2) & 7); }
 
-struct WReg {
-    uint4 a, b, c, d;
-    uint32_t e0, e1, e2;
+// shared-memory loads by 32-bit shared address (+ immediate): no generic-address arithmetic in the hot loop
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint16_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ uint4 and4(uint4 v, uint32_t m) { return make_uint4(v.x & m, v.y & m, v.z & m, v.w & m); }
+__device__ __forceinline__ int dot16_us(uint4 w, uint4 a) {  /* two independent dp4a chains */
+    const int s0 = dp4a_us(w.y, a.y, dp4a_us(w.x, a.x, 0));
+    const int s1 = dp4a_us(w.w, a.w, dp4a_us(w.z, a.z, 0));
+    return s0 + s1;
+}
+__device__ __forceinline__ int dot16_ss(uint4 w, uint4 a) {
+    const int s0 = dp4a_ss(w.y, a.y, dp4a_ss(w.x, a.x, 0));
+    const int s1 = dp4a_ss(w.w, a.w, dp4a_ss(w.z, a.z, 0));
+    return s0 + s1;
+}
+
+// the activations one lane needs for its unit of a K-tile (shared by both rows of a pair)
+struct Act {
+    uint4 a0, a1, a2, a3;
+    int b0, b1, b2, b3;   /* Q4_K: b0 = sum of sub-block 2g, b1 = sum of 2g+1; Q6_K: 32 * per-16 sums */
+    float dx0, dx1;       /* activation block scale(s) */
 };
 
+// qs_s / bs_s / dsc_s = 32-bit shared addresses of the int8 codes, per-16 sums (int16), block scales (f32)
 template <int MASK>
-__device__ __forceinline__ void load_item(WReg& w, int type, const uint8_t* tb, int U, int nsb, int lane) {
-    const bool act = lane < U;
-    w.a = w.b = w.c = w.d = make_uint4(0, 0, 0, 0);
-    w.e0 = w.e1 = w.e2 = 0;
-    if (!act) return;
-    if ((MASK & 1) && type == GGB_TYPE_Q4_K) {
-        w.a = ldg_stream(tb + 16 * lane);
-        w.b = ldg_stream(tb + 16 * U + 16 * lane);
-        w.c = ldg_cached(tb + 32 * U + 16 * (lane >> 2));
-    } else if ((MASK & 2) && type == GGB_TYPE_Q6_K) {
-        w.a = ldg_stream(tb + 16 * lane);
-        w.b = ldg_stream(tb + 16 * U + 16 * lane);
-        w.c = ldg_stream(tb + 32 * U + 16 * lane);
-        const uint2 s = __ldg(reinterpret_cast<const uint2*>(tb + 48 * U + 16 * (lane >> 2) + 8 * ((lane >> 1) & 1)));
-        w.e0 = s.x; w.e1 = s.y;
-        w.e2 = __ldg(reinterpret_cast<const uint16_t*>(tb + 48 * U + 16 * nsb + 2 * (lane >> 2)));
-    } else if ((MASK & 4) && type == GGB_TYPE_Q8_0) {
-        w.a = ldg_stream(tb + 16 * lane);
-        w.b = ldg_stream(tb + 16 * U + 16 * lane);
-        w.c = ldg_stream(tb + 32 * U + 16 * lane);
-        w.d = ldg_stream(tb + 48 * U + 16 * lane);
-        w.e0 = __ldg(reinterpret_cast<const uint32_t*>(tb + 64 * U + 4 * lane));
+__device__ __forceinline__ Act load_act(int type, int gu, uint32_t qs_s, uint32_t bs_s, uint32_t dsc_s) {
+    Act A;
+    A.b0 = A.b1 = A.b2 = A.b3 = 0;
+    A.dx1 = 0.f;
+    if ((MASK & 2) && (MASK == 2 || type == GGB_TYPE_Q6_K)) {
+        const int c0 = 4 * gu - 3 * (gu & 1); /* chunk of r = 0; r adds 2 */
+        A.a0 = lds128(qs_s + 16 * swz(c0));
+        A.a1 = lds128(qs_s + 16 * swz(c0 + 2));
+        A.a2 = lds128(qs_s + 16 * swz(c0 + 4));
+        A.a3 = lds128(qs_s + 16 * swz(c0 + 6));
+        A.b0 = 32 * (int)(int16_t)lds16(bs_s + 2 * c0);
+        A.b1 = 32 * (int)(int16_t)lds16(bs_s + 2 * c0 + 4);
+        A.b2 = 32 * (int)(int16_t)lds16(bs_s + 2 * c0 + 8);
+        A.b3 = 32 * (int)(int16_t)lds16(bs_s + 2 * c0 + 12);
+        A.dx0 = __uint_as_float(lds32(dsc_s + 4 * (gu >> 2)));
+        return A;
     }
+    A.a0 = lds128(qs_s + 16 * swz(4 * gu + 0));
+    A.a1 = lds128(qs_s + 16 * swz(4 * gu + 1));
+    A.a2 = lds128(qs_s + 16 * swz(4 * gu + 2));
+    A.a3 = lds128(qs_s + 16 * swz(4 * gu + 3));
+    if (MASK & 4) {
+        const uint2 dx = lds64(dsc_s + 8 * gu);
+        A.dx0 = __uint_as_float(dx.x); A.dx1 = __uint_as_float(dx.y);
+    } else {
+        const uint2 bs = lds64(bs_s + 8 * gu); /* four per-16 sums */
+        A.b0 = (int)(int16_t)(bs.x & 0xFFFF) + ((int)bs.x >> 16);
+        A.b1 = (int)(int16_t)(bs.y & 0xFFFF) + ((int)bs.y >> 16);
+        A.dx0 = __uint_as_float(lds32(dsc_s + 4 * (gu >> 2)));
+    }
+    return A;
 }
 
-#define DP4_US(acc, wv, av) acc = dp4a_us((wv).x, (av).x, acc); acc = dp4a_us((wv).y, (av).y, acc); acc = dp4a_us((wv).z, (av).z, acc); acc = dp4a_us((wv).w, (av).w, acc)
-__device__ __forceinline__ uint4 and4(uint4 v, uint32_t m) { return make_uint4(v.x & m, v.y & m, v.z & m, v.w & m); }
-
-// gu = global unit index (tile*32 + lane); qs/bsums/dsc = the CTA's quantised activation vector in smem
-__device__ __forceinline__ float unit_q4k(const WReg& w, int gu, const uint8_t* qs, const int16_t* bsums, const float* dsc) {
-    const uint4 a0 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 0));
-    const uint4 a1 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 1));
-    const uint4 a2 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 2));
-    const uint4 a3 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 3));
-    int dlo = 0, dhi = 0;
-    { const uint4 t = and4(w.a, 0x0F0F0F0Fu); DP4_US(dlo, t, a0); }
-    { const uint4 t = and4(w.b, 0x0F0F0F0Fu); DP4_US(dlo, t, a1); }
-    { const uint4 t = and4(w.a, 0xF0F0F0F0u); DP4_US(dhi, t, a2); }   // 16 x the high-nibble dot (exact)
-    { const uint4 t = and4(w.b, 0xF0F0F0F0u); DP4_US(dhi, t, a3); }
-    dhi >>= 4;
-    // 6-bit scales/mins of sub-blocks 2g, 2g+1 (gguf/quants.py:478-502), two bytes at a time
-    const int g = gu & 3;
-    const int sh = 16 * (g & 1);
-    const uint32_t p1 = (w.c.y >> sh) & 0xFFFFu, p2 = (w.c.z >> sh) & 0xFFFFu, p3 = (w.c.w >> sh) & 0xFFFFu;
-    uint32_t sc2, mn2;
-    if (g < 2) { sc2 = p1 & 0x3F3Fu; mn2 = p2 & 0x3F3Fu; }
-    else { sc2 = (p3 & 0x0F0Fu) | ((p1 >> 2) & 0x3030u); mn2 = ((p3 >> 4) & 0x0F0Fu) | ((p2 >> 2) & 0x3030u); }
-    const int isum = (int)(sc2 & 0xFF) * dlo + (int)(sc2 >> 8) * dhi;
-    const uint2 bs = *reinterpret_cast<const uint2*>(bsums + 4 * gu); /* four per-16 sums */
-    const int bs_lo = (int)(int16_t)(bs.x & 0xFFFF) + (int)(int16_t)(bs.x >> 16);
-    const int bs_hi = (int)(int16_t)(bs.y & 0xFFFF) + (int)(int16_t)(bs.y >> 16);
-    const int msum = (int)(mn2 & 0xFF) * bs_lo + (int)(mn2 >> 8) * bs_hi;
-    const float dx = dsc[gu >> 2];
-    const float d = h2f((uint16_t)(w.c.x & 0xFFFF)), dmin = h2f((uint16_t)(w.c.x >> 16));
-    // one f32 term per unit, fixed operation order (oracle: gref_vec_dot_q4_K_q8_K_canon)
-    return __fsub_rn(__fmul_rn(__fmul_rn(d, dx), (float)isum), __fmul_rn(__fmul_rn(dmin, dx), (float)msum));
+// per-lane constants: byte-permute selectors that pull the lane's 24-bit scale field out of the header
+// (layout.cuh: field g sits at header bytes 4+3g .. 6+3g)
+struct LaneK { uint32_t selA, selB; bool lowg; uint32_t o_q, o_h, o_sc, o_d; };
+__device__ __forceinline__ LaneK lane_consts(int lane) {
+    LaneK L;
+    const int g = lane & 3;
+    L.lowg = g < 2;
+    L.selA = (g == 0) ? 0x3210u : 0x0543u;   /* on (hdr.y, hdr.z) */
+    L.selB = (g == 2) ? 0x0432u : 0x0765u;   /* on (hdr.z, hdr.w) */
+    L.o_q = 16u * lane;                        /* the lane's 16-byte chunk inside a section */
+    L.o_h = 16u * (lane >> 2);                 /* its super-block header / scale row */
+    L.o_sc = 16u * (lane >> 2) + 8u * ((lane >> 1) & 1);  /* Q6_K: the 8 scales of half n */
+    L.o_d = 2u * (lane >> 2);
+    return L;
 }
 
-__device__ __forceinline__ float unit_q6k(const WReg& w, int gu, const uint8_t* qs, const int16_t* bsums, const float* dsc) {
-    const int tt = gu & 1;
-    const int c0 = 4 * gu - 3 * tt; /* chunk of r = 0; r adds 2 */
-    const uint4 a0 = *reinterpret_cast<const uint4*>(qs + 16 * swz(c0));
-    const uint4 a1 = *reinterpret_cast<const uint4*>(qs + 16 * swz(c0 + 2));
-    const uint4 a2 = *reinterpret_cast<const uint4*>(qs + 16 * swz(c0 + 4));
-    const uint4 a3 = *reinterpret_cast<const uint4*>(qs + 16 * swz(c0 + 6));
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    { const uint4 t = and4(w.a, 0x0F0F0F0Fu); DP4_US(s0, t, a0); }
-    { const uint4 t = and4(w.b, 0x0F0F0F0Fu); DP4_US(s1, t, a1); }
-    { const uint4 t = and4(w.a, 0xF0F0F0F0u); DP4_US(s2, t, a2); }
-    { const uint4 t = and4(w.b, 0xF0F0F0F0u); DP4_US(s3, t, a3); }
-    { const uint4 t = and4(w.c, 0x03030303u); DP4_US(h0, t, a0); }
-    { const uint4 t = and4(w.c, 0x0C0C0C0Cu); DP4_US(h1, t, a1); }
-    { const uint4 t = and4(w.c, 0x30303030u); DP4_US(h2, t, a2); }
-    { const uint4 t = and4(w.c, 0xC0C0C0C0u); DP4_US(h3, t, a3); }
-    // sum (q-32)*a over each 16-group = nibble part + 16*high-bit part - 32*sum(a)
-    const int v0 = s0 + (h0 << 4) - 32 * (int)bsums[c0];
-    const int v1 = s1 + (h1 << 2) - 32 * (int)bsums[c0 + 2];
-    const int v2 = (s2 >> 4) + h2 - 32 * (int)bsums[c0 + 4];
-    const int v3 = (s3 >> 4) + (h3 >> 2) - 32 * (int)bsums[c0 + 6];
-    // scales sc[8n + 2r + t]: e0,e1 hold the 8 scales of this half; byte (2r + t)
-    const uint32_t lo = tt ? (w.e0 >> 8) : w.e0, hi = tt ? (w.e1 >> 8) : w.e1;
+// one f32 term of a Q4_K unit: sub-blocks 2g (low nibbles) and 2g+1 (high nibbles) of one super-block
+// (oracle: gref_vec_dot_q4_K_q8_K_canon -- same integers, same f32 operation order)
+__device__ __forceinline__ float term_q4k(uint4 q0, uint4 q1, uint4 hdr, const Act& A, const LaneK& L) {
+    const int dlo = dot16_us(and4(q0, 0x0F0F0F0Fu), A.a0) + dot16_us(and4(q1, 0x0F0F0F0Fu), A.a1);
+    const int dhi = (dot16_us(and4(q0, 0xF0F0F0F0u), A.a2) + dot16_us(and4(q1, 0xF0F0F0F0u), A.a3)) >> 4; /* exact */
+    const uint32_t fa = __byte_perm(hdr.y, hdr.z, L.selA), fb = __byte_perm(hdr.z, hdr.w, L.selB);
+    const uint32_t f = L.lowg ? fa : fb;       /* sc[2g] | sc[2g+1]<<6 | min[2g]<<12 | min[2g+1]<<18 */
+    const int isum = (int)(f & 63) * dlo + (int)((f >> 6) & 63) * dhi;
+    const int msum = (int)((f >> 12) & 63) * A.b0 + (int)((f >> 18) & 63) * A.b1;
+    const float d = h2f((uint16_t)(hdr.x & 0xFFFF)), dmin = h2f((uint16_t)(hdr.x >> 16));
+    return __fsub_rn(__fmul_rn(__fmul_rn(d, A.dx0), (float)isum), __fmul_rn(__fmul_rn(dmin, A.dx0), (float)msum));
+}
+
+// Q6_K unit (half n, column t): elements 128n + 32r + 16t + (0..15), r = 0..3; sc8 = the 8 scales of half n
+__device__ __forceinline__ float term_q6k(uint4 qla, uint4 qlb, uint4 qh, uint2 sc8, uint32_t dbits, const Act& A, int tt) {
+    // sum (q-32)*a over a 16-group = nibble dot + 16*(2-bit dot) - 32*sum(a); masked bytes keep their position,
+    // the power-of-two factor is removed by an exact shift
+    const int v0 = dot16_us(and4(qla, 0x0F0F0F0Fu), A.a0) + (dot16_us(and4(qh, 0x03030303u), A.a0) << 4) - A.b0;
+    const int v1 = dot16_us(and4(qlb, 0x0F0F0F0Fu), A.a1) + (dot16_us(and4(qh, 0x0C0C0C0Cu), A.a1) << 2) - A.b1;
+    const int v2 = (dot16_us(and4(qla, 0xF0F0F0F0u), A.a2) >> 4) + dot16_us(and4(qh, 0x30303030u), A.a2) - A.b2;
+    const int v3 = (dot16_us(and4(qlb, 0xF0F0F0F0u), A.a3) >> 4) + (dot16_us(and4(qh, 0xC0C0C0C0u), A.a3) >> 2) - A.b3;
+    const uint32_t lo = tt ? (sc8.x >> 8) : sc8.x, hi = tt ? (sc8.y >> 8) : sc8.y; /* scale byte 2r + t */
     const int isum = (int)(int8_t)(lo & 0xFF) * v0 + (int)(int8_t)((lo >> 16) & 0xFF) * v1 +
                      (int)(int8_t)(hi & 0xFF) * v2 + (int)(int8_t)((hi >> 16) & 0xFF) * v3;
-    return __fmul_rn(__fmul_rn(h2f((uint16_t)w.e2), dsc[gu >> 2]), (float)isum);
+    return __fmul_rn(__fmul_rn(h2f((uint16_t)dbits), A.dx0), (float)isum);
 }
 
-#define DP4_SS(acc, wv, av) acc = dp4a_ss((wv).x, (av).x, acc); acc = dp4a_ss((wv).y, (av).y, acc); acc = dp4a_ss((wv).z, (av).z, acc); acc = dp4a_ss((wv).w, (av).w, acc)
-
-__device__ __forceinline__ double unit_q8_0(const WReg& w, int gu, const uint8_t* qs, const float* dsc) {
-    const uint4 a0 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 0));
-    const uint4 a1 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 1));
-    const uint4 a2 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 2));
-    const uint4 a3 = *reinterpret_cast<const uint4*>(qs + 16 * swz(4 * gu + 3));
-    int i0 = 0, i1 = 0;
-    DP4_SS(i0, w.a, a0); DP4_SS(i0, w.b, a1);
-    DP4_SS(i1, w.c, a2); DP4_SS(i1, w.d, a3);
-    const float2 dx = *reinterpret_cast<const float2*>(dsc + 2 * gu);
-    const float t0 = __fmul_rn((float)i0, __fmul_rn(h2f((uint16_t)(w.e0 & 0xFFFF)), dx.x));
-    const float t1 = __fmul_rn((float)i1, __fmul_rn(h2f((uint16_t)(w.e0 >> 16)), dx.y));
-    return (double)t0 + (double)t1; /* one f32 term per 32-block, added in f64 */
-}
-
-template <int MASK>
-__device__ __forceinline__ double compute_item(const WReg& w, int type, int gu, bool act, const uint8_t* qs,
-                                               const int16_t* bsums, const float* dsc) {
-    double p = 0.0;
-    if (act) {
-        if ((MASK & 1) && type == GGB_TYPE_Q4_K) p = unit_q4k(w, gu, qs, bsums, dsc);
-        else if ((MASK & 2) && type == GGB_TYPE_Q6_K) p = unit_q6k(w, gu, qs, bsums, dsc);
-        else if ((MASK & 4) && type == GGB_TYPE_Q8_0) p = unit_q8_0(w, gu, qs, dsc);
+// one (row, tile) item read from its ring slot (32-bit shared address); U16 = 16*U = section size in bytes.
+// FULL tiles (U = 32) get compile-time offsets; returns the lane's contribution as f64.
+template <int MASK, bool FULL>
+__device__ __forceinline__ double consume(int type, uint32_t slot, int lane, int U, int nsb, const Act& A, const LaneK& L) {
+    if (!FULL && lane >= U) return 0.0;
+    const uint32_t S = FULL ? 512u : 16u * (uint32_t)U;   /* bytes per 16-byte-per-unit section */
+    if ((MASK & 1) && (MASK == 1 || type == GGB_TYPE_Q4_K)) {
+        const uint4 q0 = lds128(slot + L.o_q);
+        const uint4 q1 = lds128(slot + L.o_q + S);
+        const uint4 hd = lds128(slot + L.o_h + 2 * S);
+        return (double)term_q4k(q0, q1, hd, A, L);
+    } else if ((MASK & 2) && (MASK == 2 || type == GGB_TYPE_Q6_K)) {
+        const uint4 qla = lds128(slot + L.o_q);
+        const uint4 qlb = lds128(slot + L.o_q + S);
+        const uint4 qh = lds128(slot + L.o_q + 2 * S);
+        const uint2 sc = lds64(slot + L.o_sc + 3 * S);
+        const uint32_t db = lds16(slot + L.o_d + 3 * S + (FULL ? 128u : 16u * (uint32_t)nsb));
+        return (double)term_q6k(qla, qlb, qh, sc, db, A, lane & 1);
+    } else if (MASK & 4) {
+        const uint4 w0 = lds128(slot + L.o_q);
+        const uint4 w1 = lds128(slot + L.o_q + S);
+        const uint4 w2 = lds128(slot + L.o_q + 2 * S);
+        const uint4 w3 = lds128(slot + L.o_q + 3 * S);
+        const uint32_t dd = lds32(slot + 4 * S + 4u * lane);
+        const int i0 = dot16_ss(w0, A.a0) + dot16_ss(w1, A.a1);
+        const int i1 = dot16_ss(w2, A.a2) + dot16_ss(w3, A.a3);
+        const float t0 = __fmul_rn((float)i0, __fmul_rn(h2f((uint16_t)(dd & 0xFFFF)), A.dx0));
+        const float t1 = __fmul_rn((float)i1, __fmul_rn(h2f((uint16_t)(dd >> 16)), A.dx1));
+        return (double)t0 + (double)t1; /* one f32 term per 32-block, added in f64 */
     }
-    return p;
+    return 0.0;
 }
 
 __device__ __forceinline__ void argmax_comb(float& v, int& i, float ov, int oi) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
-// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0 segments present (dead code elimination per launch shape)
-template <int MASK>
-__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_constant__ GemvK P) {
-    extern __shared__ __align__(16) uint8_t smem[];
+// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0 segments present (dead-code elimination per launch shape)
+template <int MASK, int R, int STEPS>
+__global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const __grid_constant__ GemvK P) {
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ double red[GEMV_NW];
     __shared__ float s_val[GEMV_NW];
     __shared__ int s_idx[GEMV_NW];
+    __shared__ __align__(8) uint64_t s_bar[GEMV_NW][STEPS];
+    static_assert(R == 2 || R == 4, "row group size");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = P.k, T = P.T;
-    uint8_t* qs = smem;                                                   // K bytes
-    int16_t* bsums = reinterpret_cast<int16_t*>(smem + K);                // K/16 int16
-    float* dsc = reinterpret_cast<float*>(smem + K + K / 8);              // K/32 floats
-    double* partial = reinterpret_cast<double*>(smem + K + K / 8 + K / 8); // one f64 partial per (row, tile) item
+#ifdef GGB_TIMELINE
+    const unsigned tl_slot = P.tl_slot;
+#endif
+    TL_STAMP(0);
+    uint8_t* qs = smem + GEMV_NW * P.ring_bytes;                  // K bytes
+    int16_t* bsums = reinterpret_cast<int16_t*>(qs + K);          // K/16 int16
+    float* dsc = reinterpret_cast<float*>(qs + K + K / 8);        // K/32 floats
+    float* rowv = reinterpret_cast<float*>(smem + P.rowv_off);    // one f32 result per local row
+    const uint32_t SLOT = P.slot_bytes;                           // one tile; a step holds two (rows A and B)
 
-    // ---- this CTA's row range in every segment (even-aligned so RoPE pairs stay together)
-    int r0[GGB_MAX_SEG], cnt[GGB_MAX_SEG];
-    int nloc = 0;
-#pragma unroll
-    for (int s = 0; s < GGB_MAX_SEG; s++) {
-        r0[s] = 0; cnt[s] = 0;
-        if (s < P.n_seg) {
-            const int64_t rows = P.seg[s].rows;
-            int a = (int)(rows * blockIdx.x / gridDim.x), b = (int)(rows * (blockIdx.x + 1) / gridDim.x);
-            a &= ~1; if (blockIdx.x + 1 != gridDim.x) b &= ~1;
-            r0[s] = a; cnt[s] = b - a;
-            nloc += cnt[s];
-        }
+    // ---- this CTA's row range in every segment (even-aligned: row pairs and RoPE pairs stay together)
+    const int G = gridDim.x, c = blockIdx.x;
+    int r0_0, r0_1 = 0, r0_2 = 0, cnt0, cnt1 = 0, cnt2 = 0;
+    {
+        const bool last = (c + 1 == G);
+        auto range = [&](int sg, int& r0, int& cnt) {
+            const int q = P.rq[sg], r = P.rr[sg];
+            const int a = (c * q + min(c, r)) & ~(R - 1);
+            int b = (c + 1) * q + min(c + 1, r);
+            if (!last) b &= ~(R - 1);
+            r0 = a; cnt = b - a;
+        };
+        range(0, r0_0, cnt0);
+        if (P.n_seg > 1) range(1, r0_1, cnt1);
+        if (P.n_seg > 2) range(2, r0_2, cnt2);
     }
-    const int nitems = nloc * T;
+    const int nloc = cnt0 + cnt1 + cnt2;
+    // local rows are laid out [seg0 | seg1 | seg2]; a group of R rows never straddles a segment; a count that is
+    // not a multiple of R (possible only in the last CTA) leaves a short last group.
+    const int np0 = (cnt0 + R - 1) / R, np1 = (cnt1 + R - 1) / R, np2 = (cnt2 + R - 1) / R;
+    const int npairs = np0 + np1 + np2;   /* number of row groups of this CTA */
 
-    // item -> (segment, row, tile)
-    auto locate = [&](int item, int& type, const uint8_t*& tb, int& U, int& nsb, int& t) {
-        int lr = item / T;
-        t = item - lr * T;
-        int s = 0;
-        if (lr >= cnt[0]) { lr -= cnt[0]; s = 1; if (lr >= cnt[1]) { lr -= cnt[1]; s = 2; } }
-        type = P.seg[s].type;
-        nsb = ggb_tile_nsb(K, t);
-        U = 4 * nsb;
-        tb = P.seg[s].w + (int64_t)(r0[s] + lr) * P.seg[s].stride + (int64_t)t * (ggb_sb_bytes(type) * GGB_TILE_SB);
+    // group index -> segment, first row, number of rows present (1..R), first local row index
+    auto pair_info = [&](int p, int& s, int& row, int& nv, int& lr) {
+        if (p < np0) { s = 0; row = r0_0 + R * p; nv = min(R, cnt0 - R * p); lr = R * p; }
+        else if (p < np0 + np1) { p -= np0; s = 1; row = r0_1 + R * p; nv = min(R, cnt1 - R * p); lr = cnt0 + R * p; }
+        else { p -= np0 + np1; s = 2; row = r0_2 + R * p; nv = min(R, cnt2 - R * p); lr = cnt0 + cnt1 + R * p; }
     };
 
-    // ---- weights do not depend on the previous phase: put the first item in flight before waiting for it
-    WReg w0, w1;
-    int type0 = 0, U0 = 0, nsb0 = 0, t0 = 0;
-    const uint8_t* tb0 = nullptr;
-    int item = warp;
-    if (item < nitems) { locate(item, type0, tb0, U0, nsb0, t0); load_item<MASK>(w0, type0, tb0, U0, nsb0, lane); }
+    // ---- producer (lane 0 of each warp).  One "step" = K-tile t of the R rows of a group = one ring stage
+    // (R tile slots, one mbarrier).  The cursor lives in registers: pointer of the next tile of the group's
+    // first row, tile index, group index.
+    const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
+    const uint32_t ring0 = smem_u32(smem) + warp * P.ring_bytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STEPS; i++) mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int nsb_last = ggb_tile_nsb(K, T - 1);
+    int ip = warp, it = 0, istage = 0;
+    const uint8_t* isrc = nullptr;   // tile `it` of the first row of group `ip`
+    int istride = 0, itile = 0, ilast = 0;   // row stride, full-tile bytes, last-tile bytes (16-byte rounded)
+    int inv = 0;
+    auto issue_pair_setup = [&]() {
+        int s, row, lr;
+        pair_info(ip, s, row, inv, lr);
+        const int sbb = ggb_sb_bytes(P.seg[s].type);
+        istride = (int)P.seg[s].stride;
+        itile = sbb * GGB_TILE_SB;
+        ilast = (nsb_last * sbb + 15) & ~15;
+        isrc = P.seg[s].w + (int64_t)row * istride;
+    };
+    if (ip < npairs) issue_pair_setup();
+    auto issue_step = [&]() {  // lane 0 only: tile `it` of every row of the group into stage `istage`, then advance
+        const uint32_t bytes = (it == T - 1) ? (uint32_t)ilast : (uint32_t)itile;
+        const uint32_t bar = bar0 + 8 * istage;
+        const uint32_t dst = ring0 + istage * R * SLOT;
+        mbar_expect_tx(bar, (uint32_t)inv * bytes);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (r < inv) bulk_g2s(dst + r * SLOT, isrc + (int64_t)r * istride, bytes, bar);
+        istage = (istage + 1 == STEPS) ? 0 : istage + 1;
+        isrc += itile;
+        if (++it == T) {
+            it = 0;
+            ip += GEMV_NW;
+            if (ip < npairs) issue_pair_setup();
+        }
+    };
+    // fill the ring before waiting for the previous phase (weights are independent of it)
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STEPS; i++) if (ip < npairs) issue_step();
+    }
 
+    // optional: ask the L2 to pull this CTA's whole byte range from HBM now (no registers / smem involved), so
+    // that HBM keeps streaming through the dependency wait and the prologue and the ring refills hit L2
+    if (P.l2_prefetch) {
+        constexpr int PIECE = 8192;
+        auto pf = [&](int sg, int r0, int cnt) {
+            if (cnt <= 0) return;
+            const uint8_t* base = P.seg[sg].w + (int64_t)r0 * P.seg[sg].stride;
+            const int64_t bytes = (int64_t)cnt * P.seg[sg].stride;
+            for (int64_t off = (int64_t)tid * PIECE; off < bytes; off += (int64_t)GEMV_THREADS * PIECE) {
+                const uint32_t sz = (uint32_t)min((int64_t)PIECE, bytes - off) & ~15u;
+                if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+            }
+        };
+        pf(0, r0_0, cnt0);
+        if (P.n_seg > 1) pf(1, r0_1, cnt1);
+        if (P.n_seg > 2) pf(2, r0_2, cnt2);
+    }
+
+    // the RMSNorm gains are weights too: fetch this lane's eight for the warp's first 256-block now
+    float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+    if (P.pro == GGB_PRO_RMSNORM && warp < K / 256) {
+        g0 = *reinterpret_cast<const float4*>(P.norm_w + warp * 256 + lane * 8);
+        g1 = *reinterpret_cast<const float4*>(P.norm_w + warp * 256 + lane * 8 + 4);
+    }
+
+    TL_STAMP(1);
     pdl_launch_dependents();
     pdl_wait();
+    TL_STAMP(2);
+
+    // epilogue operands that only depend on the previous phase: request them now, use them at the end
+    float res_pre = 0.f;
+    if (P.epi == GGB_EPI_RESIDUAL && tid < cnt0) res_pre = P.residual[r0_0 + tid];
 
     // ---- prologue: (rms_norm * gain) and activation quantisation into shared memory
     float scale = 1.f;
@@ -251,93 +424,153 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         const float mean = (float)(tot / (double)K);
         scale = __fdiv_rn(1.0f, __fsqrt_rn(mean + P.eps));
     }
-    for (int b = warp; b < K / 256; b += GEMV_NW) {
-        const int e0 = b * 256 + lane * 8;
-        const float4 x0 = *reinterpret_cast<const float4*>(P.x + e0), x1 = *reinterpret_cast<const float4*>(P.x + e0 + 4);
-        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    // two 256-blocks per warp iteration, loads of both issued before either is quantised
+    auto quant_block = [&](int b, float v[8], const float4& ga, const float4& gb) {
         if (P.pro == GGB_PRO_RMSNORM) {
-            const float4 g0 = *reinterpret_cast<const float4*>(P.norm_w + e0), g1 = *reinterpret_cast<const float4*>(P.norm_w + e0 + 4);
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), g[i]);
         }
-        const int chunk = e0 >> 4;
+        const int chunk = (b * 256 + lane * 8) >> 4;
         uint2* dst = reinterpret_cast<uint2*>(qs + 16 * swz(chunk) + 8 * (lane & 1));
         if (P.act_q8_0) {
             float df; uint16_t db;
-            const Q8Codes c = warp_quantize_q8_0(v, df, db);
-            *dst = c.q;
+            const Q8Codes cq = warp_quantize_q8_0(v, df, db);
+            *dst = cq.q;
             if (!(lane & 3)) dsc[b * 8 + (lane >> 2)] = df;
         } else {
             float dd;
-            const Q8Codes c = warp_quantize_q8_K(v, lane, dd);
-            *dst = c.q;
-            const int s16 = c.sum8 + __shfl_xor_sync(0xffffffffu, c.sum8, 1);
+            const Q8Codes cq = warp_quantize_q8_K(v, lane, dd);
+            *dst = cq.q;
+            const int s16 = cq.sum8 + __shfl_xor_sync(0xffffffffu, cq.sum8, 1);
             if (!(lane & 1)) bsums[chunk] = (int16_t)s16;
             if (lane == 0) dsc[b] = dd;
         }
+    };
+    const int nblk = K / 256;
+    constexpr int PB = 4;   /* 256-blocks per warp iteration: all their loads are in flight before the first is quantised */
+    for (int b = warp; b < nblk; b += PB * GEMV_NW) {
+        float4 xa[PB], xb[PB], ga[PB], gb[PB];
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+            const int bj = b + j * GEMV_NW;
+            const int e = (bj < nblk ? bj : b) * 256 + lane * 8;
+            xa[j] = *reinterpret_cast<const float4*>(P.x + e);
+            xb[j] = *reinterpret_cast<const float4*>(P.x + e + 4);
+            if (P.pro == GGB_PRO_RMSNORM) {
+                if (j == 0 && b == warp) { ga[j] = g0; gb[j] = g1; }
+                else { ga[j] = *reinterpret_cast<const float4*>(P.norm_w + e); gb[j] = *reinterpret_cast<const float4*>(P.norm_w + e + 4); }
+            } else { ga[j] = g0; gb[j] = g1; }
+        }
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+            const int bj = b + j * GEMV_NW;
+            if (bj < nblk) {
+                float v[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+                quant_block(bj, v, ga[j], gb[j]);
+            }
+        }
     }
     __syncthreads();
+    TL_STAMP(3);
 
-    // ---- main loop: one (row, tile) item per warp per step, next item's loads in flight
-    for (; item < nitems; item += 2 * GEMV_NW) {
-        int type1 = 0, U1 = 0, nsb1 = 0, t1 = 0;
-        const uint8_t* tb1 = nullptr;
-        const int nx = item + GEMV_NW;
-        if (nx < nitems) { locate(nx, type1, tb1, U1, nsb1, t1); load_item<MASK>(w1, type1, tb1, U1, nsb1, lane); }
-        {
-            double p = compute_item<MASK>(w0, type0, t0 * 32 + lane, lane < U0, qs, bsums, dsc);
-            p = warp_sum_f64(p);
-            if (lane == 0) partial[item] = p;
+    // ---- main loop over this warp's row groups
+    const LaneK L = lane_consts(lane);
+    const uint32_t qs_s = smem_u32(qs), bs_s = smem_u32(bsums), dsc_s = smem_u32(dsc);
+    const int U_last = 4 * nsb_last;
+    const bool last_full = (nsb_last == GGB_TILE_SB);
+    int cstage = 0;
+    uint32_t cphase = 0;   // parity of the current pass over the ring
+    for (int p = warp; p < npairs; p += GEMV_NW) {
+        int s, row, lr, nv;
+        pair_info(p, s, row, nv, lr);
+        const int type = P.seg[s].type;
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0.0;
+        for (int t = 0; t < T; t++) {
+            const bool full = (t != T - 1) || last_full;
+            const int U = full ? 32 : U_last;
+            Act A;
+            if (lane < U) A = load_act<MASK>(type, t * 32 + lane, qs_s, bs_s, dsc_s);
+            const uint32_t slot0 = ring0 + cstage * R * SLOT;
+            mbar_wait(bar0 + 8 * cstage, cphase);
+            if (full) {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (r < nv) acc[r] += consume<MASK, true>(type, slot0 + r * SLOT, lane, 32, GGB_TILE_SB, A, L);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (r < nv) acc[r] += consume<MASK, false>(type, slot0 + r * SLOT, lane, U, nsb_last, A, L);
+            }
+            if (++cstage == STEPS) { cstage = 0; cphase ^= 1; }
+            // the stage is free again: refill it (lane 0) once every lane's reads have been issued
+            __syncwarp();
+            if (lane == 0 && ip < npairs) issue_step();
         }
-        const int nx2 = item + 2 * GEMV_NW;
-        if (nx2 < nitems) { locate(nx2, type0, tb0, U0, nsb0, t0); load_item<MASK>(w0, type0, tb0, U0, nsb0, lane); }
-        if (nx < nitems) {
-            double p = compute_item<MASK>(w1, type1, t1 * 32 + lane, lane < U1, qs, bsums, dsc);
-            p = warp_sum_f64(p);
-            if (lane == 0) partial[nx] = p;
+        // butterfly reduction of the group: after log2(R) exchange levels each lane holds ONE row's partial,
+        // then the remaining levels finish all R rows at once.  Row r ends up in lane r * (32 / R).
+        {
+            if constexpr (R == 4) {
+            const bool up16 = lane & 16, up8 = lane & 8;
+            double k0 = up16 ? acc[2] : acc[0], k1 = up16 ? acc[3] : acc[1];
+            const double s0 = up16 ? acc[0] : acc[2], s1 = up16 ? acc[1] : acc[3];
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            double keep = up8 ? k1 : k0;
+            const double send = up8 ? k0 : k1;
+            keep += __shfl_xor_sync(0xffffffffu, send, 8);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+            const int r = lane >> 3;
+            if ((lane & 7) == 0 && r < nv) rowv[lr + r] = (float)keep;   /* the only rounding of the accumulated sum */
+            } else {
+            const bool up = lane & 16;
+            const double send = up ? acc[0] : acc[1];
+            double keep = up ? acc[1] : acc[0];
+            keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+            const int r = lane >> 4;
+            if ((lane & 15) == 0 && r < nv) rowv[lr + r] = (float)keep;
+            }
         }
     }
     __syncthreads();
+    TL_STAMP(4);
 
     // ---- epilogue
-    auto rowval = [&](int lr) {
-        double v = 0.0;
-        for (int t = 0; t < T; t++) v += partial[lr * T + t];
-        return (float)v; /* the only rounding of the accumulated sum */
-    };
     if (P.epi == GGB_EPI_STORE) {
         for (int lr = tid; lr < nloc; lr += GEMV_THREADS) {
-            int s = 0, l = lr;
-            if (l >= cnt[0]) { l -= cnt[0]; s = 1; if (l >= cnt[1]) { l -= cnt[1]; s = 2; } }
-            P.seg[s].y[r0[s] + l] = rowval(lr);
+            if (lr < cnt0) P.seg[0].y[r0_0 + lr] = rowv[lr];
+            else if (lr < cnt0 + cnt1) P.seg[1].y[r0_1 + lr - cnt0] = rowv[lr];
+            else P.seg[2].y[r0_2 + lr - cnt0 - cnt1] = rowv[lr];
         }
     } else if (P.epi == GGB_EPI_RESIDUAL) {
-        for (int lr = tid; lr < cnt[0]; lr += GEMV_THREADS) {
-            const int r = r0[0] + lr;
-            P.seg[0].y[r] = P.residual[r] + rowval(lr);
+        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {
+            const int r = r0_0 + lr;
+            P.seg[0].y[r] = __fadd_rn(lr == tid ? res_pre : P.residual[r], rowv[lr]);
         }
     } else if (P.epi == GGB_EPI_SWIGLU) {
-        for (int lr = tid; lr < cnt[0]; lr += GEMV_THREADS) {
-            const float g = rowval(lr), u = rowval(cnt[0] + lr);
-            P.seg[0].y[r0[0] + lr] = silu_mul_ref(g, u);
-        }
+        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) P.seg[0].y[r0_0 + lr] = silu_mul_ref(rowv[lr], rowv[cnt0 + lr]);
     } else if (P.epi == GGB_EPI_ROPE_KV) {
         const int pos = *P.pos_dev;
         const float* tab = P.rope_tab + (int64_t)pos * P.n_rot; /* [n_rot/2][2] */
         const int npair = nloc >> 1;
         for (int pr = tid; pr < npair; pr += GEMV_THREADS) {
-            int s = 0, l = 2 * pr;
-            if (l >= cnt[0]) { l -= cnt[0]; s = 1; if (l >= cnt[1]) { l -= cnt[1]; s = 2; } }
-            const int r = r0[s] + l;
-            float v0 = rowval(2 * pr), v1 = rowval(2 * pr + 1);
+            int s = 0, l = 2 * pr, r;
+            if (l < cnt0) r = r0_0 + l;
+            else if (l < cnt0 + cnt1) { s = 1; r = r0_1 + l - cnt0; }
+            else { s = 2; r = r0_2 + l - cnt0 - cnt1; }
+            float v0 = rowv[2 * pr], v1 = rowv[2 * pr + 1];
             if (s < 2) {
                 const int j = r % P.head_dim;
                 if (j < P.n_rot) {
-                    const float c = tab[j], sn = tab[j + 1];  /* pair index j/2 -> floats 2*(j/2) = j */
+                    const float cs = tab[j], sn = tab[j + 1];  /* pair index j/2 -> floats 2*(j/2) = j */
                     const float a = v0, b = v1;
-                    v0 = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, sn));
-                    v1 = __fadd_rn(__fmul_rn(a, sn), __fmul_rn(b, c));
+                    v0 = __fsub_rn(__fmul_rn(a, cs), __fmul_rn(b, sn));
+                    v1 = __fadd_rn(__fmul_rn(a, sn), __fmul_rn(b, cs));
                 }
             }
             if (s == 0) { P.seg[0].y[r] = v0; P.seg[0].y[r + 1] = v1; }
@@ -350,9 +583,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
     } else if (P.epi == GGB_EPI_ARGMAX) {
         float bv = -FLT_MAX;
         int bi = 0x7fffffff;
-        for (int lr = tid; lr < cnt[0]; lr += GEMV_THREADS) {
-            const float v = rowval(lr);
-            const int r = r0[0] + lr;
+        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {
+            const float v = rowv[lr];
+            const int r = r0_0 + lr;
             if (P.seg[0].y) P.seg[0].y[r] = v;
             argmax_comb(bv, bi, v, r);
         }
@@ -366,14 +599,28 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
             P.part_idx[blockIdx.x] = bi;
         }
     }
+    TL_STAMP(5);
 }
+
+#ifdef GGB_TIMELINE
+static unsigned g_tl_counter = 0;
+extern "C" int ggb_debug_timeline(unsigned long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, ggb_tl, sizeof(unsigned long long) * 8 * 1024 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 // ------------------------------------------------------------------ host side
 static int act_class(int type) { return type == GGB_TYPE_Q8_0 ? 1 : 0; }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 static int default_grid(const ggb_gemv_args* a) {
     if (a->grid > 0) return a->grid;
-    return ggb_num_sms();
+    static int per_sm = env_int("GGB_GEMV_CTAS_PER_SM", 1);
+    return ggb_num_sms() * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
 }
 
 extern "C" int ggb_gemv_grid(const ggb_gemv_args* a) {
@@ -381,14 +628,14 @@ extern "C" int ggb_gemv_grid(const ggb_gemv_args* a) {
     return default_grid(a);
 }
 
-template <int MASK>
+#define GEMV_MAX_SMEM (200 * 1024)
+
+template <int MASK, int R, int STEPS>
 static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
     static bool attr_done = false;
-    static size_t attr_smem = 0;
-    if (!attr_done || smem > attr_smem) {
-        GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (!attr_done) {
+        GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK, R, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMV_MAX_SMEM));
         attr_done = true;
-        attr_smem = 160 * 1024;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -400,7 +647,7 @@ static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_kernel<MASK>, P));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_kernel<MASK, R, STEPS>, P));
     return GGB_OK;
 }
 
@@ -412,7 +659,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     if (((uintptr_t)a->x & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: x must be 16-byte aligned");
     if (a->prologue == GGB_PRO_RMSNORM && (!a->norm_w || ((uintptr_t)a->norm_w & 15))) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: RMSNORM prologue needs a 16-byte aligned norm_w");
     GemvK P = {};
-    int mask = 0, cls = -1;
+    int mask = 0, cls = -1, max_tile = 0;
     int64_t total_rows = 0;
     for (int s = 0; s < a->n_seg; s++) {
         const ggb_gemv_seg& g = a->seg[s];
@@ -434,6 +681,8 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
         P.seg[s].type = g.type;
         P.seg[s].rows = g.rows;
         total_rows += g.rows;
+        const int tile = ggb_sb_bytes(g.type) * (a->k >= GGB_TILE_ELEMS ? GGB_TILE_SB : a->k / 256);
+        if (tile > max_tile) max_tile = tile;
     }
     switch (a->epilogue) {
         case GGB_EPI_STORE:
@@ -461,17 +710,31 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     P.x = a->x; P.norm_w = a->norm_w; P.eps = a->eps; P.residual = a->residual;
     P.pos_dev = a->pos_dev; P.rope_tab = a->rope_tab; P.n_rot = a->n_rot; P.head_dim = a->head_dim;
     P.kcache = a->kcache; P.vcache = a->vcache; P.part_val = a->part_val; P.part_idx = a->part_idx;
+    // ring geometry: RING_SLOTS slots sized for the largest tile of the launch
+    P.slot_bytes = (max_tile + 15) & ~15;
+    const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;
+    P.n_slots = R * STEPS;
+    P.ring_bytes = P.n_slots * P.slot_bytes;
+#ifdef GGB_TIMELINE
+    P.tl_slot = g_tl_counter++;
+#endif
+    static int l2pf = env_int("GGB_L2_PREFETCH", 0);
+    P.l2_prefetch = l2pf;
     const int grid = default_grid(a);
+    for (int s = 0; s < a->n_seg; s++) { P.rq[s] = a->seg[s].rows / grid; P.rr[s] = a->seg[s].rows % grid; }
     int64_t max_local = 0;
-    for (int s = 0; s < a->n_seg; s++) max_local += (a->seg[s].rows + grid - 1) / grid + 2;
-    const size_t smem = (size_t)a->k + a->k / 8 + a->k / 8 + (size_t)max_local * P.T * sizeof(double);
-    if (smem > 160 * 1024) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
+    for (int s = 0; s < a->n_seg; s++) max_local += (a->seg[s].rows + grid - 1) / grid + 2 * GEMV_MAX_R;
+    size_t off = (size_t)GEMV_NW * P.ring_bytes + (size_t)a->k + a->k / 8 + a->k / 8;
+    off = (off + 15) & ~(size_t)15;
+    P.rowv_off = (int)off;
+    const size_t smem = off + (size_t)max_local * sizeof(float);
+    if (smem > GEMV_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
     cudaStream_t st = (cudaStream_t)stream;
     switch (mask) {
-        case 1: return launch<1>(P, grid, smem, a->use_pdl, st);
-        case 2: return launch<2>(P, grid, smem, a->use_pdl, st);
-        case 3: return launch<3>(P, grid, smem, a->use_pdl, st);
-        case 4: return launch<4>(P, grid, smem, a->use_pdl, st);
+        case 1: return launch<1, 4, 2>(P, grid, smem, a->use_pdl, st);
+        case 2: return launch<2, 4, 2>(P, grid, smem, a->use_pdl, st);
+        case 3: return launch<3, 2, 3>(P, grid, smem, a->use_pdl, st);
+        case 4: return launch<4, 2, 2>(P, grid, smem, a->use_pdl, st);
         default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: unsupported type mix (mask %d)", mask);
     }
 }

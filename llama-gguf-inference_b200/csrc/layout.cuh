@@ -8,7 +8,10 @@
 //
 //   Q4_K tile (144*nsb B):  Q0[u] 16 B | Q1[u] 16 B | HDR[sb] 16 B            u = 4*sb + g, U = 4*nsb
 //       canonical 32-byte group g of block sb = {sub-block 2g in low nibbles, 2g+1 in high nibbles};
-//       Q0[u] = its bytes 0..15, Q1[u] = bytes 16..31; HDR[sb] = {f16 d, f16 dmin, u8 scales[12]}.
+//       Q0[u] = its bytes 0..15, Q1[u] = bytes 16..31; HDR[sb] = {f16 d, f16 dmin, 4 x 24-bit fields}:
+//       field g = sc[2g] | sc[2g+1] << 6 | min[2g] << 12 | min[2g+1] << 18 -- the same sixteen 6-bit values as the
+//       canonical 12 scale bytes (gguf/quants.py:478-502), regrouped so that lane u = 4*sb + g extracts the four
+//       it needs with one byte-permute and three shifts instead of ~20 bit operations.
 //       unit u covers elements 64u .. 64u+63 of the tile.
 //   Q6_K tile (210*nsb B):  QLA[u] | QLB[u] | QH[u] (16 B each) | SC[sb] 16 B | D[sb] 2 B
 //       u = 4*sb + 2*n + t (n = 128-element half, t = 16-element column); with l = 16t..16t+15:
@@ -50,6 +53,28 @@ GGB_HD int ggb_tile_nsb(int64_t k, int t) { /* super-blocks in tile t */
     return nsb > GGB_TILE_SB ? GGB_TILE_SB : (int)nsb;
 }
 
+// canonical 6-bit (scale, min) of sub-block j from the 12 packed scale bytes (gguf/quants.py:478-502)
+GGB_HD void ggb_k4_scale_min(int j, const uint8_t* s, int* sc, int* mn) {
+    if (j < 4) { *sc = s[j] & 63; *mn = s[j + 4] & 63; }
+    else { *sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4); *mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4); }
+}
+// byte i (0..11) of the re-encoded scale area of a tile-SoA Q4_K/Q5_K header
+GGB_HD uint8_t ggb_hdr2_byte(const uint8_t* canon_scales, int i) {
+    const int g = i / 3;
+    int s0, m0, s1, m1;
+    ggb_k4_scale_min(2 * g, canon_scales, &s0, &m0);
+    ggb_k4_scale_min(2 * g + 1, canon_scales, &s1, &m1);
+    const uint32_t f = (uint32_t)s0 | ((uint32_t)s1 << 6) | ((uint32_t)m0 << 12) | ((uint32_t)m1 << 18);
+    return (uint8_t)(f >> (8 * (i - 3 * g)));
+}
+// (scale, min) of sub-block j from a tile-SoA header
+GGB_HD void ggb_hdr2_scale_min(const uint8_t* hdr, int j, int* sc, int* mn) {
+    const uint8_t* p = hdr + 4 + 3 * (j >> 1);
+    const uint32_t f = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    *sc = (f >> (6 * (j & 1))) & 63;
+    *mn = (f >> (12 + 6 * (j & 1))) & 63;
+}
+
 // byte offset inside the CANONICAL row for the byte at offset `o` inside the REPACKED row (o < canonical row
 // bytes).  Used by the repack kernel (one thread per 2 bytes: every field boundary in both layouts is even).
 GGB_HD int64_t ggb_repacked_to_canon(int type, int64_t k, int64_t o) {
@@ -73,6 +98,7 @@ GGB_HD int64_t ggb_repacked_to_canon(int type, int64_t k, int64_t o) {
             if (o3 < 8 * U) return -1; /* QHU is bit-gathered, not a byte permutation: handled by the kernel */
             o3 -= 8 * U;
         }
+        if ((o3 & 15) >= 4) return -2; /* re-encoded 6-bit scales/mins: computed by the repack kernel */
         return (sb0 + (o3 >> 4)) * sbb + (o3 & 15);
     }
     if (type == GGB_TYPE_Q6_K) {

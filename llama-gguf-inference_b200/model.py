@@ -126,7 +126,8 @@ class Engine:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
         canon = self._upload(name)
         stride = self.lib.ggb_repacked_row_stride(ti.ggml_type, k)
-        dst = torch.empty(rows * stride, dtype=torch.uint8, device=self.dev)
+        # +16: the GEMV's bulk copies round a partial last tile up to 16 bytes
+        dst = torch.zeros(rows * stride + 16, dtype=torch.uint8, device=self.dev)
         cabi.check(self.lib.ggb_repack(ti.ggml_type, canon.data_ptr(), dst.data_ptr(), rows, k, self._sptr()), f"repack {name}")
         torch.cuda.current_stream().synchronize()
         del canon

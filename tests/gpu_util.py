@@ -35,7 +35,7 @@ def gpu_repack(qtype: int, raw: np.ndarray, rows: int, k: int) -> torch.Tensor:
     stride = L.ggb_repacked_row_stride(qtype, k)
     assert stride > 0
     src = to_dev(raw.reshape(-1))
-    dst = torch.empty(rows * stride, dtype=torch.uint8, device=DEV)
+    dst = torch.zeros(rows * stride + 16, dtype=torch.uint8, device=DEV)  # +16: bulk copies round the last tile up
     cabi.check(L.ggb_repack(qtype, src.data_ptr(), dst.data_ptr(), rows, k, stream_ptr()), "ggb_repack")
     sync()
     return dst
