@@ -82,9 +82,222 @@ class Weight:
         return self.t.data_ptr()
 
 
+class Slot:
+    """One sequence: KV cache, activations, device-side counters and the captured graphs that advance it."""
+
+    def __init__(self, eng: "Engine", index: int):
+        self.eng, self.index = eng, index
+        torch, hp, dev = eng.torch, eng.hp, eng.dev
+        self.torch, self.lib, self.hp = torch, eng.lib, hp
+        self.n_ctx, self.max_new, self.use_pdl = eng.n_ctx, eng.max_new, eng.use_pdl
+        self.stream = eng.stream
+        kvd = hp.n_kv * hp.head_dim
+        self.kc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
+        self.vc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
+        f32 = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
+        i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)  # noqa: E731
+        self.x, self.q, self.attn = f32(hp.d), f32(hp.n_head * hp.head_dim), f32(hp.n_head * hp.head_dim)
+        self.h, self.logits = f32(hp.ff), f32(hp.vocab)
+        self.attn_ws = torch.zeros(max(16, self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim)), dtype=torch.uint8, device=dev)
+        self.tok_dev, self.pos_dev, self.step_dev = i32(1), i32(1), i32(1)
+        self.out_tokens = i32(self.max_new)
+        self.part_val, self.part_idx = f32(1), i32(1)
+        a = self._head_args()
+        self.n_part = self.lib.ggb_gemv_grid(C.byref(a))
+        self.part_val, self.part_idx = f32(self.n_part), i32(self.n_part)
+        self.host_i32 = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.host_logits = None
+        self._graphs = {}
+        self._build_args()
+        self.n_past = 0   # host mirror of the number of positions held in the KV cache
+
+    # ------------------------------------------------------------------ launch descriptions
+    def _head_args(self):
+        hp, e = self.hp, self.eng
+        return cabi.make_gemv_args(
+            [(e.w_out.ptr, e.w_out.type, e.w_out.rows, self.logits.data_ptr())], hp.d, self.x.data_ptr(),
+            prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ARGMAX, norm_w=e.out_norm.data_ptr(), eps=hp.eps,
+            use_pdl=self.use_pdl, part_val=self.part_val.data_ptr(), part_idx=self.part_idx.data_ptr())
+
+    def _build_args(self):
+        hp, e = self.hp, self.eng
+        self._layer_args = []
+        for i, L in enumerate(e.layers):
+            qkv = cabi.make_gemv_args(
+                [(L["wq"].ptr, L["wq"].type, L["wq"].rows, self.q.data_ptr()),
+                 (L["wk"].ptr, L["wk"].type, L["wk"].rows, 0),
+                 (L["wv"].ptr, L["wv"].type, L["wv"].rows, 0)],
+                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ROPE_KV,
+                norm_w=L["attn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, pos_dev=self.pos_dev.data_ptr(),
+                rope_tab=e.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
+                kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
+            o = cabi.make_gemv_args(
+                [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.x.data_ptr())], L["wo"].k, self.attn.data_ptr(),
+                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+            gu = cabi.make_gemv_args(
+                [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
+                 (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
+                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_SWIGLU,
+                norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
+            dn = cabi.make_gemv_args(
+                [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.x.data_ptr())], L["wd"].k, self.h.data_ptr(),
+                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+            self._layer_args.append((qkv, o, gu, dn))
+        self._head = self._head_args()
+
+    # ------------------------------------------------------------------ enqueue
+    def _enqueue_embed(self, s: int):
+        e = self.eng
+        cabi.check(self.lib.ggb_embed_row(e.emb_type, e.emb_canon.data_ptr(), self.hp.d, self.tok_dev.data_ptr(),
+                                          self.x.data_ptr(), s), "embed_row")
+
+    def _enqueue_layers(self, s: int):
+        hp, lib = self.hp, self.lib
+        for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
+            cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
+            cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                                           self.pos_dev.data_ptr(), hp.n_head, hp.n_kv, hp.head_dim, self.n_ctx,
+                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self.use_pdl, s), "attn_decode")
+            cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
+            cabi.check(lib.ggb_gemv(C.byref(gu), s), "gemv gate/up")
+            cabi.check(lib.ggb_gemv(C.byref(dn), s), "gemv down")
+
+    def _enqueue_head(self, s: int):
+        lib, e = self.lib, self.eng
+        cabi.check(lib.ggb_gemv(C.byref(self._head), s), "gemv head")
+        cabi.check(lib.ggb_argmax_next(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
+                                       self.tok_dev.data_ptr(), self.pos_dev.data_ptr(), self.step_dev.data_ptr(),
+                                       self.out_tokens.data_ptr(), self.max_new, e.emb_type,
+                                       e.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
+
+    def _run(self, kind: str):
+        """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head)."""
+        torch = self.torch
+
+        def body(s):
+            if kind != "decode":
+                self._enqueue_embed(s)
+            self._enqueue_layers(s)
+            if kind != "prompt":
+                self._enqueue_head(s)
+
+        if not self.eng.use_graph:
+            body(self.stream.cuda_stream)
+            return
+        g = self._graphs.get(kind)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                body(torch.cuda.current_stream().cuda_stream)
+            self._graphs[kind] = g
+        g.replay()
+
+    # ------------------------------------------------------------------ sequence API
+    def reset(self):
+        with self.torch.cuda.stream(self.stream):
+            self.pos_dev.zero_()
+            self.step_dev.zero_()
+        self.n_past = 0
+
+    def _set_tok_pos(self, tok: int, pos: int):
+        self.host_i32[0] = tok
+        self.host_i32[1] = pos
+        self.tok_dev.copy_(self.host_i32[0:1], non_blocking=True)
+        self.pos_dev.copy_(self.host_i32[1:2], non_blocking=True)
+
+    def warmup(self):
+        """Run every graph once (sets kernel attributes, captures graphs), then clear the state."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            graph = self.eng.use_graph
+            self.eng.use_graph = False
+            self._set_tok_pos(0, 0)
+            self._run("prompt_last")
+            self.stream.synchronize()
+            self.eng.use_graph = graph
+            if graph:
+                for kind in ("prompt", "prompt_last", "decode"):
+                    self._set_tok_pos(0, 0)
+                    self._run(kind)
+                self.stream.synchronize()
+        self.reset()
+
+    def prefill(self, tokens: list[int], start_pos: int | None = None):
+        """Feed tokens at positions start_pos.. (default: append).  v1 runs them one by one through the decode
+        kernels; the last one also runs the head, which emits the first generated token (greedy) and the logits."""
+        if not tokens:
+            raise ValueError("empty prompt")
+        start = self.n_past if start_pos is None else start_pos
+        if start + len(tokens) >= self.n_ctx:
+            raise ValueError(f"prompt of {len(tokens)} tokens does not fit the context ({self.n_ctx})")
+        with self.torch.cuda.stream(self.stream):
+            for i, t in enumerate(tokens):
+                self._set_tok_pos(int(t), start + i)
+                self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
+                self.stream.synchronize()  # host_i32 is reused for the next token
+        self.n_past = start + len(tokens)
+
+    def decode(self, n_steps: int):
+        """Enqueue n greedy decode steps (no host synchronisation); tokens land in out_tokens."""
+        if self.n_past + n_steps >= self.n_ctx + 1:
+            raise ValueError("context window exhausted")
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(n_steps):
+                self._run("decode")
+        self.n_past += n_steps
+
+    def feed(self, tok: int):
+        """Sampled decoding: the host chose `tok`; run it through the model and produce logits."""
+        self.prefill([tok])
+
+    def read_last_token(self) -> int:
+        """Device -> pinned host read of the newest greedy token (what a streaming server does per step)."""
+        with self.torch.cuda.stream(self.stream):
+            self.host_tok.copy_(self.tok_dev, non_blocking=True)
+        self.stream.synchronize()
+        return int(self.host_tok[0])
+
+    def read_logits(self) -> np.ndarray:
+        if self.host_logits is None:
+            self.host_logits = self.torch.zeros(self.hp.vocab, dtype=self.torch.float32).pin_memory()
+        with self.torch.cuda.stream(self.stream):
+            self.host_logits.copy_(self.logits, non_blocking=True)
+        self.stream.synchronize()
+        return self.host_logits.numpy()
+
+    def tokens(self, n: int) -> list[int]:
+        self.stream.synchronize()
+        return self.out_tokens[:n].cpu().tolist()
+
+    def generate(self, prompt: list[int], n_new: int, stream_cb=None) -> list[int]:
+        """Greedy generation.  With stream_cb the newest token is read back after every step (streaming);
+        otherwise all steps are enqueued back-to-back and read once."""
+        if len(prompt) + n_new >= self.n_ctx:
+            raise ValueError("prompt + n_new exceeds the context window")
+        self.reset()
+        self.prefill(prompt)
+        if stream_cb is None:
+            self.decode(n_new - 1)
+            return self.tokens(n_new)
+        out = [self.read_last_token()]
+        stream_cb(out[-1])
+        for _ in range(n_new - 1):
+            self.decode(1)
+            out.append(self.read_last_token())
+            stream_cb(out[-1])
+        return out
+
+    def last_logits(self) -> np.ndarray:
+        self.stream.synchronize()
+        return self.logits.cpu().numpy()
+
+
 class Engine:
+    """Weights in HBM + n_slots independent sequences.  The single-sequence methods act on slot 0."""
+
     def __init__(self, path: str, n_ctx: int = 4096, device: int = 0, use_graph: bool = True, use_pdl: bool = True,
-                 max_new: int = 65536, verbose: bool = False):
+                 max_new: int = 65536, verbose: bool = False, n_slots: int = 1):
         import torch
 
         if not torch.cuda.is_available():
@@ -102,8 +315,7 @@ class Engine:
         t0 = time.time()
         self._load_weights()
         self.load_seconds = time.time() - t0
-        self._alloc_state()
-        self._graphs = {}
+        self.slots = [Slot(self, i) for i in range(max(1, n_slots))]
         if verbose:
             print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
 
@@ -113,8 +325,8 @@ class Engine:
 
     def _upload(self, name: str):
         torch = self.torch
-        raw = self.file.data(name)
-        return torch.from_numpy(np.asarray(raw)).to(self.dev, non_blocking=False)
+        raw = np.array(self.file.data(name))  # copy: torch refuses read-only mmap views
+        return torch.from_numpy(raw).to(self.dev, non_blocking=False)
 
     def _load_matrix(self, name: str) -> Weight:
         torch = self.torch
@@ -171,202 +383,52 @@ class Engine:
             ff = self._load_f32("rope_freqs.weight").cpu().numpy()
         self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
 
-    # ------------------------------------------------------------------ state
-    def _alloc_state(self):
-        torch, hp = self.torch, self.hp
-        dev = self.dev
-        kvd = hp.n_kv * hp.head_dim
-        self.kc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
-        self.vc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
-        f32 = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
-        self.x = f32(hp.d)
-        self.q = f32(hp.n_head * hp.head_dim)
-        self.attn = f32(hp.n_head * hp.head_dim)
-        self.h = f32(hp.ff)
-        self.logits = f32(hp.vocab)
-        self.attn_ws = torch.zeros(self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim), dtype=torch.uint8, device=dev)
-        i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)  # noqa: E731
-        self.tok_dev, self.pos_dev, self.step_dev = i32(1), i32(1), i32(1)
-        self.out_tokens = i32(self.max_new)
-        # arg-max partials: one per GEMV CTA
-        a = self._head_args()
-        self.n_part = self.lib.ggb_gemv_grid(C.byref(a))
-        self.part_val, self.part_idx = f32(self.n_part), i32(self.n_part)
-        self.host_i32 = torch.zeros(4, dtype=torch.int32).pin_memory()
-        self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
-
-    # ------------------------------------------------------------------ launch descriptions
-    def _head_args(self):
-        hp = self.hp
-        return cabi.make_gemv_args(
-            [(self.w_out.ptr, self.w_out.type, self.w_out.rows, self.logits.data_ptr())], hp.d, self.x.data_ptr(),
-            prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ARGMAX, norm_w=self.out_norm.data_ptr(), eps=hp.eps,
-            use_pdl=self.use_pdl, part_val=getattr(self, "part_val", self.x).data_ptr(),
-            part_idx=getattr(self, "part_idx", self.x).data_ptr())
-
-    def _build_args(self):
-        hp = self.hp
-        self._layer_args = []
-        for i, L in enumerate(self.layers):
-            qkv = cabi.make_gemv_args(
-                [(L["wq"].ptr, L["wq"].type, L["wq"].rows, self.q.data_ptr()),
-                 (L["wk"].ptr, L["wk"].type, L["wk"].rows, 0),
-                 (L["wv"].ptr, L["wv"].type, L["wv"].rows, 0)],
-                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ROPE_KV,
-                norm_w=L["attn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, pos_dev=self.pos_dev.data_ptr(),
-                rope_tab=self.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
-                kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
-            o = cabi.make_gemv_args(
-                [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.x.data_ptr())], L["wo"].k, self.attn.data_ptr(),
-                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
-            gu = cabi.make_gemv_args(
-                [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
-                 (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
-                hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_SWIGLU,
-                norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
-            dn = cabi.make_gemv_args(
-                [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.x.data_ptr())], L["wd"].k, self.h.data_ptr(),
-                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
-            self._layer_args.append((qkv, o, gu, dn))
-        self._head = self._head_args()
-
     def launches_per_step(self) -> int:
         """kernels of libggufb200 launched by one decode step (layers + head)."""
         return self.hp.n_layer * 5 + 3
 
-    # ------------------------------------------------------------------ enqueue
-    def _enqueue_embed(self, s: int):
-        cabi.check(self.lib.ggb_embed_row(self.emb_type, self.emb_canon.data_ptr(), self.hp.d, self.tok_dev.data_ptr(),
-                                          self.x.data_ptr(), s), "embed_row")
-
-    def _enqueue_layers(self, s: int):
-        hp, lib = self.hp, self.lib
-        for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
-            cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
-            cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
-                                           self.pos_dev.data_ptr(), hp.n_head, hp.n_kv, hp.head_dim, self.n_ctx,
-                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self.use_pdl, s), "attn_decode")
-            cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
-            cabi.check(lib.ggb_gemv(C.byref(gu), s), "gemv gate/up")
-            cabi.check(lib.ggb_gemv(C.byref(dn), s), "gemv down")
-
-    def _enqueue_head(self, s: int):
-        lib = self.lib
-        cabi.check(lib.ggb_gemv(C.byref(self._head), s), "gemv head")
-        cabi.check(lib.ggb_argmax_next(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
-                                       self.tok_dev.data_ptr(), self.pos_dev.data_ptr(), self.step_dev.data_ptr(),
-                                       self.out_tokens.data_ptr(), self.max_new, self.emb_type,
-                                       self.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
-
-    def _run(self, kind: str):
-        """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head)."""
-        torch = self.torch
-        if not hasattr(self, "_layer_args"):
-            self._build_args()
-
-        def body(s):
-            if kind != "decode":
-                self._enqueue_embed(s)
-            self._enqueue_layers(s)
-            if kind != "prompt":
-                self._enqueue_head(s)
-
-        if not self.use_graph:
-            body(self.stream.cuda_stream)
-            return
-        g = self._graphs.get(kind)
-        if g is None:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
-                body(torch.cuda.current_stream().cuda_stream)
-            self._graphs[kind] = g
-            return self._run_graph_after_capture(g)
-        g.replay()
-
-    def _run_graph_after_capture(self, g):
-        g.replay()  # capture does not execute; run it once for real
-
-    # ------------------------------------------------------------------ public API
-    def reset(self):
-        with self.torch.cuda.stream(self.stream):
-            self.pos_dev.zero_()
-            self.step_dev.zero_()
-
-    def _set_tok_pos(self, tok: int, pos: int):
-        self.host_i32[0] = tok
-        self.host_i32[1] = pos
-        self.tok_dev.copy_(self.host_i32[0:1], non_blocking=True)
-        self.pos_dev.copy_(self.host_i32[1:2], non_blocking=True)
+    # ------------------------------------------------------------------ single-sequence convenience (slot 0)
+    @property
+    def _s0(self) -> Slot:
+        return self.slots[0]
 
     def warmup(self):
-        """Run every graph once (sets kernel attributes, captures graphs), then clear the state."""
-        torch = self.torch
-        with torch.cuda.stream(self.stream):
-            graph = self.use_graph
-            self.use_graph = False
-            self._set_tok_pos(0, 0)
-            self._run("prompt_last")
-            self.stream.synchronize()
-            self.use_graph = graph
-            if graph:
-                for kind in ("prompt", "prompt_last", "decode"):
-                    self._set_tok_pos(0, 0)
-                    self._run(kind)
-                self.stream.synchronize()
-        self.reset()
+        for s in self.slots:
+            s.warmup()
 
-    def prefill(self, tokens: list[int], start_pos: int = 0):
-        """Feed the prompt (v1: token by token through the decode kernels); the last token also runs the head,
-        which emits the first generated token and leaves pos = start_pos + len(tokens)."""
-        if not tokens:
-            raise ValueError("empty prompt")
-        if start_pos + len(tokens) >= self.n_ctx:
-            raise ValueError(f"prompt of {len(tokens)} tokens does not fit the context ({self.n_ctx})")
-        with self.torch.cuda.stream(self.stream):
-            for i, t in enumerate(tokens):
-                self._set_tok_pos(int(t), start_pos + i)
-                self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
-                self.stream.synchronize()  # host_i32 is reused for the next token
+    def reset(self):
+        self._s0.reset()
+
+    def prefill(self, tokens, start_pos=None):
+        self._s0.prefill(tokens, start_pos)
 
     def decode(self, n_steps: int):
-        """Enqueue n decode steps (no host synchronisation); tokens land in out_tokens."""
-        with self.torch.cuda.stream(self.stream):
-            for _ in range(n_steps):
-                self._run("decode")
+        self._s0.decode(n_steps)
 
     def read_last_token(self) -> int:
-        """Device -> pinned host read of the newest token (what a streaming server does per step)."""
-        with self.torch.cuda.stream(self.stream):
-            self.host_tok.copy_(self.tok_dev, non_blocking=True)
-        self.stream.synchronize()
-        return int(self.host_tok[0])
+        return self._s0.read_last_token()
 
-    def tokens(self, n: int) -> list[int]:
-        self.stream.synchronize()
-        return self.out_tokens[:n].cpu().tolist()
+    def tokens(self, n: int):
+        return self._s0.tokens(n)
 
-    def generate(self, prompt: list[int], n_new: int, stream_cb=None) -> list[int]:
-        """Greedy generation.  With stream_cb the newest token is read back after every step (streaming);
-        otherwise all steps are enqueued back-to-back and read once."""
-        if len(prompt) + n_new >= self.n_ctx:
-            raise ValueError("prompt + n_new exceeds the context window")
-        self.reset()
-        self.prefill(prompt)
-        if stream_cb is None:
-            self.decode(n_new - 1)
-            return self.tokens(n_new)
-        out = [self.read_last_token()]
-        stream_cb(out[-1])
-        for _ in range(n_new - 1):
-            self.decode(1)
-            out.append(self.read_last_token())
-            stream_cb(out[-1])
-        return out
+    def generate(self, prompt, n_new, stream_cb=None):
+        return self._s0.generate(prompt, n_new, stream_cb)
 
-    def last_logits(self) -> np.ndarray:
-        self.stream.synchronize()
-        return self.logits.cpu().numpy()
+    def last_logits(self):
+        return self._s0.last_logits()
+
+    @property
+    def _layer_args(self):
+        return self._s0._layer_args
+
+    @property
+    def _head(self):
+        return self._s0._head
+
+    def _set_tok_pos(self, tok, pos):
+        self._s0._set_tok_pos(tok, pos)
 
     def close(self):
-        self._graphs.clear()
+        for s in self.slots:
+            s._graphs.clear()
         self.file.close()

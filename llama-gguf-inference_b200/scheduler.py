@@ -1,0 +1,222 @@
+"""Slot scheduler: maps concurrent completion requests onto the engine's sequence slots.
+
+Stands in for llama-server's slot / continuous-batching loop [UPSTREAM-MEM: tools/server/server.cpp]: requests
+queue up, each free slot takes one, prompt tokens are fed, and every scheduler tick advances each active slot by
+one token.  The gateway in front limits what arrives (`MAX_CONCURRENT_REQUESTS`, scripts/gateway.py:113,132);
+`/health` never touches this thread, so probes are answered while a generation runs (gateway.py:326-376).
+
+Greedy requests (temperature 0 / top_k 1) stay on the GPU: the arg-max kernel picks the token and the host only
+reads it back.  Other requests read the logits back and sample on the host (temperature, top-k, top-p, seed).
+
+The engine is duck-typed (`slots[i].reset/prefill/decode/read_last_token/feed/read_logits`), so the HTTP
+boundary can be tested on a CPU box with a stand-in engine.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+from collections import deque
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class SamplingParams:
+    temperature: float = 0.8
+    top_k: int = 40
+    top_p: float = 0.95
+    seed: int | None = None
+
+    @property
+    def greedy(self) -> bool:
+        return self.temperature <= 0.0 or self.top_k == 1
+
+
+@dataclass
+class Request:
+    prompt_ids: list
+    max_tokens: int
+    sampling: SamplingParams = field(default_factory=SamplingParams)
+    stop: list = field(default_factory=list)
+    ignore_eos: bool = False
+    events: "queue.Queue" = field(default_factory=queue.Queue)   # ("piece", text, token_id) | ("done", reason, usage) | ("error", msg)
+    cancelled: threading.Event = field(default_factory=threading.Event)
+    t_submit: float = field(default_factory=time.time)
+
+
+def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator) -> int:
+    """temperature -> top-k -> top-p -> multinomial, the default order of upstream's sampler chain [UPSTREAM-MEM]."""
+    if sp.greedy:
+        return int(np.argmax(logits))
+    x = logits.astype(np.float64) / max(sp.temperature, 1e-6)
+    k = sp.top_k if 0 < sp.top_k < x.size else x.size
+    idx = np.argpartition(x, -k)[-k:]
+    idx = idx[np.argsort(-x[idx], kind="stable")]
+    p = np.exp(x[idx] - x[idx[0]])
+    p /= p.sum()
+    if 0.0 < sp.top_p < 1.0:
+        keep = int(np.searchsorted(np.cumsum(p), sp.top_p) + 1)
+        idx, p = idx[:keep], p[:keep] / p[:keep].sum()
+    return int(idx[rng.choice(len(idx), p=p)])
+
+
+class _Active:
+    def __init__(self, req: Request, slot, tokenizer):
+        from .tokenizer import StreamDecoder
+        self.req, self.slot = req, slot
+        self.dec = StreamDecoder(tokenizer)
+        self.n_gen = 0
+        self.text = ""
+        self.sent = 0          # characters of self.text already emitted
+        self.rng = np.random.default_rng(req.sampling.seed)
+        self.t_first = None
+        self.t_start = time.time()
+
+
+class Scheduler(threading.Thread):
+    def __init__(self, engine, tokenizer, ignore_eos: bool = False, log=None):
+        super().__init__(daemon=True, name="ggufb200-scheduler")
+        self.engine, self.tok = engine, tokenizer
+        self.ignore_eos = ignore_eos
+        self.pending: deque[Request] = deque()
+        self.cv = threading.Condition()
+        self.active: dict[int, _Active] = {}
+        self.stop_flag = False
+        self.log = log or (lambda *a: None)
+        self.stats = {"requests": 0, "prompt_tokens": 0, "completion_tokens": 0, "decode_seconds": 0.0}
+        self.fatal: str | None = None
+
+    # ------------------------------------------------------------------ public
+    def submit(self, req: Request) -> Request:
+        with self.cv:
+            if self.fatal:
+                req.events.put(("error", self.fatal))
+                return req
+            self.pending.append(req)
+            self.cv.notify()
+        return req
+
+    def shutdown(self):
+        with self.cv:
+            self.stop_flag = True
+            self.cv.notify()
+
+    def idle_slots(self) -> int:
+        return len(self.engine.slots) - len(self.active)
+
+    # ------------------------------------------------------------------ loop
+    def run(self):
+        try:
+            while True:
+                with self.cv:
+                    while not self.stop_flag and not self.pending and not self.active:
+                        self.cv.wait()
+                    if self.stop_flag:
+                        break
+                    while self.pending and len(self.active) < len(self.engine.slots):
+                        req = self.pending.popleft()
+                        free = next(i for i in range(len(self.engine.slots)) if i not in self.active)
+                        self.active[free] = _Active(req, self.engine.slots[free], self.tok)
+                        self._start(free)
+                for i in list(self.active):
+                    self._step(i)
+        except Exception as e:  # a CUDA error is fatal: surface it to every waiter, then let the process die loudly
+            self.fatal = f"engine failure: {e!r}"
+            self.log(self.fatal)
+            for a in self.active.values():
+                a.req.events.put(("error", self.fatal))
+            with self.cv:
+                for r in self.pending:
+                    r.events.put(("error", self.fatal))
+                self.pending.clear()
+            raise
+
+    def _start(self, i: int):
+        a = self.active[i]
+        req, slot = a.req, a.slot
+        n_ctx = slot.n_ctx
+        if len(req.prompt_ids) + 1 >= n_ctx:
+            req.events.put(("error", f"the request exceeds the available context size ({len(req.prompt_ids)} prompt tokens, context {n_ctx})"))
+            del self.active[i]
+            return
+        req.max_tokens = max(0, min(req.max_tokens, n_ctx - len(req.prompt_ids) - 1))
+        slot.reset()
+        slot.prefill(req.prompt_ids)
+        self.stats["requests"] += 1
+        self.stats["prompt_tokens"] += len(req.prompt_ids)
+        a.t_decode0 = time.time()
+        if req.max_tokens == 0:
+            self._finish(i, "length")
+            return
+        self._emit(i, self._pick(a))
+
+    def _pick(self, a: _Active) -> int:
+        """token produced by the step that just ran"""
+        if a.req.sampling.greedy:
+            return a.slot.read_last_token()
+        return sample_token(a.slot.read_logits(), a.req.sampling, a.rng)
+
+    def _step(self, i: int):
+        a = self.active.get(i)
+        if a is None:
+            return
+        if a.req.cancelled.is_set():
+            self._finish(i, "cancelled")
+            return
+        if a.req.sampling.greedy:
+            a.slot.decode(1)
+        else:
+            a.slot.feed(a.last_tok)
+        self._emit(i, self._pick(a))
+
+    def _emit(self, i: int, tok: int):
+        a = self.active[i]
+        req = a.req
+        a.last_tok = tok
+        if a.t_first is None:
+            a.t_first = time.time()
+        if tok in self.tok.eog and not (req.ignore_eos or self.ignore_eos):
+            self._flush(a, final=True)
+            self._finish(i, "stop")
+            return
+        a.n_gen += 1
+        a.text += a.dec.push(tok)
+        # stop strings: hold back text that could be the beginning of one
+        hit = None
+        for s in req.stop:
+            j = a.text.find(s, max(0, a.sent - len(s)))
+            if j >= 0 and (hit is None or j < hit):
+                hit = j
+        if hit is not None:
+            a.text = a.text[:hit]
+            self._flush(a, final=True, tok=tok)
+            self._finish(i, "stop")
+            return
+        self._flush(a, final=False, tok=tok)
+        if a.n_gen >= req.max_tokens:
+            a.text += a.dec.flush()
+            self._flush(a, final=True, tok=tok)
+            self._finish(i, "length")
+
+    def _flush(self, a: _Active, final: bool, tok: int = -1):
+        hold = 0 if final else max((len(s) - 1 for s in a.req.stop), default=0)
+        upto = len(a.text) - hold
+        if upto > a.sent:
+            a.req.events.put(("piece", a.text[a.sent:upto], tok))
+            a.sent = upto
+        elif not final and not a.req.stop:
+            a.req.events.put(("piece", "", tok))   # token without printable text yet (partial UTF-8)
+
+    def _finish(self, i: int, reason: str):
+        a = self.active.pop(i)
+        dt = time.time() - getattr(a, "t_decode0", a.t_start)
+        self.stats["completion_tokens"] += a.n_gen
+        self.stats["decode_seconds"] += dt
+        usage = {"prompt_tokens": len(a.req.prompt_ids), "completion_tokens": a.n_gen,
+                 "total_tokens": len(a.req.prompt_ids) + a.n_gen}
+        timings = {"prompt_n": len(a.req.prompt_ids), "predicted_n": a.n_gen, "predicted_ms": dt * 1e3,
+                   "predicted_per_second": (a.n_gen / dt) if dt > 0 else 0.0,
+                   "ttft_ms": ((a.t_first or time.time()) - a.t_start) * 1e3}
+        a.req.events.put(("done", reason, usage, timings))

@@ -112,6 +112,9 @@ def weight_bytes_per_token(cfg: LlamaConfig, ftype: str) -> dict:
             "kv_per_pos": 2 * 2 * cfg.n_layer * cfg.n_kv * cfg.head_dim}
 
 
+N_SPECIAL = 3 + 256  # <unk> <s> </s> + byte-fallback tokens
+
+
 # ----------------------------------------------------------------------------- random packed blocks
 _UNIT_STD = {}  # dequantised std of a block whose f16 scale(s) are 1.0 (closed forms, uniform random fields)
 
@@ -161,11 +164,22 @@ def random_tensor(name: str, ne: tuple, tt: int, std, rng: np.random.Generator) 
     n = 1
     for x in ne:
         n *= x
-    return random_blocks(tt, n // G.GGML_TYPES[tt][1], std, rng)
+    raw = random_blocks(tt, n // G.GGML_TYPES[tt][1], std, rng)
+    if name == "output.weight":
+        # lm-head rows of the control and byte-fallback tokens get a zero scale: their logit is exactly 0, below
+        # the best of the thousands of random word logits, so greedy text is one leading-space word per token
+        blocks_per_row = ne[0] // G.GGML_TYPES[tt][1]
+        sp = raw[: N_SPECIAL * blocks_per_row]
+        if tt == G.GGML_Q8_0:
+            sp[:, 0:2] = 0
+        elif tt in (G.GGML_Q4_K, G.GGML_Q5_K):
+            sp[:, 0:4] = 0
+        elif tt == G.GGML_Q6_K:
+            sp[:, 208:210] = 0
+    return raw
 
 
 # ----------------------------------------------------------------------------- vocabulary
-N_SPECIAL = 3 + 256  # <unk> <s> </s> + byte-fallback tokens
 
 
 def synthetic_vocab(vocab: int):

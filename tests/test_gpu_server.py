@@ -1,0 +1,76 @@
+"""-m gpu: the real `bin/llama-server` process (GPU engine) behind its HTTP contract, launched with the argv
+scripts/start.sh:473-494 builds; output checked against the CPU oracle."""
+import http.client
+import json
+import os
+import signal
+import socket
+import subprocess
+import time
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEY = "gateway-" + "Z" * 43
+MSG = [{"role": "user", "content": "Write a short poem about the sea"}]
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def call(port, method, path, body=None, key=KEY):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+    h = {"Content-Type": "application/json"}
+    if key:
+        h["Authorization"] = f"Bearer {key}"
+    c.request(method, path, json.dumps(body) if body is not None else None, h)
+    r = c.getresponse()
+    data = r.read()
+    c.close()
+    return r.status, (json.loads(data) if data else None)
+
+
+def test_llama_server_process_contract_and_parity(oracle, model_dir, tmp_path):
+    from ggufb200 import synth
+    from ggufb200.gguf_reader import GGUFFile
+    from ggufb200.tokenizer import Tokenizer
+    path = os.path.join(model_dir, "proc-small.gguf")
+    synth.write_gguf(path, "small", "Q4_K_M", seed=0xB200)
+    keyfile = tmp_path / "backend.key"
+    keyfile.write_text(KEY + "\n")
+    port = free_port()
+    argv = [os.path.join(ROOT, "bin", "llama-server"), "-m", path, "--host", "127.0.0.1", "--port", str(port), "-c", "256",
+            "-ngl", "99", "--api-key-file", str(keyfile), "-t", "4", "--parallel", "2", "--temp", "0", "--ignore-eos"]
+    proc = subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        ok = False
+        for _ in range(120):                    # start.sh polls /health for ~30 s; 503 while loading, then 200
+            try:
+                st, body = call(port, "GET", "/health", key=None)
+                if st == 200 and body["status"] == "ok":
+                    ok = True
+                    break
+            except OSError:
+                pass
+            assert proc.poll() is None, proc.stdout.read()
+            time.sleep(0.25)
+        assert ok
+        assert call(port, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 4}, key=None)[0] == 401
+        st, body = call(port, "POST", "/v1/chat/completions", {"model": "default", "messages": MSG, "max_tokens": 48})
+        assert st == 200
+        tok = Tokenizer(GGUFFile(path).meta)
+        ids = tok.encode_chat(MSG)
+        ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")
+        assert body["choices"][0]["message"]["content"] == tok.decode(ref.greedy(ids, 48))
+        assert body["usage"]["completion_tokens"] == 48 and body["timings"]["predicted_per_second"] > 0
+        proc.send_signal(signal.SIGTERM)
+        assert proc.wait(timeout=30) == 0       # start.sh gives 30 s before SIGKILL (start.sh:414-428)
+    finally:
+        if proc.poll() is None:
+            proc.kill()

@@ -1,0 +1,232 @@
+"""CPU tests of the drop-in boundary: llama-server argv contract, HTTP contract, scheduler, tokenizer -- and, when
+the reference checkout is mounted, the reference's UNCHANGED gateway and benchmark client in front of it.
+The compute behind the boundary is a test double built on the oracle (tests/fake_engine.py); the GPU engine is
+exercised through the same server in tests/test_gpu_server.py."""
+import http.client
+import json
+import os
+import socket
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("REF_DIR", "/root/reference")
+KEY = "gateway-" + "A" * 43
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.fixture(scope="module")
+def tiny_path(model_dir):
+    from ggufb200 import synth
+    p = os.path.join(model_dir, "srv-tiny.gguf")
+    synth.write_gguf(p, "tiny", "Q4_K_M", seed=0xB200)
+    return p
+
+
+@pytest.fixture(scope="module")
+def backend(oracle, tiny_path):
+    from fake_engine import OracleEngine
+    from ggufb200.gguf_reader import GGUFFile
+    from ggufb200.scheduler import SamplingParams, Scheduler
+    from ggufb200.server import ServerState, make_server
+    from ggufb200.tokenizer import Tokenizer
+    tok = Tokenizer(GGUFFile(tiny_path).meta)
+    eng = OracleEngine(tiny_path, n_ctx=160, n_slots=2)
+    sched = Scheduler(eng, tok, ignore_eos=True)
+    sched.start()
+    st = ServerState(sched, tok, "srv-tiny.gguf", KEY, 160, SamplingParams(temperature=0.0), log=lambda *a: None)
+    st.ready.set()
+    port = free_port()
+    httpd = make_server("127.0.0.1", port, st)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    yield {"port": port, "tok": tok, "state": st, "path": tiny_path}
+    httpd.shutdown()
+    sched.shutdown()
+
+
+def call(port, method, path, body=None, key=KEY, raw=False):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=60)
+    h = {"Content-Type": "application/json"}
+    if key:
+        h["Authorization"] = f"Bearer {key}"
+    c.request(method, path, json.dumps(body) if body is not None else None, h)
+    r = c.getresponse()
+    data = r.read()
+    c.close()
+    return (r.status, data, dict(r.getheaders())) if raw else (r.status, json.loads(data) if data else None)
+
+
+def expected_text(oracle, backend, messages, n):
+    tok = backend["tok"]
+    ids = tok.encode_chat(messages)
+    m = oracle.OracleLlama(backend["path"], n_ctx=160, mode="canon")
+    return tok.decode(m.greedy(ids, n)), len(ids)
+
+
+MSG = [{"role": "user", "content": "Write a short poem about the sea"}]
+
+
+def test_health_is_public_single_packet_json(backend):
+    s = socket.create_connection(("127.0.0.1", backend["port"]))
+    s.sendall(b"GET /health HTTP/1.1\r\nHost: x\r\nConnection: close\r\n\r\n")  # no Authorization, like gateway.py:336-340
+    data = s.recv(4096)                                                            # ONE read, like gateway.py:344
+    s.close()
+    head, _, body = data.partition(b"\r\n\r\n")
+    assert head.startswith(b"HTTP/1.1 200")
+    assert b"chunked" not in head.lower()
+    assert json.loads(body)["status"] == "ok" and len(data) < 4096
+
+
+def test_key_is_enforced_except_on_public_paths(backend):
+    p = backend["port"]
+    assert call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 2}, key=None)[0] == 401
+    assert call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 2}, key="gateway-" + "B" * 43)[0] == 401
+    st, body = call(p, "GET", "/v1/models", key=None)
+    assert st == 200 and body["object"] == "list" and body["data"][0]["object"] == "model"
+    st, body = call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 2}, key=None)
+    assert body["error"]["type"] == "authentication_error"
+
+
+def test_chat_completion_matches_oracle_tokens(oracle, backend):
+    st, body = call(backend["port"], "POST", "/v1/chat/completions", {"model": "default", "messages": MSG, "max_tokens": 12, "temperature": 0})
+    assert st == 200 and body["object"] == "chat.completion"
+    text, n_prompt = expected_text(oracle, backend, MSG, 12)
+    ch = body["choices"][0]
+    assert ch["message"] == {"role": "assistant", "content": text}
+    assert ch["finish_reason"] == "length"
+    assert body["usage"] == {"prompt_tokens": n_prompt, "completion_tokens": 12, "total_tokens": n_prompt + 12}
+    # the synthetic vocabulary gives one leading-space word per token (benchmark.py counts whitespace words)
+    assert len(text.split()) == 12
+
+
+def test_streaming_sse_framing_and_close(oracle, backend):
+    s = socket.create_connection(("127.0.0.1", backend["port"]))
+    body = json.dumps({"model": "default", "messages": MSG, "max_tokens": 8, "stream": True, "temperature": 0}).encode()
+    s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nhost: x\r\nauthorization: Bearer " + KEY.encode() +
+              b"\r\ncontent-type: application/json\r\ncontent-length: " + str(len(body)).encode() + b"\r\nConnection: close\r\n\r\n" + body)
+    buf = b""
+    while True:
+        d = s.recv(8192)
+        if not d:
+            break   # the backend closes the socket when the response is complete (gateway.py:777-783 relays until EOF)
+        buf += d
+    s.close()
+    head, _, payload = buf.partition(b"\r\n\r\n")
+    assert b"text/event-stream" in head and b"chunked" not in head.lower()
+    events = [l[5:].strip() for l in payload.decode().split("\n") if l.startswith("data:")]
+    assert events[-1] == "[DONE]"
+    chunks = [json.loads(e) for e in events[:-1]]
+    assert all(c["object"] == "chat.completion.chunk" for c in chunks)
+    assert chunks[0]["choices"][0]["delta"].get("role") == "assistant"
+    text = "".join(c["choices"][0]["delta"].get("content") or "" for c in chunks)
+    assert text == expected_text(oracle, backend, MSG, 8)[0]
+    assert chunks[-1]["choices"][0]["finish_reason"] == "length"
+    assert all(c["choices"][0]["finish_reason"] is None for c in chunks[:-1])
+    assert chunks[-1]["usage"]["completion_tokens"] == 8
+
+
+def test_completions_endpoint_stop_and_errors(oracle, backend):
+    p = backend["port"]
+    tok = backend["tok"]
+    m = oracle.OracleLlama(backend["path"], n_ctx=160, mode="canon")
+    ids = tok.encode("hello world")
+    full = tok.decode(m.greedy(ids, 10))
+    st, body = call(p, "POST", "/v1/completions", {"prompt": "hello world", "max_tokens": 10, "temperature": 0})
+    assert st == 200 and body["choices"][0]["text"] == full
+    third = full.split()[2]
+    st, body = call(p, "POST", "/v1/completions", {"prompt": "hello world", "max_tokens": 10, "temperature": 0, "stop": [third]})
+    assert body["choices"][0]["finish_reason"] == "stop" and body["choices"][0]["text"] == full[:full.index(third)]
+    assert call(p, "POST", "/v1/chat/completions", {"max_tokens": 4})[0] == 400
+    assert call(p, "POST", "/v1/chat/completions", {"messages": [{"role": "user", "content": "x" * 4000}], "max_tokens": 4})[0] == 400  # context
+    assert call(p, "GET", "/nope")[0] == 404
+    c = http.client.HTTPConnection("127.0.0.1", p, timeout=10)
+    c.request("POST", "/v1/chat/completions", "{not json", {"Authorization": f"Bearer {KEY}"})
+    assert c.getresponse().status == 400
+
+
+def test_sampling_is_seeded_and_differs_from_greedy(backend):
+    p = backend["port"]
+    req = {"messages": MSG, "max_tokens": 12, "temperature": 1.5, "top_k": 50, "seed": 7}
+    a = call(p, "POST", "/v1/chat/completions", req)[1]["choices"][0]["message"]["content"]
+    b = call(p, "POST", "/v1/chat/completions", req)[1]["choices"][0]["message"]["content"]
+    g = call(p, "POST", "/v1/chat/completions", {**req, "temperature": 0})[1]["choices"][0]["message"]["content"]
+    assert a == b and a != g
+
+
+def test_concurrent_requests_and_health_during_generation(backend):
+    p = backend["port"]
+    out, errs = [None] * 5, []
+
+    def worker(i):
+        try:
+            out[i] = call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 24, "temperature": 0})
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(5)]
+    [t.start() for t in ts]
+    t0 = time.time()
+    st, h = call(p, "GET", "/health", key=None)      # must not queue behind the generations
+    assert st == 200 and time.time() - t0 < 1.0
+    [t.join() for t in ts]
+    assert not errs and all(o[0] == 200 for o in out)
+    assert len({o[1]["choices"][0]["message"]["content"] for o in out}) == 1   # same prompt, greedy -> same text on every slot
+
+
+def test_cli_version_and_argv_contract():
+    exe = os.path.join(ROOT, "bin", "llama-server")
+    r = subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip().startswith("version:")
+    from ggufb200.cli import build_parser
+    # the exact argv scripts/start.sh:473-494 builds, plus pass-through extras
+    argv = ["-m", "/data/models/m.gguf", "--host", "127.0.0.1", "--port", "8080", "-c", "16384", "-ngl", "99",
+            "--api-key-file", "/dev/shm/llama-keys/backend-1.key", "-t", "8", "--flash-attn", "--parallel", "16"]
+    a, unknown = build_parser().parse_known_args(argv)
+    assert (a.model, a.host, a.port, a.ctx_size, a.ngl, a.parallel) == ("/data/models/m.gguf", "127.0.0.1", 8080, 16384, "99", 16)
+    assert unknown == ["--flash-attn"]
+    r = subprocess.run([exe, "-m", "/nonexistent.gguf", "--port", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "not found" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "scripts", "gateway.py")), reason="reference checkout not mounted (set REF_DIR)")
+def test_unchanged_reference_gateway_and_benchmark_in_front(oracle, backend):
+    """The reference's own gateway.py and benchmark.py, executed from where they are mounted, against this backend."""
+    gport = free_port()
+    env = {**os.environ, "GATEWAY_PORT": str(gport), "PORT_BACKEND": str(backend["port"]), "BACKEND_HOST": "127.0.0.1",
+           "BACKEND_API_KEY": KEY, "AUTH_ENABLED": "false", "MAX_CONCURRENT_REQUESTS": "2", "DATA_DIR": "/tmp"}
+    gw = subprocess.Popen([sys.executable, os.path.join(REF, "scripts", "gateway.py")], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    try:
+        for _ in range(100):
+            try:
+                if call(gport, "GET", "/ping", key=None, raw=True)[0] == 200:
+                    break
+            except OSError:
+                time.sleep(0.1)
+        st, h = call(gport, "GET", "/health", key=None)
+        assert st == 200 and h["backend"]["status"] == "ok"          # gateway surfaces our JSON (gateway.py:356-363)
+        st, body = call(gport, "POST", "/v1/chat/completions", {"model": "default", "messages": MSG, "max_tokens": 10, "temperature": 0}, key=None)
+        assert st == 200 and body["choices"][0]["message"]["content"] == expected_text(oracle, backend, MSG, 10)[0]
+        # the reference's benchmark client (streaming, whitespace token count)
+        r = subprocess.run([sys.executable, os.path.join(REF, "scripts", "benchmark.py"), "--url", f"http://127.0.0.1:{gport}",
+                            "--requests", "2", "--warmup", "0", "--max-tokens", "12", "--concurrency", "2", "--output", "json"],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rep = json.loads(r.stdout)
+        inf = rep["inference"]
+        assert inf["requests_success"] == 2 and inf["requests_failed"] == 0
+        assert inf["tokens_per_sec"]["count"] == 2 and inf["ttft"]["count"] == 2   # it saw content deltas and counted words
+    finally:
+        gw.terminate()
+        gw.wait(timeout=10)
