@@ -79,6 +79,9 @@ int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m,
  *                       vcache[pos]  (ggml_rope NORM mode + ggml_cpy into the KV cache); pos is read from
  *                       device memory so a captured graph can be replayed for every position
  *     GGB_EPI_ARGMAX    y_0[r] = dot and per-CTA (max, first index) partials for the greedy sampler
+ *     GGB_EPI_STORE_F64 y_0 is a double*: the unrounded f64 row sums.  Tensor-parallel ranks that hold a K-slice of
+ *                       W exchange these (all-reduce in f64) so the single rounding to f32 happens after the
+ *                       cross-rank sum and the result is bit-identical with the unsharded GEMV.
  */
 #define GGB_MAX_SEG 3
 #define GGB_PRO_PLAIN 0
@@ -88,6 +91,7 @@ int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m,
 #define GGB_EPI_SWIGLU 2
 #define GGB_EPI_ROPE_KV 3
 #define GGB_EPI_ARGMAX 4
+#define GGB_EPI_STORE_F64 5
 
 typedef struct ggb_gemv_seg {
     const void* w;   /* tile-SoA weights [rows][row_stride] */
@@ -135,6 +139,17 @@ int ggb_argmax_next(const float* part_val, const int32_t* part_idx, int n_part, 
 int ggb_rms_norm(const float* x, const float* w, float* y, int64_t k, int m, float eps, void* stream);
 int ggb_swiglu(const float* g, const float* u, float* out, int64_t n, void* stream);
 int ggb_argmax(const float* x, int64_t n, int32_t* out_idx, void* stream);
+
+/* ---- tensor-parallel glue (one process per GPU; the collectives themselves are NCCL calls made by the host)
+ * x[i] += (float)y64[i]  -- applied after the f64 all-reduce of GGB_EPI_STORE_F64 partials (ggml_add) */
+int ggb_residual_add_f64(float* x, const double* y64, int64_t n, int use_pdl, void* stream);
+/* vocabulary-sharded greedy sampling: reduce this rank's GEMV arg-max partials (row indices local to the shard,
+ * row_offset = first vocabulary row of the shard) to ONE sortable 64-bit key (larger logit wins, then smaller index);
+ * the host all-reduces the keys with MAX; unpack turns the winner into the token id and does the rest of
+ * ggb_argmax_next (append to out_tokens, advance pos/step, gather the next embedding row). */
+int ggb_argmax_pack(const float* part_val, const int32_t* part_idx, int n_part, int32_t row_offset, int64_t* key, void* stream);
+int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_dev, int32_t* step_dev, int32_t* out_tokens,
+                           int32_t out_cap, int emb_type, const void* token_embd, int64_t k, float* x, void* stream);
 
 /* ---- KV-cache attention, one query token (ggml flash_attn_ext / soft_max path, GQA)
  * q [n_head*hd] f32 (already rotated); caches [n_ctx][n_kv*hd] f16; attends positions 0..*pos_dev inclusive.

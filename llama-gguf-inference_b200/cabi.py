@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libggufb200.so")
 F32, F16, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 8, 12, 13, 14
 MAX_SEG = 3
 PRO_PLAIN, PRO_RMSNORM = 0, 1
-EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU, EPI_ROPE_KV, EPI_ARGMAX = 0, 1, 2, 3, 4
+EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU, EPI_ROPE_KV, EPI_ARGMAX, EPI_STORE_F64 = 0, 1, 2, 3, 4, 5
 
 # every symbol include/ggufb200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
@@ -24,6 +24,7 @@ EXPORTS = [
     "ggb_gemv", "ggb_gemv_grid",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
+    "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
 ]
 
 
@@ -82,6 +83,9 @@ def lib() -> C.CDLL:
         "ggb_argmax": ([vp, i64, vp, vp], i32),
         "ggb_attn_decode_ws_bytes": ([i32, i32], sz),
         "ggb_attn_decode": ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp], i32),
+        "ggb_residual_add_f64": ([vp, vp, i64, i32, vp], i32),
+        "ggb_argmax_pack": ([vp, vp, i32, i32, vp, vp], i32),
+        "ggb_argmax_unpack_next": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     uint8_t* qs = smem + GEMV_NW * P.ring_bytes;                  // K bytes
     int16_t* bsums = reinterpret_cast<int16_t*>(qs + K);          // K/16 int16
     float* dsc = reinterpret_cast<float*>(qs + K + K / 8);        // K/32 floats
-    float* rowv = reinterpret_cast<float*>(smem + P.rowv_off);    // one f32 result per local row
+    double* rowv = reinterpret_cast<double*>(smem + P.rowv_off);  // one f64 row sum per local row (rounded once, in the epilogue)
     const uint32_t SLOT = P.slot_bytes;                           // one tile; a step holds two (rows A and B)
 
     // ---- this CTA's row range in every segment (even-aligned: row pairs and RoPE pairs stay together)
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
             const int r = lane >> 3;
-            if ((lane & 7) == 0 && r < nv) rowv[lr + r] = (float)keep;   /* the only rounding of the accumulated sum */
+            if ((lane & 7) == 0 && r < nv) rowv[lr + r] = keep;
             } else {
             const bool up = lane & 16;
             const double send = up ? acc[0] : acc[1];
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
             const int r = lane >> 4;
-            if ((lane & 15) == 0 && r < nv) rowv[lr + r] = (float)keep;
+            if ((lane & 15) == 0 && r < nv) rowv[lr + r] = keep;
             }
         }
     }
@@ -541,19 +541,23 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     TL_STAMP(4);
 
     // ---- epilogue
+    // (float)rowv[..] below is the only rounding of an accumulated row sum
     if (P.epi == GGB_EPI_STORE) {
         for (int lr = tid; lr < nloc; lr += GEMV_THREADS) {
-            if (lr < cnt0) P.seg[0].y[r0_0 + lr] = rowv[lr];
-            else if (lr < cnt0 + cnt1) P.seg[1].y[r0_1 + lr - cnt0] = rowv[lr];
-            else P.seg[2].y[r0_2 + lr - cnt0 - cnt1] = rowv[lr];
+            if (lr < cnt0) P.seg[0].y[r0_0 + lr] = (float)rowv[lr];
+            else if (lr < cnt0 + cnt1) P.seg[1].y[r0_1 + lr - cnt0] = (float)rowv[lr];
+            else P.seg[2].y[r0_2 + lr - cnt0 - cnt1] = (float)rowv[lr];
         }
+    } else if (P.epi == GGB_EPI_STORE_F64) {
+        double* y64 = reinterpret_cast<double*>(P.seg[0].y);   /* tensor-parallel partial: summed across ranks before rounding */
+        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) y64[r0_0 + lr] = rowv[lr];
     } else if (P.epi == GGB_EPI_RESIDUAL) {
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {
             const int r = r0_0 + lr;
-            P.seg[0].y[r] = __fadd_rn(lr == tid ? res_pre : P.residual[r], rowv[lr]);
+            P.seg[0].y[r] = __fadd_rn(lr == tid ? res_pre : P.residual[r], (float)rowv[lr]);
         }
     } else if (P.epi == GGB_EPI_SWIGLU) {
-        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) P.seg[0].y[r0_0 + lr] = silu_mul_ref(rowv[lr], rowv[cnt0 + lr]);
+        for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) P.seg[0].y[r0_0 + lr] = silu_mul_ref((float)rowv[lr], (float)rowv[cnt0 + lr]);
     } else if (P.epi == GGB_EPI_ROPE_KV) {
         const int pos = *P.pos_dev;
         const float* tab = P.rope_tab + (int64_t)pos * P.n_rot; /* [n_rot/2][2] */
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
             if (l < cnt0) r = r0_0 + l;
             else if (l < cnt0 + cnt1) { s = 1; r = r0_1 + l - cnt0; }
             else { s = 2; r = r0_2 + l - cnt0 - cnt1; }
-            float v0 = rowv[2 * pr], v1 = rowv[2 * pr + 1];
+            float v0 = (float)rowv[2 * pr], v1 = (float)rowv[2 * pr + 1];
             if (s < 2) {
                 const int j = r % P.head_dim;
                 if (j < P.n_rot) {
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
         float bv = -FLT_MAX;
         int bi = 0x7fffffff;
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {
-            const float v = rowv[lr];
+            const float v = (float)rowv[lr];
             const int r = r0_0 + lr;
             if (P.seg[0].y) P.seg[0].y[r] = v;
             argmax_comb(bv, bi, v, r);
@@ -688,6 +692,9 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
         case GGB_EPI_STORE:
             for (int s = 0; s < a->n_seg; s++) if (a->seg[s].rows && !a->seg[s].y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: STORE needs y for every segment");
             break;
+        case GGB_EPI_STORE_F64:
+            if (a->n_seg != 1 || !a->seg[0].y || ((uintptr_t)a->seg[0].y & 7)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: STORE_F64 needs one segment and an 8-byte aligned f64 output");
+            break;
         case GGB_EPI_RESIDUAL:
             if (a->n_seg != 1 || !a->residual || !a->seg[0].y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: RESIDUAL needs one segment, y and residual");
             break;
@@ -727,7 +734,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     size_t off = (size_t)GEMV_NW * P.ring_bytes + (size_t)a->k + a->k / 8 + a->k / 8;
     off = (off + 15) & ~(size_t)15;
     P.rowv_off = (int)off;
-    const size_t smem = off + (size_t)max_local * sizeof(float);
+    const size_t smem = off + (size_t)max_local * sizeof(double);
     if (smem > GEMV_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
     cudaStream_t st = (cudaStream_t)stream;
     switch (mask) {

@@ -176,3 +176,75 @@ extern "C" int ggb_argmax_next(const float* part_val, const int32_t* part_idx, i
     if (token_embd) return ggb_embed_row(emb_type, token_embd, k, tok_dev, x, stream);
     return GGB_OK;
 }
+
+
+// ------------------------------------------------------------------ tensor-parallel glue
+__global__ void residual_add_f64_kernel(float* __restrict__ x, const double* __restrict__ y, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = __fadd_rn(x[i], (float)y[i]);
+}
+extern "C" int ggb_residual_add_f64(float* x, const double* y64, int64_t n, int use_pdl, void* stream) {
+    if (n < 0 || (n && (!x || !y64))) GGB_FAIL(GGB_ERR_ARG, "ggb_residual_add_f64: bad argument");
+    if (n == 0) return GGB_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, residual_add_f64_kernel, x, y64, n));
+    return GGB_OK;
+}
+
+// sortable key: larger value first, then smaller index.  Float bits are mapped to a monotone u32, the top bit of
+// the u64 is flipped so that SIGNED 64-bit MAX (what the collective offers) orders the keys correctly.
+__device__ __forceinline__ long long argmax_key(float v, int idx) {
+    const unsigned b = __float_as_uint(v);
+    const unsigned mono = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const unsigned long long k = ((unsigned long long)mono << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+    return (long long)(k ^ 0x8000000000000000ull);
+}
+__global__ void argmax_pack_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int n_part,
+                                   int32_t row_offset, long long* __restrict__ key) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    pdl_wait();
+    float v = -FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) argmax_combine(v, idx, part_val[i], part_idx[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -FLT_MAX;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) argmax_combine(v, idx, __shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+        if (threadIdx.x == 0) *key = (idx == 0x7fffffff) ? argmax_key(-FLT_MAX, 0x7ffffffe) : argmax_key(v, idx + row_offset);
+    }
+}
+extern "C" int ggb_argmax_pack(const float* part_val, const int32_t* part_idx, int n_part, int32_t row_offset, int64_t* key, void* stream) {
+    if (!part_val || !part_idx || n_part <= 0 || !key) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_pack: bad argument");
+    argmax_pack_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(part_val, part_idx, n_part, row_offset, (long long*)key);
+    GGB_CHECK_LAUNCH("ggb_argmax_pack");
+    return GGB_OK;
+}
+__global__ void argmax_unpack_kernel(const long long* __restrict__ key, int32_t* tok, int32_t* pos, int32_t* step, int32_t* out_tokens, int32_t out_cap) {
+    const unsigned long long k = (unsigned long long)(*key) ^ 0x8000000000000000ull;
+    const int idx = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+    *tok = idx;
+    const int s = *step;
+    if (s < out_cap) out_tokens[s] = idx;
+    *step = s + 1;
+    *pos = *pos + 1;
+}
+extern "C" int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_dev, int32_t* step_dev, int32_t* out_tokens,
+                                      int32_t out_cap, int emb_type, const void* token_embd, int64_t k, float* x, void* stream) {
+    if (!key || !tok_dev || !pos_dev || !step_dev || !out_tokens) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_unpack_next: bad argument");
+    argmax_unpack_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const long long*)key, tok_dev, pos_dev, step_dev, out_tokens, out_cap);
+    GGB_CHECK_LAUNCH("ggb_argmax_unpack_next");
+    if (token_embd) return ggb_embed_row(emb_type, token_embd, k, tok_dev, x, stream);
+    return GGB_OK;
+}

@@ -23,6 +23,7 @@ import numpy as np
 
 from . import cabi
 from . import gguf_reader as G
+from . import parallel
 
 QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q6_K, G.GGML_Q8_0)
 
@@ -91,13 +92,17 @@ class Slot:
         self.torch, self.lib, self.hp = torch, eng.lib, hp
         self.n_ctx, self.max_new, self.use_pdl = eng.n_ctx, eng.max_new, eng.use_pdl
         self.stream = eng.stream
-        kvd = hp.n_kv * hp.head_dim
+        tp = eng.tp_size
+        self.nh, self.nkv, self.ffl, self.vl = hp.n_head // tp, hp.n_kv // tp, hp.ff // tp, hp.vocab // tp   # this rank's share
+        kvd = self.nkv * hp.head_dim
         self.kc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
         self.vc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
         f32 = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
         i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)  # noqa: E731
-        self.x, self.q, self.attn = f32(hp.d), f32(hp.n_head * hp.head_dim), f32(hp.n_head * hp.head_dim)
-        self.h, self.logits = f32(hp.ff), f32(hp.vocab)
+        self.x, self.q, self.attn = f32(hp.d), f32(self.nh * hp.head_dim), f32(self.nh * hp.head_dim)
+        self.h, self.logits = f32(self.ffl), f32(self.vl)
+        self.y64 = torch.zeros(hp.d, dtype=torch.float64, device=dev)       # row-split partial sums (tensor parallel)
+        self.key = torch.zeros(1, dtype=torch.int64, device=dev)            # sharded arg-max key
         self.attn_ws = torch.zeros(max(16, self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim)), dtype=torch.uint8, device=dev)
         self.tok_dev, self.pos_dev, self.step_dev = i32(1), i32(1), i32(1)
         self.out_tokens = i32(self.max_new)
@@ -132,17 +137,20 @@ class Slot:
                 norm_w=L["attn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, pos_dev=self.pos_dev.data_ptr(),
                 rope_tab=e.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
                 kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
+            tp = e.tp_size > 1
             o = cabi.make_gemv_args(
-                [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.x.data_ptr())], L["wo"].k, self.attn.data_ptr(),
-                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+                [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wo"].k,
+                self.attn.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_STORE_F64 if tp else cabi.EPI_RESIDUAL,
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl)
             gu = cabi.make_gemv_args(
                 [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
                  (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
                 hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_SWIGLU,
                 norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
             dn = cabi.make_gemv_args(
-                [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.x.data_ptr())], L["wd"].k, self.h.data_ptr(),
-                prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_RESIDUAL, residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+                [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wd"].k,
+                self.h.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_STORE_F64 if tp else cabi.EPI_RESIDUAL,
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl)
             self._layer_args.append((qkv, o, gu, dn))
         self._head = self._head_args()
 
@@ -152,20 +160,39 @@ class Slot:
         cabi.check(self.lib.ggb_embed_row(e.emb_type, e.emb_canon.data_ptr(), self.hp.d, self.tok_dev.data_ptr(),
                                           self.x.data_ptr(), s), "embed_row")
 
+    def _allreduce_residual(self, s: int):
+        """x += (float) sum over ranks of the f64 partials (the exchange step of a row-split projection)"""
+        e = self.eng
+        e.dist.all_reduce(self.y64, op=e.dist.ReduceOp.SUM, group=e.pg)
+        cabi.check(self.lib.ggb_residual_add_f64(self.x.data_ptr(), self.y64.data_ptr(), self.hp.d, 0, s), "residual_add_f64")
+
     def _enqueue_layers(self, s: int):
         hp, lib = self.hp, self.lib
+        tp = self.eng.tp_size > 1
         for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
             cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
             cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
-                                           self.pos_dev.data_ptr(), hp.n_head, hp.n_kv, hp.head_dim, self.n_ctx,
+                                           self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
                                            self.attn_ws.data_ptr(), self.attn.data_ptr(), self.use_pdl, s), "attn_decode")
             cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
+            if tp:
+                self._allreduce_residual(s)
             cabi.check(lib.ggb_gemv(C.byref(gu), s), "gemv gate/up")
             cabi.check(lib.ggb_gemv(C.byref(dn), s), "gemv down")
+            if tp:
+                self._allreduce_residual(s)
 
     def _enqueue_head(self, s: int):
         lib, e = self.lib, self.eng
         cabi.check(lib.ggb_gemv(C.byref(self._head), s), "gemv head")
+        if e.tp_size > 1:   # vocabulary-sharded arg-max: one sortable key per rank, MAX across ranks
+            cabi.check(lib.ggb_argmax_pack(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
+                                           e.tp_rank * self.vl, self.key.data_ptr(), s), "argmax_pack")
+            e.dist.all_reduce(self.key, op=e.dist.ReduceOp.MAX, group=e.pg)
+            cabi.check(lib.ggb_argmax_unpack_next(self.key.data_ptr(), self.tok_dev.data_ptr(), self.pos_dev.data_ptr(),
+                                                  self.step_dev.data_ptr(), self.out_tokens.data_ptr(), self.max_new, e.emb_type,
+                                                  e.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_unpack_next")
+            return
         cabi.check(lib.ggb_argmax_next(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
                                        self.tok_dev.data_ptr(), self.pos_dev.data_ptr(), self.step_dev.data_ptr(),
                                        self.out_tokens.data_ptr(), self.max_new, e.emb_type,
@@ -260,7 +287,7 @@ class Slot:
 
     def read_logits(self) -> np.ndarray:
         if self.host_logits is None:
-            self.host_logits = self.torch.zeros(self.hp.vocab, dtype=self.torch.float32).pin_memory()
+            self.host_logits = self.torch.zeros(self.vl, dtype=self.torch.float32).pin_memory()
         with self.torch.cuda.stream(self.stream):
             self.host_logits.copy_(self.logits, non_blocking=True)
         self.stream.synchronize()
@@ -297,7 +324,8 @@ class Engine:
     """Weights in HBM + n_slots independent sequences.  The single-sequence methods act on slot 0."""
 
     def __init__(self, path: str, n_ctx: int = 4096, device: int = 0, use_graph: bool = True, use_pdl: bool = True,
-                 max_new: int = 65536, verbose: bool = False, n_slots: int = 1):
+                 max_new: int = 65536, verbose: bool = False, n_slots: int = 1, tp_rank: int = 0, tp_size: int = 1,
+                 process_group=None):
         import torch
 
         if not torch.cuda.is_available():
@@ -309,6 +337,13 @@ class Engine:
         self.use_graph, self.use_pdl = use_graph, int(bool(use_pdl))
         self.file = G.GGUFFile(path)
         self.hp = HParams.from_gguf(self.file)
+        self.tp_rank, self.tp_size, self.pg = int(tp_rank), int(tp_size), process_group
+        parallel.check_divisible(self.hp, self.tp_size)
+        if self.tp_size > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise cabi.GGBError("tensor parallelism needs torch.distributed to be initialised (one process per GPU)")
+            self.dist = dist
         self.n_ctx = int(n_ctx)
         self.max_new = max_new
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -336,14 +371,19 @@ class Engine:
         k, rows = ti.ne[0], ti.ne[1]
         if k % 256:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
-        canon = self._upload(name)
+        sh = parallel.shard_of(name, self.hp, self.tp_size, self.tp_rank)
+        if sh.kind == parallel.FULL:
+            canon = self._upload(name)
+        else:
+            part, rows, k = parallel.slice_canonical(np.asarray(self.file.data(name)), ti.ggml_type, k, rows, sh)
+            canon = torch.from_numpy(np.array(part)).to(self.dev)
         stride = self.lib.ggb_repacked_row_stride(ti.ggml_type, k)
         # +16: the GEMV's bulk copies round a partial last tile up to 16 bytes
         dst = torch.zeros(rows * stride + 16, dtype=torch.uint8, device=self.dev)
         cabi.check(self.lib.ggb_repack(ti.ggml_type, canon.data_ptr(), dst.data_ptr(), rows, k, self._sptr()), f"repack {name}")
         torch.cuda.current_stream().synchronize()
+        self.weight_bytes += canon.numel()
         del canon
-        self.weight_bytes += ti.nbytes
         return Weight(dst, ti.ggml_type, rows, k)
 
     def _load_f32(self, name: str):
@@ -384,8 +424,8 @@ class Engine:
         self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
 
     def launches_per_step(self) -> int:
-        """kernels of libggufb200 launched by one decode step (layers + head)."""
-        return self.hp.n_layer * 5 + 3
+        """kernels of libggufb200 launched by one decode step (layers + head); NCCL kernels are not counted."""
+        return self.hp.n_layer * (7 if self.tp_size > 1 else 5) + (4 if self.tp_size > 1 else 3)
 
     # ------------------------------------------------------------------ single-sequence convenience (slot 0)
     @property

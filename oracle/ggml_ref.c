@@ -554,7 +554,7 @@ float gref_exp_ref(float x) {
 }
 
 /* per "unit" (64 consecutive elements: a pair of 32-element sub-blocks) one f32 term, summed in f64 */
-float gref_vec_dot_q4_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+static double vec_dot_q4_K_q8_K_f64(int64_t k, const void *vw, const void *va) {
     const blk_q4_K *w = (const blk_q4_K *)vw;
     const blk_q8_K *a = (const blk_q8_K *)va;
     double acc = 0.0;
@@ -574,10 +574,10 @@ float gref_vec_dot_q4_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
             acc += (double)term;
         }
     }
-    return (float)acc;
+    return acc;
 }
 
-float gref_vec_dot_q5_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+static double vec_dot_q5_K_q8_K_f64(int64_t k, const void *vw, const void *va) {
     const blk_q5_K *w = (const blk_q5_K *)vw;
     const blk_q8_K *a = (const blk_q8_K *)va;
     double acc = 0.0;
@@ -600,11 +600,11 @@ float gref_vec_dot_q5_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
             acc += (double)term;
         }
     }
-    return (float)acc;
+    return acc;
 }
 
 /* unit = (half n, column t): elements 128n + 32r + 16t + (0..15), r = 0..3 */
-float gref_vec_dot_q6_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
+static double vec_dot_q6_K_q8_K_f64(int64_t k, const void *vw, const void *va) {
     const blk_q6_K *w = (const blk_q6_K *)vw;
     const blk_q8_K *a = (const blk_q8_K *)va;
     double acc = 0.0;
@@ -628,10 +628,10 @@ float gref_vec_dot_q6_K_q8_K_canon(int64_t k, const void *vw, const void *va) {
                 acc += (double)(d * (float)isum);
             }
     }
-    return (float)acc;
+    return acc;
 }
 
-float gref_vec_dot_q8_0_q8_0_canon(int64_t k, const void *vw, const void *va) {
+static double vec_dot_q8_0_q8_0_f64(int64_t k, const void *vw, const void *va) {
     const blk_q8_0 *w = (const blk_q8_0 *)vw;
     const blk_q8_0 *a = (const blk_q8_0 *)va;
     double acc = 0.0;
@@ -640,7 +640,37 @@ float gref_vec_dot_q8_0_q8_0_canon(int64_t k, const void *vw, const void *va) {
         for (int j = 0; j < QK8_0; j++) s += w[b].qs[j] * a[b].qs[j];
         acc += (double)((float)s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d)));
     }
-    return (float)acc;
+    return acc;
+}
+
+float gref_vec_dot_q4_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q4_K_q8_K_f64(k, w, a); }
+float gref_vec_dot_q5_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q5_K_q8_K_f64(k, w, a); }
+float gref_vec_dot_q6_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q6_K_q8_K_f64(k, w, a); }
+float gref_vec_dot_q8_0_q8_0_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q8_0_q8_0_f64(k, w, a); }
+
+/* unrounded canon row sums (what tensor-parallel ranks exchange): Y[rows] f64 for one activation vector */
+int gref_matvec_f64(int type, const void *W, int64_t rows, int64_t k, const float *x, double *Y, int nthreads) {
+    const int64_t wrow = gref_row_bytes(type, k);
+    const int64_t arow = gref_act_row_bytes(type, k);
+    if (wrow <= 0 || type == GREF_F32 || type == GREF_F16) return -1;
+    uint8_t *act = (uint8_t *)malloc((size_t)arow);
+    if (!act) return -2;
+    gref_quantize_act(type, x, act, k);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; r++) {
+        const uint8_t *wr = (const uint8_t *)W + r * wrow;
+        switch (type) {
+            case GREF_Q4_K: Y[r] = vec_dot_q4_K_q8_K_f64(k, wr, act); break;
+            case GREF_Q5_K: Y[r] = vec_dot_q5_K_q8_K_f64(k, wr, act); break;
+            case GREF_Q6_K: Y[r] = vec_dot_q6_K_q8_K_f64(k, wr, act); break;
+            default: Y[r] = vec_dot_q8_0_q8_0_f64(k, wr, act); break;
+        }
+    }
+    free(act);
+    return 0;
 }
 
 /* mode 0 = generic ggml order, 1 = canon */

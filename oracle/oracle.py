@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         # order-independent ("canon") variants, see ggml_ref.c
         L.gref_matmul_mode.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32, i32]; L.gref_matmul_mode.restype = i32
         L.gref_exp_ref.argtypes = [f32]; L.gref_exp_ref.restype = f32
+        L.gref_matvec_f64.argtypes = [i32, vp, i64, i64, vp, vp, i32]; L.gref_matvec_f64.restype = i32
         L.gref_swiglu_canon.argtypes = [vp, vp, vp, i64]; L.gref_swiglu_canon.restype = None
         L.gref_rope_table_canon.argtypes = [i32, i32, f32, vp, vp]; L.gref_rope_table_canon.restype = None
         L.gref_rope_apply.argtypes = [vp, i32, i32, i32, vp]; L.gref_rope_apply.restype = None
@@ -132,6 +133,17 @@ def matmul(qtype: int, w_raw: np.ndarray, rows: int, k: int, x: np.ndarray, nthr
     rc = lib().gref_matmul_mode(qtype, _p(w_raw), rows, k, _p(x), m, _p(y), nthreads, 1 if mode == CANON else 0)
     assert rc == 0
     return y[0] if x.ndim == 1 else y
+
+
+def matvec_f64(qtype: int, w_raw: np.ndarray, rows: int, k: int, x: np.ndarray, nthreads: int = 0) -> np.ndarray:
+    """unrounded canon row sums (f64) of W.x -- what tensor-parallel ranks exchange before the single rounding"""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    w_raw = np.ascontiguousarray(w_raw, dtype=np.uint8).reshape(-1)
+    assert x.size == k and w_raw.size == rows * row_bytes(qtype, k)
+    y = np.empty(rows, dtype=np.float64)
+    rc = lib().gref_matvec_f64(qtype, _p(w_raw), rows, k, _p(x), _p(y), nthreads)
+    assert rc == 0
+    return y
 
 
 def rms_norm(x: np.ndarray, w: np.ndarray | None, eps: float) -> np.ndarray:
