@@ -127,6 +127,22 @@ int ggb_gemv(const ggb_gemv_args* args, void* stream);
 /* number of CTAs ggb_gemv will launch for these args (size of part_val/part_idx) */
 int ggb_gemv_grid(const ggb_gemv_args* args);
 
+/* ---- K2: dequant-GEMM on tcgen05 / TMEM (ggml mul_mat with many activation columns: prefill, large batches)
+ *   Y[tokens][y_stride >= rows] (f32) = X[tokens][k] (bf16) . W[rows][k]^T,  W in tile-SoA layout, k % 128 == 0.
+ * Weights are dequantised exactly (f32) and rounded to bf16 inside the kernel; accumulation is f32 in TMEM. */
+int ggb_gemm(int type, const void* w, int rows, int k, const void* x_bf16, int tokens, float* y, int64_t y_stride, void* stream);
+int ggb_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+
+/* ---- batched glue of the prefill path (ggml get_rows / rope / cpy / flash_attn_ext / add on T tokens) */
+int ggb_embed_rows(int type, const void* token_embd, int64_t k, const int32_t* ids_dev, int tokens, float* out, void* stream);
+/* q [T][n_head*hd] rotated in place; k rotated, v copied, both stored as f16 at cache rows pos0..pos0+T-1 */
+int ggb_rope_kv_prefill(float* q, const float* k, const float* v, int tokens, int pos0, int n_head, int n_kv, int head_dim,
+                        int n_rot, const float* rope_tab, uint16_t* kcache, uint16_t* vcache, void* stream);
+/* causal GQA attention of T query tokens (positions pos0..) over the f16 cache; out [T][n_head*hd] f32 */
+int ggb_attn_prefill(const float* q, const uint16_t* kcache, const uint16_t* vcache, int tokens, int pos0, int n_head, int n_kv,
+                     int head_dim, float* out, void* stream);
+int ggb_add_f32(float* x, const float* y, int64_t n, void* stream);
+
 /* ---- small fused glue */
 /* embedding gather (ggml get_rows on canonical token_embd): x[k] = dequant(row tok) ; tok read from device */
 int ggb_embed_row(int type, const void* token_embd, int64_t k, const int32_t* tok_dev, float* x, void* stream);

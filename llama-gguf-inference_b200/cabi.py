@@ -21,10 +21,11 @@ EXPORTS = [
     "ggb_abi_version", "ggb_last_error", "ggb_device_info",
     "ggb_dequant", "ggb_repacked_row_stride", "ggb_repack", "ggb_dequant_repacked",
     "ggb_quantize_q8_K", "ggb_quantize_q8_0",
-    "ggb_gemv", "ggb_gemv_grid",
+    "ggb_gemv", "ggb_gemv_grid", "ggb_gemm", "ggb_f32_to_bf16",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
+    "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
 ]
 
 
@@ -76,6 +77,8 @@ def lib() -> C.CDLL:
         "ggb_quantize_q8_0": ([vp, vp, vp, i64, i32, vp], i32),
         "ggb_gemv": ([C.POINTER(GemvArgs), vp], i32),
         "ggb_gemv_grid": ([C.POINTER(GemvArgs)], i32),
+        "ggb_gemm": ([i32, vp, i32, i32, vp, i32, vp, i64, vp], i32),
+        "ggb_f32_to_bf16": ([vp, vp, i64, vp], i32),
         "ggb_embed_row": ([i32, vp, i64, vp, vp, vp], i32),
         "ggb_argmax_next": ([vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp], i32),
         "ggb_rms_norm": ([vp, vp, vp, i64, i32, f32, vp], i32),
@@ -84,6 +87,10 @@ def lib() -> C.CDLL:
         "ggb_attn_decode_ws_bytes": ([i32, i32], sz),
         "ggb_attn_decode": ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp], i32),
         "ggb_residual_add_f64": ([vp, vp, i64, i32, vp], i32),
+        "ggb_embed_rows": ([i32, vp, i64, vp, i32, vp, vp], i32),
+        "ggb_rope_kv_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+        "ggb_attn_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
+        "ggb_add_f32": ([vp, vp, i64, vp], i32),
         "ggb_argmax_pack": ([vp, vp, i32, i32, vp, vp], i32),
         "ggb_argmax_unpack_next": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp], i32),
     }

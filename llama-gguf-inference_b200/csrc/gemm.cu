@@ -1,0 +1,353 @@
+// gemm.cu -- K2: dequant-GEMM for prefill / large batches on the 5th-generation tensor cores.
+//   Y[tokens][rows] = X[tokens][K] . W[rows][K]^T      W quantised (tile-SoA Q4_K / Q6_K / Q8_0), X bf16
+// Stands in for ggml-cuda's mul_mat_q / dequantise+cuBLAS path of the reference's backend [UPSTREAM-MEM].
+//
+// One CTA computes a 128 (weight rows) x 256 (tokens) output tile:
+//   * 8 producer warps unpack the packed weights of the current 128-wide K block straight into shared memory as
+//     bf16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
+//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5), and copy the matching
+//     bf16 activation block next to it; fence.proxy.async + mbarrier hand the stage to the MMA warp;
+//   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) eight
+//     times per K block from shared-memory descriptors; the f32 accumulator (128 lanes x 256 columns) lives in
+//     TMEM; tcgen05.commit releases the shared-memory stage back to the producers and, after the last block,
+//     signals the epilogue;
+//   * epilogue: the 8 producer warps read the accumulator with tcgen05.ld (32x32b.x32) and store Y.
+// Two shared-memory stages (2 x 96 KB); TMEM allocation = 256 columns.
+// Numerics: weights are dequantised exactly as ggml does (f32) and rounded to bf16, activations are bf16, products
+// are accumulated in f32 by the tensor core -- the tolerance-level path (like upstream's CUDA backend for batches),
+// not the bit-exact integer path of the decode GEMV.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "layout.cuh"
+
+#define GM_BM 128      /* weight rows per CTA  (UMMA M) */
+#define GM_BN 256      /* tokens per CTA       (UMMA N) */
+#define GM_BK 128      /* K elements per stage (two 64-element swizzle atoms, eight K=16 MMAs) */
+#define GM_STAGES 2
+#define GM_PRODUCER_WARPS 8
+#define GM_THREADS ((GM_PRODUCER_WARPS + 1) * 32)
+#define GM_A_BYTES (GM_BM * GM_BK * 2)   /* 32 KB */
+#define GM_B_BYTES (GM_BN * GM_BK * 2)   /* 64 KB */
+#define GM_STAGE_BYTES (GM_A_BYTES + GM_B_BYTES)
+#define GM_TMEM_COLS 256
+
+__device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gm_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gm_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gm_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GM_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GM_DONE;\n\t"
+        "bra GM_WAIT;\n\t"
+        "GM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64))
+__device__ __forceinline__ uint64_t gm_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                    /* leading byte offset (unused for swizzled K-major) */
+    d |= (uint64_t)(1024 >> 4) << 32;          /* stride byte offset: next 8-row group */
+    d |= (uint64_t)1 << 46;                    /* descriptor version (Blackwell) */
+    d |= (uint64_t)2 << 61;                    /* SWIZZLE_128B */
+    return d;
+}
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t gm_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+}
+
+// byte offset of the 16-byte chunk `c` (0..7 inside a 128-byte swizzle row) of row `r` in a [rows][64 bf16] atom
+__device__ __forceinline__ uint32_t gm_sw(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// dequantise 64 consecutive elements (one "unit") of a weight row into 8 chunks of 8 bf16
+struct Chunk8 { uint4 c[8]; };
+
+__device__ __forceinline__ void dq_unit_q4k(const uint8_t* tile, int U, int u, Chunk8& o) {
+    const uint4 q0 = ldg_stream(tile + 16 * u), q1 = ldg_stream(tile + 16 * U + 16 * u);
+    const uint8_t* hdr = tile + 32 * U + 16 * (u >> 2);
+    const uint4 h = ldg_cached(hdr);
+    int s0, m0, s1, m1;
+    {
+        const int g = u & 3;
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(&h) + 4 + 3 * g;
+        const uint32_t f = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+        s0 = f & 63; s1 = (f >> 6) & 63; m0 = (f >> 12) & 63; m1 = (f >> 18) & 63;
+    }
+    const float d = h2f((uint16_t)(h.x & 0xFFFF)), dmin = h2f((uint16_t)(h.x >> 16));
+    const float d0 = __fmul_rn(d, (float)s0), d1 = __fmul_rn(d, (float)s1);
+    const float n0 = __fmul_rn(dmin, (float)m0), n1 = __fmul_rn(dmin, (float)m1);
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};   /* bytes 0..31 of the 32-byte group */
+    // elements 0..31 = low nibbles (sub-block 2g), 32..63 = high nibbles (sub-block 2g+1)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const float dd = half ? d1 : d0, nn = half ? n1 : n0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {       /* 8 elements = bytes 8c..8c+7 = words 2c, 2c+1 */
+            uint32_t r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t word = w[2 * c + (j >> 1)];
+                const int b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
+                const int b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
+                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, (float)b0), nn), __fsub_rn(__fmul_rn(dd, (float)b1), nn));
+            }
+            o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    }
+}
+
+// Q6_K: a 64-element K block j (0..3) of a super-block = elements 64j..64j+63 = half n=j>>1, r in {2*(j&1), 2*(j&1)+1}
+__device__ __forceinline__ void dq_block64_q6k(const uint8_t* tile, int U, int nsb, int sb, int j, Chunk8& o) {
+    const int n = j >> 1, rp = (j & 1) * 2;
+    const float d = h2f(__ldg(reinterpret_cast<const uint16_t*>(tile + 48 * U + 16 * nsb + 2 * sb)));
+    const int8_t* sc = reinterpret_cast<const int8_t*>(tile + 48 * U + 16 * sb + 8 * n);
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = rp + rr;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {       /* 16 elements l = 16t..16t+15 of row-group r */
+            const int u = 4 * sb + 2 * n + t;
+            const uint4 ql = ldg_stream(tile + ((r & 1) ? 16 * U : 0) + 16 * u);
+            const uint4 qh = ldg_stream(tile + 32 * U + 16 * u);
+            const float ds = __fmul_rn(d, (float)sc[2 * r + t]);
+            const uint32_t lw[4] = {ql.x, ql.y, ql.z, ql.w}, hw[4] = {qh.x, qh.y, qh.z, qh.w};
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    float v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int i = 8 * c + 2 * jj + e;                 /* byte index 0..15 */
+                        const uint32_t lb = (lw[i >> 2] >> (8 * (i & 3))) & 0xFF, hb = (hw[i >> 2] >> (8 * (i & 3))) & 0xFF;
+                        const int lo = (r & 2) ? (lb >> 4) : (lb & 0xF);
+                        const int q = (lo | (((hb >> (2 * r)) & 3) << 4)) - 32;
+                        v[e] = __fmul_rn(ds, (float)q);
+                    }
+                    pk[jj] = pack_bf16(v[0], v[1]);
+                }
+                o.c[4 * rr + 2 * t + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void dq_unit_q8_0(const uint8_t* tile, int U, int u, Chunk8& o) {
+    const uint32_t dd = __ldg(reinterpret_cast<const uint32_t*>(tile + 64 * U + 4 * u));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 q = ldg_stream(tile + i * 16 * U + 16 * u);
+        const float d = h2f((uint16_t)((i >> 1) ? (dd >> 16) : (dd & 0xFFFF)));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i0 = 8 * c + 2 * j;
+                const float a = __fmul_rn((float)(int8_t)((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xFF), d);
+                const float b = __fmul_rn((float)(int8_t)((w[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFF), d);
+                pk[j] = pack_bf16(a, b);
+            }
+            o.c[2 * i + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, const __nv_bfloat16* __restrict__ X, int tokens,
+            float* __restrict__ Y, int64_t y_stride) {
+    extern __shared__ __align__(1024) uint8_t gsm[];
+    __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * GM_BM, tok0 = blockIdx.y * GM_BN;
+    const int nkb = K / GM_BK;
+    uint8_t* stage_base = (uint8_t*)(((uintptr_t)gsm + 1023) & ~(uintptr_t)1023);
+
+    if (tid == 0) {
+        for (int s = 0; s < GM_STAGES; s++) { gm_mbar_init(gm_smem_u32(&bar_full[s]), GM_PRODUCER_WARPS); gm_mbar_init(gm_smem_u32(&bar_empty[s]), 1); }
+        gm_mbar_init(gm_smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == GM_PRODUCER_WARPS) {   // the MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gm_smem_u32(&tmem_base_s)), "n"(GM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = tmem_base_s;
+
+    if (warp < GM_PRODUCER_WARPS) {
+        // ===== producers: dequantise A, copy B =====
+        const int pt = tid;                                   /* 0..255 */
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % GM_STAGES;
+            const uint32_t ph = (kb / GM_STAGES) & 1;
+            gm_mbar_wait(gm_smem_u32(&bar_empty[s]), ph ^ 1);   /* first pass over a fresh barrier returns at once */
+            uint8_t* sA = stage_base + s * GM_STAGE_BYTES;
+            uint8_t* sB = sA + GM_A_BYTES;
+            // A: thread -> (row, 64-element half of the K block)
+            {
+                const int r = pt & 127, hk = pt >> 7;         /* hk = which 64-wide atom of the 128-wide block */
+                const int k0 = kb * GM_BK + hk * 64;
+                Chunk8 ch;
+                const int grow = row0 + r;
+                if (grow < rows) {
+                    const int t = k0 / GGB_TILE_ELEMS, ek = k0 - t * GGB_TILE_ELEMS;
+                    const int nsb = ggb_tile_nsb(K, t), U = 4 * nsb;
+                    const uint8_t* tile = W + (int64_t)grow * w_stride + (int64_t)t * (ggb_sb_bytes(TYPE) * GGB_TILE_SB);
+                    if (TYPE == GGB_TYPE_Q4_K) dq_unit_q4k(tile, U, ek >> 6, ch);
+                    else if (TYPE == GGB_TYPE_Q6_K) dq_block64_q6k(tile, U, nsb, ek >> 8, (ek >> 6) & 3, ch);
+                    else dq_unit_q8_0(tile, U, ek >> 6, ch);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) ch.c[c] = make_uint4(0, 0, 0, 0);
+                }
+                uint8_t* atom = sA + hk * (GM_BM * 128);
+#pragma unroll
+                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(atom + gm_sw(r, c)) = ch.c[c];
+            }
+            // B: 256 tokens x 128 K bf16 = 4096 chunks of 16 B, 16 per thread; chunk id -> (token, k chunk)
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int id = i * 256 + pt;
+                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 bf16 = 128 K */
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (tok0 + tk < tokens) v = __ldg(reinterpret_cast<const uint4*>(X + (int64_t)(tok0 + tk) * K + kb * GM_BK + kc * 8));
+                uint8_t* atom = sB + (kc >> 3) * (GM_BN * 128);
+                *reinterpret_cast<uint4*>(atom + gm_sw(tk, kc & 7)) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the tensor core */
+            __syncwarp();
+            if (lane == 0) gm_mbar_arrive(gm_smem_u32(&bar_full[s]));
+        }
+        // ===== epilogue: TMEM -> registers -> Y =====
+        gm_mbar_wait(gm_smem_u32(&bar_acc), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, colh = warp >> 2;              /* TMEM lane quarter, column half */
+        const int grow = row0 + 32 * q + lane;
+#pragma unroll 1
+        for (int cb = 0; cb < 4; cb++) {                       /* 4 x 32 columns = this warp's 128 tokens */
+            const int col = colh * 128 + cb * 32;
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)col;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                  "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                  "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (grow < rows) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int tk = tok0 + col + j;
+                    if (tk < tokens) Y[(int64_t)tk * y_stride + grow] = __uint_as_float(v[j]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA warp: one elected lane issues =====
+        const uint32_t idesc = gm_idesc();
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % GM_STAGES;
+            const uint32_t ph = (kb / GM_STAGES) & 1;
+            gm_mbar_wait(gm_smem_u32(&bar_full[s]), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a0 = gm_smem_u32(stage_base + s * GM_STAGE_BYTES), b0 = a0 + GM_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < GM_BK / 16; k++) {
+                    const uint32_t aoff = (k >> 2) * (GM_BM * 128) + (k & 3) * 32;   /* atom, then 32 B per K=16 step */
+                    const uint32_t boff = (k >> 2) * (GM_BN * 128) + (k & 3) * 32;
+                    const uint64_t da = gm_desc(a0 + aoff), db = gm_desc(b0 + boff);
+                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                }
+                // tcgen05.commit implies fence::before_thread_sync; frees the smem stage when the MMAs have read it
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(&bar_empty[s])) : "memory");
+                if (kb == nkb - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(&bar_acc)) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == GM_PRODUCER_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(GM_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ f32 -> bf16 activations
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x[i], x[i + 1]);
+    } else if (i < n) {
+        y[i] = __float2bfloat16_rn(x[i]);
+    }
+}
+
+extern "C" int ggb_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
+    if (n < 0 || (n && (!x || !y_bf16))) GGB_FAIL(GGB_ERR_ARG, "ggb_f32_to_bf16: bad argument");
+    if (n == 0) return GGB_OK;
+    f32_to_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, n);
+    GGB_CHECK_LAUNCH("ggb_f32_to_bf16");
+    return GGB_OK;
+}
+
+template <int TYPE>
+static int launch_gemm(const void* w, int rows, int k, const void* x, int tokens, float* y, int64_t y_stride, cudaStream_t st) {
+    static bool attr = false;
+    const size_t smem = GM_STAGES * GM_STAGE_BYTES + 1024;
+    if (!attr) {
+        GGB_CUDA(cudaFuncSetAttribute(gemm_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((rows + GM_BM - 1) / GM_BM, (tokens + GM_BN - 1) / GM_BN);
+    gemm_kernel<TYPE><<<grid, GM_THREADS, smem, st>>>((const uint8_t*)w, ggb_row_stride(TYPE, k), rows, k, (const __nv_bfloat16*)x, tokens, y, y_stride);
+    GGB_CHECK_LAUNCH("ggb_gemm");
+    return GGB_OK;
+}
+
+extern "C" int ggb_gemm(int type, const void* w, int rows, int k, const void* x_bf16, int tokens, float* y, int64_t y_stride, void* stream) {
+    if (rows < 0 || tokens < 0 || k <= 0 || (k % GM_BK)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: k=%d must be a positive multiple of %d", k, GM_BK);
+    if (rows == 0 || tokens == 0) return GGB_OK;
+    if (!w || !x_bf16 || !y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: null pointer");
+    if (((uintptr_t)w & 15) || ((uintptr_t)x_bf16 & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: operands must be 16-byte aligned");
+    if (y_stride < rows) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: y_stride smaller than rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (type) {
+        case GGB_TYPE_Q4_K: return launch_gemm<GGB_TYPE_Q4_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q6_K: return launch_gemm<GGB_TYPE_Q6_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q8_0: return launch_gemm<GGB_TYPE_Q8_0>(w, rows, k, x_bf16, tokens, y, y_stride, st);
+        default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemm: unsupported weight type %d", type);
+    }
+}

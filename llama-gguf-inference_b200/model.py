@@ -16,6 +16,7 @@ Position, token and step counters live in device memory, so one captured graph s
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass
 
@@ -250,14 +251,64 @@ class Slot:
                 self.stream.synchronize()
         self.reset()
 
+    def _prefill_gemm(self, tokens: list[int], start: int):
+        """Many tokens at once: tcgen05 dequant-GEMMs + batched attention (csrc/gemm.cu, csrc/prefill.cu).  The last
+        token's hidden state then goes through the decode head (arg-max, next embedding), like the GEMV path."""
+        torch, lib, hp, e = self.torch, self.lib, self.hp, self.eng
+        T = len(tokens)
+        B = e.prefill_buffers(T)
+        s = self.stream.cuda_stream
+        qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
+
+        def gemm(w, xb, y):
+            cabi.check(lib.ggb_gemm(w.type, w.ptr, w.rows, w.k, xb.data_ptr(), T, y.data_ptr(), w.rows, s), "gemm")
+
+        def to_bf16(x, n):
+            cabi.check(lib.ggb_f32_to_bf16(x.data_ptr(), B["xb"].data_ptr(), n, s), "f32_to_bf16")
+
+        with torch.cuda.stream(self.stream):
+            ids = torch.tensor(tokens, dtype=torch.int32).to(e.dev)
+            X, XN, Y = B["x"], B["xn"], B["y"]
+            cabi.check(lib.ggb_embed_rows(e.emb_type, e.emb_canon.data_ptr(), hp.d, ids.data_ptr(), T, X.data_ptr(), s), "embed_rows")
+            for i, L in enumerate(e.layers):
+                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["attn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
+                to_bf16(XN, T * hp.d)
+                gemm(L["wq"], B["xb"], B["q"]); gemm(L["wk"], B["xb"], B["k"]); gemm(L["wv"], B["xb"], B["v"])
+                cabi.check(lib.ggb_rope_kv_prefill(B["q"].data_ptr(), B["k"].data_ptr(), B["v"].data_ptr(), T, start, hp.n_head, hp.n_kv,
+                                                   hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), s), "rope_kv_prefill")
+                cabi.check(lib.ggb_attn_prefill(B["q"].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), T, start, hp.n_head, hp.n_kv,
+                                                hp.head_dim, B["att"].data_ptr(), s), "attn_prefill")
+                to_bf16(B["att"], T * qd)
+                gemm(L["wo"], B["xb"], Y)
+                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
+                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["ffn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
+                to_bf16(XN, T * hp.d)
+                gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
+                cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
+                to_bf16(B["gate"], T * hp.ff)
+                gemm(L["wd"], B["xb"], Y)
+                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
+            self.x.copy_(X[(T - 1) * hp.d:T * hp.d], non_blocking=True)
+            self._set_tok_pos(int(tokens[-1]), start + T - 1)
+            self._enqueue_head(s)
+            self.stream.synchronize()
+        self.n_past = start + T
+
     def prefill(self, tokens: list[int], start_pos: int | None = None):
-        """Feed tokens at positions start_pos.. (default: append).  v1 runs them one by one through the decode
-        kernels; the last one also runs the head, which emits the first generated token (greedy) and the logits."""
+        """Feed tokens at positions start_pos.. (default: append).  Long prompts go through the tcgen05 GEMM path
+        (tolerance-level numerics, like upstream's batched CUDA path); short ones run token by token through the
+        decode kernels (bit-exact integer path).  The last token also runs the head, which emits the first
+        generated token (greedy) and the logits."""
         if not tokens:
             raise ValueError("empty prompt")
         start = self.n_past if start_pos is None else start_pos
         if start + len(tokens) >= self.n_ctx:
             raise ValueError(f"prompt of {len(tokens)} tokens does not fit the context ({self.n_ctx})")
+        e = self.eng
+        if e.tp_size == 1 and len(tokens) >= e.gemm_prefill_min:
+            for c0 in range(0, len(tokens), e.prefill_chunk):
+                self._prefill_gemm(tokens[c0:c0 + e.prefill_chunk], start + c0)
+            return
         with self.torch.cuda.stream(self.stream):
             for i, t in enumerate(tokens):
                 self._set_tok_pos(int(t), start + i)
@@ -350,6 +401,9 @@ class Engine:
         t0 = time.time()
         self._load_weights()
         self.load_seconds = time.time() - t0
+        self.gemm_prefill_min = int(os.environ.get("GGB_GEMM_PREFILL_MIN", "32"))   # prompts at least this long use the GEMM path
+        self.prefill_chunk = 2048
+        self._pf = None
         self.slots = [Slot(self, i) for i in range(max(1, n_slots))]
         if verbose:
             print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
@@ -422,6 +476,18 @@ class Engine:
         if "rope_freqs.weight" in f.tensors:
             ff = self._load_f32("rope_freqs.weight").cpu().numpy()
         self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
+
+    def prefill_buffers(self, T: int) -> dict:
+        """activation buffers of the GEMM prefill path, sized for the largest chunk seen so far (shared by the slots)"""
+        cap = max(T, 64)
+        if self._pf is None or self._pf["cap"] < cap:
+            torch, hp, dev = self.torch, self.hp, self.dev
+            f32 = lambda n: torch.empty(cap * n, dtype=torch.float32, device=dev)  # noqa: E731
+            qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
+            self._pf = {"cap": cap, "x": f32(hp.d), "xn": f32(hp.d), "y": f32(hp.d), "q": f32(qd), "k": f32(kvd), "v": f32(kvd),
+                        "att": f32(qd), "gate": f32(hp.ff), "up": f32(hp.ff),
+                        "xb": torch.empty(cap * max(hp.d, hp.ff, qd), dtype=torch.bfloat16, device=dev)}
+        return self._pf
 
     def launches_per_step(self) -> int:
         """kernels of libggufb200 launched by one decode step (layers + head); NCCL kernels are not counted."""

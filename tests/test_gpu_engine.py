@@ -137,3 +137,36 @@ def test_context_limits_and_errors(oracle, model_dir):
         eng.prefill([])
     assert len(eng.generate(PROMPT, 26)) == 26   # fills the window up to the last slot
     eng.close()
+
+
+@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K")])
+def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_dir, preset, ftype):
+    """Long prompts take the tcgen05 GEMM path (bf16 operands, f32 accumulation) instead of the integer GEMV path:
+    logits after the prompt must agree with the GEMV path and with the oracle inside the bf16 tolerance, the KV
+    cache must agree to f16 rounding, and decoding continues from the GEMM-filled cache."""
+    import torch
+    from ggufb200.model import Engine
+    path = _model(model_dir, preset, ftype)
+    rng = np.random.default_rng(5)
+    prompt = [1] + [int(t) for t in rng.integers(300, 500, size=70)]
+    eng = Engine(path, n_ctx=256)
+    eng.warmup()
+    eng.gemm_prefill_min = 10 ** 9
+    eng.reset(); eng.prefill(prompt)
+    l_gemv, kc_gemv = eng.last_logits(), eng.slots[0].kc.float().cpu().numpy()
+    eng.gemm_prefill_min = 16
+    eng.reset(); eng.prefill(prompt)
+    l_gemm, kc_gemm = eng.last_logits(), eng.slots[0].kc.float().cpu().numpy()
+    n = len(prompt)
+    rel = float(np.linalg.norm(l_gemm - l_gemv) / np.linalg.norm(l_gemv))
+    assert rel <= 5e-2, rel
+    assert np.abs(kc_gemm[:, :n] - kc_gemv[:, :n]).max() <= 5e-2 * np.abs(kc_gemv[:, :n]).max()
+    ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")
+    for i, t in enumerate(prompt):
+        lr = ref.forward(t, i)
+    assert float(np.linalg.norm(l_gemm - lr) / np.linalg.norm(lr)) <= 5e-2
+    assert np.corrcoef(l_gemm, lr)[0, 1] > 0.995
+    eng.decode(8)                           # decode continues from the GEMM-filled cache
+    toks = eng.tokens(9)
+    assert len(toks) == 9 and all(0 <= t < eng.hp.vocab for t in toks)
+    eng.close()
