@@ -62,7 +62,6 @@ struct GemvK {
     int ring_bytes;            /* per warp = n_slots * slot_bytes: 4.5 KB (Q4_K) .. 8.5 KB (Q8_0) -> 72..136 KB per CTA */
     int rowv_off;              /* byte offset of the per-row results in dynamic shared memory */
     unsigned tl_slot;
-    int l2_prefetch;
     int rq[GGB_MAX_SEG], rr[GGB_MAX_SEG];   /* rows = rq*grid + rr: CTA c starts at c*rq + min(c, rr) (no division on the device) */
     const float* x;
     const float* norm_w;
@@ -373,24 +372,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < STEPS; i++) if (ip < npairs) issue_step();
-    }
-
-    // optional: ask the L2 to pull this CTA's whole byte range from HBM now (no registers / smem involved), so
-    // that HBM keeps streaming through the dependency wait and the prologue and the ring refills hit L2
-    if (P.l2_prefetch) {
-        constexpr int PIECE = 8192;
-        auto pf = [&](int sg, int r0, int cnt) {
-            if (cnt <= 0) return;
-            const uint8_t* base = P.seg[sg].w + (int64_t)r0 * P.seg[sg].stride;
-            const int64_t bytes = (int64_t)cnt * P.seg[sg].stride;
-            for (int64_t off = (int64_t)tid * PIECE; off < bytes; off += (int64_t)GEMV_THREADS * PIECE) {
-                const uint32_t sz = (uint32_t)min((int64_t)PIECE, bytes - off) & ~15u;
-                if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
-            }
-        };
-        pf(0, r0_0, cnt0);
-        if (P.n_seg > 1) pf(1, r0_1, cnt1);
-        if (P.n_seg > 2) pf(2, r0_2, cnt2);
     }
 
     // the RMSNorm gains are weights too: fetch this lane's eight for the warp's first 256-block now
@@ -725,8 +706,6 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
 #ifdef GGB_TIMELINE
     P.tl_slot = g_tl_counter++;
 #endif
-    static int l2pf = env_int("GGB_L2_PREFETCH", 0);
-    P.l2_prefetch = l2pf;
     const int grid = default_grid(a);
     for (int s = 0; s < a->n_seg; s++) { P.rq[s] = a->seg[s].rows / grid; P.rr[s] = a->seg[s].rows % grid; }
     int64_t max_local = 0;

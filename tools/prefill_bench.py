@@ -37,15 +37,16 @@ def main():
     ap.add_argument("--ftype", default="Q4_K_M")
     ap.add_argument("--tokens", type=int, default=2048)
     ap.add_argument("--gemm-only", action="store_true")
+    ap.add_argument("--one", action="store_true", help="a single GEMM shape (for ncu)")
     a = ap.parse_args()
     L = cabi.lib()
     T = a.tokens
     names = {12: "Q4_K", 14: "Q6_K", 8: "Q8_0"}
-    for qt in (12, 14, 8):
-        for rows, k in ((4096, 4096), (14336, 4096), (4096, 14336)):
+    for qt in ((12,) if a.one else (12, 14, 8)):
+        for rows, k in (((14336, 4096),) if a.one else ((4096, 4096), (14336, 4096), (4096, 14336))):
             ms, tf = gemm_alone(L, qt, rows, k, T)
             print(f"gemm {names[qt]} rows={rows:6d} k={k:6d} tokens={T}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s", flush=True)
-    if a.gemm_only:
+    if a.gemm_only or a.one:
         return
     cfg = synth.PRESETS[a.model]
     path = f"/dev/shm/pf-{a.model}-{a.ftype}.gguf"
