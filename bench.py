@@ -260,7 +260,7 @@ def run_ours(args):
                     f"tp{tp}: q/k/v/gate/up/lm-head column-split, attn_output/ffn_down row-split, NCCL all-reduce of f64 partials "
                     f"after each row-split projection ({2 * cfg.n_layer} per token) + one 8-byte arg-max all-reduce" if tp > 1
                     else f"{world} independent replicas"),
-                "l2": "inputs_larger_than_l2 (4.6 GB of weights per step vs 126 MB L2)",
+                "l2": f"inputs_larger_than_l2 ({bpt['weights'] / tp / 1e9:.1f} GB of weights per GPU per step vs 126 MB L2)",
                 "launch": "CUDA graph per step" + ("" if args.no_pdl else " + programmatic dependent launch"),
                 "step_bytes": int(step_bytes),
                 "step_roofline_frac_of_measured_hbm": (step_bytes * value / world / 1e9) / peak,

@@ -227,7 +227,7 @@ class GGUFWriter:
     def __init__(self, alignment: int = DEFAULT_ALIGNMENT):
         self.alignment = alignment
         self._kv: list[bytes] = []
-        self._tensors: list[tuple[str, tuple, int, np.ndarray]] = []
+        self._tensors: list[tuple] = []   # (name, ne, type, bytes-or-callable, size)
 
     @staticmethod
     def _s(s: str) -> bytes:
@@ -252,28 +252,43 @@ class GGUFWriter:
             out += np.asarray(values, dtype=np.dtype(_NP[etype]).newbyteorder("<")).tobytes()
         self._kv.append(out)
 
-    def add_tensor(self, name: str, ne: tuple, ggml_type: int, raw: np.ndarray):
-        """ne is in ggml order (innermost first); raw = the tensor's bytes (any dtype, C-contiguous)."""
-        raw = np.ascontiguousarray(raw).reshape(-1).view(np.uint8)
+    def add_tensor(self, name: str, ne: tuple, ggml_type: int, raw):
+        """ne is in ggml order (innermost first); raw = the tensor's bytes (any dtype, C-contiguous), or a
+        zero-argument callable producing them at write time (keeps a 40 GB model out of host memory)."""
         rows = 1
         for d in ne[1:]:
             rows *= d
-        if raw.size != rows * row_bytes(ggml_type, ne[0]):
-            raise GGUFError(f"{name}: {raw.size} bytes given, {rows * row_bytes(ggml_type, ne[0])} expected")
-        self._tensors.append((name, tuple(ne), ggml_type, raw))
+        size = rows * row_bytes(ggml_type, ne[0])
+        if not callable(raw):
+            raw = np.ascontiguousarray(raw).reshape(-1).view(np.uint8)
+            if raw.size != size:
+                raise GGUFError(f"{name}: {raw.size} bytes given, {size} expected")
+        self._tensors.append((name, tuple(ne), ggml_type, raw, size))
 
     def write(self, path: str):
         a = self.alignment
         head = struct.pack("<IIQQ", GGUF_MAGIC, 3, len(self._tensors), len(self._kv)) + b"".join(self._kv)
         infos, rel = [], 0
-        for name, ne, tt, raw in self._tensors:
+        for name, ne, tt, _, size in self._tensors:
             infos.append(self._s(name) + struct.pack("<I", len(ne)) + b"".join(struct.pack("<Q", d) for d in ne)
                          + struct.pack("<IQ", tt, rel))
-            rel = (rel + raw.size + a - 1) // a * a
+            rel = (rel + size + a - 1) // a * a
         head += b"".join(infos)
         with open(path, "wb") as f:
             f.write(head)
             f.write(b"\0" * ((-len(head)) % a))
-            for _, _, _, raw in self._tensors:
-                f.write(raw.data)
-                f.write(b"\0" * ((-raw.size) % a))
+            # lazily produced tensors are generated a few ahead on worker threads, written in order
+            from concurrent.futures import ThreadPoolExecutor
+            ahead = max(1, min(6, (os.cpu_count() or 2) - 1))
+            with ThreadPoolExecutor(ahead) as pool:
+                pending = {}
+                for i, (name, _, _, raw, size) in enumerate(self._tensors):
+                    for j in range(i, min(i + ahead, len(self._tensors))):
+                        if j not in pending and callable(self._tensors[j][3]):
+                            pending[j] = pool.submit(self._tensors[j][3])
+                    if callable(raw):
+                        raw = np.ascontiguousarray(pending.pop(i).result()).reshape(-1).view(np.uint8)
+                        if raw.size != size:
+                            raise GGUFError(f"{name}: {raw.size} bytes produced, {size} expected")
+                    f.write(raw.data)
+                    f.write(b"\0" * ((-size) % a))

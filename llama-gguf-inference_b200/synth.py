@@ -228,7 +228,8 @@ def write_gguf(path: str, cfg: LlamaConfig | str, ftype: str = Q4_K_M, seed: int
     w.add("tokenizer.ggml.add_bos_token", G.T_BOOL, True)
     w.add("tokenizer.ggml.add_eos_token", G.T_BOOL, False)
     for idx, (name, ne, tt, std) in enumerate(tensor_plan(cfg, ftype)):
-        rng = np.random.Generator(np.random.PCG64(seed + idx))
-        w.add_tensor(name, ne, tt, random_tensor(name, ne, tt, std, rng))
+        def make(idx=idx, name=name, ne=ne, tt=tt, std=std):
+            return random_tensor(name, ne, tt, std, np.random.Generator(np.random.PCG64(seed + idx)))
+        w.add_tensor(name, ne, tt, make)
     w.write(path)
     return {"config": asdict(cfg), "ftype": ftype, "seed": seed, "bytes_per_token": weight_bytes_per_token(cfg, ftype)}
