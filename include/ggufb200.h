@@ -174,6 +174,46 @@ size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim);
 int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
                     int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream);
 
+/* ---- small-batch decode: several sequences ("slots"), ONE new token each, in one pass over the weights.
+ * Stands in for llama-server's continuous batching (ggml mul_mat with a few activation columns); the arithmetic
+ * per token is the batch-1 GEMV's, so a sequence decodes to bit-identical logits alone or inside a batch.
+ *
+ * ggb_act_prep: what the GEMV prologue does, once per token instead of once per CTA: optional rms_norm * norm_w,
+ *   then quantisation (Q8_K, or Q8_0 when q8_0 != 0) into an "activation image" of ggb_act_image_bytes(k) bytes
+ *   per token (int8 codes in the kernel's bank-swizzled order | per-16 sums | block scales).  x is [nb][k].
+ * ggb_gemv_batch: y_s[b][r] = dot(W_s[r], x[b]) for nb tokens; epilogues STORE, RESIDUAL (y_0[b][r] =
+ *   residual[b][r] + dot, y_0 may alias residual), SWIGLU.  Outputs are row-major [nb][rows_s].  Launches as many
+ *   passes of <= 8 tokens as shared memory allows. */
+int64_t ggb_act_image_bytes(int64_t k);
+int ggb_act_prep(const float* x, const float* norm_w, float eps, int64_t k, int nb, int q8_0, void* act, int use_pdl, void* stream);
+
+typedef struct ggb_gemv_batch_args {
+    int32_t n_seg;
+    int32_t k;
+    ggb_gemv_seg seg[GGB_MAX_SEG];
+    int32_t epilogue;          /* GGB_EPI_STORE / GGB_EPI_RESIDUAL / GGB_EPI_SWIGLU */
+    int32_t nb;                /* tokens */
+    const void* act;           /* [nb][ggb_act_image_bytes(k)] from ggb_act_prep */
+    const float* residual;     /* [nb][rows_0] (GGB_EPI_RESIDUAL) */
+    int32_t use_pdl;
+    int32_t grid;              /* 0 = one CTA per SM */
+} ggb_gemv_batch_args;
+int ggb_gemv_batch(const ggb_gemv_batch_args* args, void* stream);
+
+/* Per-token cache addressing for the batch: token b belongs to slot slot_dev[b] at position pos_dev[b]; the caches
+ * of all slots live in one allocation, slot s starting slot_stride elements after slot s-1
+ * (cache row = [n_kv*hd] f16).  pos_dev[b] < 0 marks an idle entry (skipped).
+ * ggb_rope_kv_batch: rotate q [nb][n_head*hd] in place, rotate k and store k, v as f16 at (slot, pos)
+ *   (ggml_rope NORM mode + ggml_cpy).  ggb_attn_decode_batch: the one-token attention of ggb_attn_decode for every
+ *   batch entry, out [nb][n_head*hd].  ggb_argmax_rows: first index of the maximum of each row of x [nb][n]. */
+int ggb_rope_kv_batch(float* q, const float* k, const float* v, int nb, const int32_t* pos_dev, const int32_t* slot_dev,
+                      int64_t slot_stride, int n_head, int n_kv, int head_dim, int n_rot, const float* rope_tab,
+                      uint16_t* kcache, uint16_t* vcache, void* stream);
+int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
+                          const int32_t* slot_dev, int64_t slot_stride, int nb, int n_head, int n_kv, int head_dim,
+                          int n_ctx, float* out, int use_pdl, void* stream);
+int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+"""Batched decode: several sequences ("slots") advance by one token each in ONE pass over the weights.
+
+What llama-server's continuous batching does for concurrent requests (the reference's benchmark drives it with
+`--concurrent N`, /root/reference/scripts/benchmark.py:178-214): the decode tokens of all busy slots form one batch.
+Here the batch goes through csrc/gemv_batch.cu (weights streamed once for up to 8 tokens per launch) with per-token
+cache addressing for RoPE / KV write / attention; every token's arithmetic is the batch-1 path's, so a sequence
+produces bit-identical logits alone or in a batch (tests/test_gpu_engine.py).
+
+The host owns the schedule: each step it hands (slot, token, position) triples; they are staged through pinned
+memory, one captured CUDA graph per batch size replays the whole forward pass, and the greedy tokens (and, for
+sampled requests, logits rows) are read back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+
+
+class BatchDecoder:
+    def __init__(self, eng, max_batch: int | None = None):
+        torch = eng.torch
+        if eng.tp_size != 1:
+            raise cabi.GGBError("batched decode is single-GPU (tensor-parallel engines time-slice their slots)")
+        self.eng, self.torch, self.lib, self.hp = eng, torch, eng.lib, eng.hp
+        hp, dev = eng.hp, eng.dev
+        self.nb_max = NB = int(max_batch or len(eng.slots))
+        self.stream = eng.stream
+        self.use_pdl = eng.use_pdl
+        qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        self.x, self.q, self.k, self.v, self.att = f32(NB, hp.d), f32(NB, qd), f32(NB, kvd), f32(NB, kvd), f32(NB, qd)
+        self.h, self.logits = f32(NB, hp.ff), f32(NB, hp.vocab)
+        kmax = max(hp.d, hp.ff, qd)
+        self.act = torch.zeros(NB * self.lib.ggb_act_image_bytes(kmax), dtype=torch.uint8, device=dev)
+        self.meta = torch.zeros((3, NB), dtype=torch.int32, device=dev)          # token ids | positions | slots
+        self.meta_host = torch.zeros((3, NB), dtype=torch.int32).pin_memory()
+        self.next_tok = torch.zeros(NB, dtype=torch.int32, device=dev)
+        self.next_host = torch.zeros(NB, dtype=torch.int32).pin_memory()
+        self.logits_host = None
+        self.slot_stride = hp.n_layer * eng.n_ctx * kvd                         # elements between two slots' caches
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ one forward pass for nb tokens
+    def _enqueue(self, nb: int, s: int):
+        lib, hp, e, pdl = self.lib, self.hp, self.eng, self.use_pdl
+        qd = hp.n_head * hp.head_dim
+        ids, pos, slot = (self.meta[i].data_ptr() for i in range(3))
+        act = self.act.data_ptr()
+
+        def prep(x, norm, k, w):
+            cabi.check(lib.ggb_act_prep(x.data_ptr(), norm.data_ptr() if norm is not None else 0, hp.eps, k, nb,
+                                        int(w.type == cabi.Q8_0), act, pdl, s), "act_prep")
+
+        def gemv(segs, k, epi, residual=0):
+            a = cabi.make_gemv_batch_args(segs, k, act, nb, epilogue=epi, residual=residual, use_pdl=pdl)
+            cabi.check(lib.ggb_gemv_batch(C.byref(a), s), "gemv_batch")
+
+        cabi.check(lib.ggb_embed_rows(e.emb_type, e.emb_canon.data_ptr(), hp.d, ids, nb, self.x.data_ptr(), s), "embed_rows")
+        xp = self.x.data_ptr()
+        for i, L in enumerate(e.layers):
+            prep(self.x, L["attn_norm"], hp.d, L["wq"])
+            gemv([(L["wq"].ptr, L["wq"].type, L["wq"].rows, self.q.data_ptr()),
+                  (L["wk"].ptr, L["wk"].type, L["wk"].rows, self.k.data_ptr()),
+                  (L["wv"].ptr, L["wv"].type, L["wv"].rows, self.v.data_ptr())], hp.d, cabi.EPI_STORE)
+            kc, vc = e.k_all[0, i].data_ptr(), e.v_all[0, i].data_ptr()
+            cabi.check(lib.ggb_rope_kv_batch(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), nb, pos, slot, self.slot_stride,
+                                             hp.n_head, hp.n_kv, hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), kc, vc, s), "rope_kv_batch")
+            cabi.check(lib.ggb_attn_decode_batch(self.q.data_ptr(), kc, vc, pos, slot, self.slot_stride, nb, hp.n_head, hp.n_kv,
+                                                 hp.head_dim, e.n_ctx, self.att.data_ptr(), 0, s), "attn_decode_batch")
+            prep(self.att, None, qd, L["wo"])
+            gemv([(L["wo"].ptr, L["wo"].type, L["wo"].rows, xp)], qd, cabi.EPI_RESIDUAL, residual=xp)
+            prep(self.x, L["ffn_norm"], hp.d, L["wg"])
+            gemv([(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
+                  (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)], hp.d, cabi.EPI_SWIGLU)
+            prep(self.h, None, hp.ff, L["wd"])
+            gemv([(L["wd"].ptr, L["wd"].type, L["wd"].rows, xp)], hp.ff, cabi.EPI_RESIDUAL, residual=xp)
+        prep(self.x, e.out_norm, hp.d, e.w_out)
+        gemv([(e.w_out.ptr, e.w_out.type, e.w_out.rows, self.logits.data_ptr())], hp.d, cabi.EPI_STORE)
+        cabi.check(lib.ggb_argmax_rows(self.logits.data_ptr(), hp.vocab, nb, self.next_tok.data_ptr(), s), "argmax_rows")
+
+    def launches_per_step(self, nb: int) -> int:
+        passes = lambda k: -(-nb // 8)   # noqa: E731  (an upper bound: very large K runs more, smaller passes)
+        per_layer = 4 + passes(0) * 4 + 2
+        return nb + self.hp.n_layer * per_layer + 1 + passes(0) + 1
+
+    # ------------------------------------------------------------------ public
+    def step(self, entries) -> list[int]:
+        """entries: [(slot index, token id, position)], distinct slots.  Runs the tokens through the model, writes
+        their K/V at the given positions and returns the greedy next token of each entry (logits stay on the
+        device: logits_row)."""
+        nb = len(entries)
+        if not 0 < nb <= self.nb_max:
+            raise ValueError(f"batch of {nb} entries (1..{self.nb_max})")
+        e, torch = self.eng, self.torch
+        slots = [en[0] for en in entries]
+        if len(set(slots)) != nb:
+            raise ValueError("a slot appears twice in one batch")
+        for sl, tok, pos in entries:
+            if not (0 <= sl < len(e.slots) and 0 <= pos < e.n_ctx and 0 <= tok < self.hp.vocab):
+                raise ValueError(f"bad batch entry (slot {sl}, token {tok}, position {pos})")
+        mh = self.meta_host
+        mh[0, :nb] = torch.tensor([en[1] for en in entries], dtype=torch.int32)
+        mh[1, :nb] = torch.tensor([en[2] for en in entries], dtype=torch.int32)
+        mh[2, :nb] = torch.tensor(slots, dtype=torch.int32)
+        with torch.cuda.stream(self.stream):
+            self.meta.copy_(mh, non_blocking=True)
+            if not e.use_graph:
+                self._enqueue(nb, self.stream.cuda_stream)
+            else:
+                g = self._graphs.get(nb)
+                if g is None:
+                    self._enqueue(nb, self.stream.cuda_stream)      # first use: sets kernel attributes outside capture
+                    self.stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self._enqueue(nb, torch.cuda.current_stream().cuda_stream)
+                    self._graphs[nb] = g
+                g.replay()
+            self.next_host.copy_(self.next_tok, non_blocking=True)
+        self.stream.synchronize()
+        for sl, _, pos in entries:
+            e.slots[sl].n_past = pos + 1
+            e.slots[sl].chain_valid = False     # the slot's own device-side (token, position, x) no longer match
+        return self.next_host[:nb].tolist()
+
+    def logits_row(self, b: int) -> np.ndarray:
+        if self.logits_host is None:
+            self.logits_host = self.torch.zeros(self.hp.vocab, dtype=self.torch.float32).pin_memory()
+        with self.torch.cuda.stream(self.stream):
+            self.logits_host.copy_(self.logits[b], non_blocking=True)
+        self.stream.synchronize()
+        return self.logits_host.numpy()

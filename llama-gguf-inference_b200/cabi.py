@@ -26,6 +26,7 @@ EXPORTS = [
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
+    "ggb_act_image_bytes", "ggb_act_prep", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows",
 ]
 
 
@@ -50,6 +51,16 @@ class GemvArgs(C.Structure):
         ("kcache", C.c_void_p), ("vcache", C.c_void_p),
         ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
         ("grid", C.c_int32),
+    ]
+
+
+class GemvBatchArgs(C.Structure):
+    _fields_ = [
+        ("n_seg", C.c_int32), ("k", C.c_int32),
+        ("seg", GemvSeg * MAX_SEG),
+        ("epilogue", C.c_int32), ("nb", C.c_int32),
+        ("act", C.c_void_p), ("residual", C.c_void_p),
+        ("use_pdl", C.c_int32), ("grid", C.c_int32),
     ]
 
 
@@ -91,6 +102,12 @@ def lib() -> C.CDLL:
         "ggb_rope_kv_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
         "ggb_attn_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "ggb_add_f32": ([vp, vp, i64, vp], i32),
+        "ggb_act_image_bytes": ([i64], i64),
+        "ggb_act_prep": ([vp, vp, f32, i64, i32, i32, vp, i32, vp], i32),
+        "ggb_gemv_batch": ([C.POINTER(GemvBatchArgs), vp], i32),
+        "ggb_rope_kv_batch": ([vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+        "ggb_attn_decode_batch": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, vp], i32),
+        "ggb_argmax_rows": ([vp, i64, i32, vp, vp], i32),
         "ggb_argmax_pack": ([vp, vp, i32, i32, vp, vp], i32),
         "ggb_argmax_unpack_next": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp], i32),
     }
@@ -130,4 +147,14 @@ def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w
     a.x, a.norm_w, a.eps, a.use_pdl, a.residual = x, norm_w, eps, use_pdl, residual
     a.pos_dev, a.rope_tab, a.n_rot, a.head_dim = pos_dev, rope_tab, n_rot, head_dim
     a.kcache, a.vcache, a.part_val, a.part_idx, a.grid = kcache, vcache, part_val, part_idx, grid
+    return a
+
+
+def make_gemv_batch_args(segs, k, act, nb, *, epilogue=EPI_STORE, residual=0, use_pdl=0, grid=0) -> GemvBatchArgs:
+    """segs: list of (w_ptr, type, rows, y_ptr); outputs are [nb][rows]."""
+    a = GemvBatchArgs()
+    a.n_seg, a.k = len(segs), k
+    for i, (w, t, rows, y) in enumerate(segs):
+        a.seg[i].w, a.seg[i].type, a.seg[i].rows, a.seg[i].y = w, t, rows, y
+    a.epilogue, a.nb, a.act, a.residual, a.use_pdl, a.grid = epilogue, nb, act, residual, use_pdl, grid
     return a

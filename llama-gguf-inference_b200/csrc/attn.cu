@@ -25,7 +25,8 @@ namespace cg = cooperative_groups;
 template <int HD>
 __global__ void __cluster_dims__(ATTN_CL, 1, 1) __launch_bounds__(ATTN_WARPS * 32)
 attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
-                   const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out) {
+                   const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
+                   const int32_t* __restrict__ slot_dev, int64_t slot_stride) {
     constexpr int LPG = HD / 8;        // lanes per position (each lane owns 8 consecutive dims = one 16-byte load)
     constexpr int PPW = 32 / LPG;      // positions per warp step
     constexpr int SLOTS = ATTN_WARPS * PPW;
@@ -46,7 +47,14 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     const int64_t kv_stride = (int64_t)n_kv * HD;
 
     pdl_wait();
-    const int n = *pos_dev + 1;
+    // batch entry blockIdx.y: its own query row, position and (through slot_dev) cache
+    const int be = blockIdx.y;
+    const int pos = pos_dev[be];
+    if (pos < 0) return;   /* idle batch entry: the whole cluster leaves before any cluster barrier */
+    if (slot_dev) { const int64_t o = (int64_t)slot_dev[be] * slot_stride; kc += o; vc += o; }
+    q += (int64_t)be * n_head * HD;
+    out += (int64_t)be * n_head * HD;
+    const int n = pos + 1;
     int chunk = (n + ATTN_CL - 1) / ATTN_CL;
     chunk = (chunk + 7) & ~7;
     const int p_begin = min(n, crank * chunk), p_end = min(n, p_begin + chunk);
@@ -153,7 +161,8 @@ extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
 
 template <int HD>
 static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
-                       int n_ctx, float* out, int use_pdl, cudaStream_t st) {
+                       int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev = nullptr, int64_t slot_stride = 0,
+                       int nb = 1) {
     int chunk_max = (n_ctx + ATTN_CL - 1) / ATTN_CL;
     chunk_max = (chunk_max + 7) & ~7;
     const size_t smem = (size_t)chunk_max * sizeof(float);
@@ -164,7 +173,7 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
         attr = 96 * 1024;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_head * ATTN_CL);
+    cfg.gridDim = dim3(n_head * ATTN_CL, nb);
     cfg.blockDim = dim3(ATTN_WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -173,7 +182,7 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD>, q, kc, vc, pos_dev, n_head, n_kv, out));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
     return GGB_OK;
 }
 
@@ -187,4 +196,18 @@ extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uin
     if (head_dim == 128) return launch_attn<128>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     if (head_dim == 64) return launch_attn<64>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: head_dim=%d (supported: 64, 128)", head_dim);
+}
+
+extern "C" int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
+                                     const int32_t* slot_dev, int64_t slot_stride, int nb, int n_head, int n_kv, int head_dim,
+                                     int n_ctx, float* out, int use_pdl, void* stream) {
+    if (nb < 0 || nb > 65535) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: nb=%d out of range", nb);
+    if (nb == 0) return GGB_OK;
+    if (!q || !kcache || !vcache || !pos_dev || !slot_dev || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: null pointer");
+    if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
+    if (n_ctx <= 0 || slot_stride < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: n_ctx must be positive, slot_stride non-negative");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) return launch_attn<128>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+    if (head_dim == 64) return launch_attn<64>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+    GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode_batch: head_dim=%d (supported: 64, 128)", head_dim);
 }

@@ -67,6 +67,92 @@ extern "C" int ggb_rope_kv_prefill(float* q, const float* k, const float* v, int
     return GGB_OK;
 }
 
+// The same rotation for a decode batch: token b sits at position pos[b] of slot slot[b]'s cache (all slots in one
+// allocation, slot_stride elements apart).  pos[b] < 0 = idle entry.
+__global__ void rope_kv_batch_kernel(float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int nb,
+                                     const int32_t* __restrict__ pos_dev, const int32_t* __restrict__ slot_dev, int64_t slot_stride,
+                                     int n_head, int n_kv, int hd, int n_rot, const float* __restrict__ tab,
+                                     uint16_t* __restrict__ kc, uint16_t* __restrict__ vc) {
+    const int qd = n_head * hd, kvd = n_kv * hd;
+    const int pairs_per_tok = (qd + 2 * kvd) / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * pairs_per_tok) return;
+    const int t = idx / pairs_per_tok, p = idx - t * pairs_per_tok;
+    const int pos = pos_dev[t];
+    if (pos < 0) return;
+    const int64_t cbase = (int64_t)slot_dev[t] * slot_stride + (int64_t)pos * kvd;
+    const int e = 2 * p;
+    const float* rt = tab + (int64_t)pos * n_rot;
+    if (e < qd) {
+        const int j = e % hd;
+        float* x = q + (int64_t)t * qd + e;
+        if (j < n_rot) {
+            const float c = rt[j], s = rt[j + 1], a = x[0], b = x[1];
+            x[0] = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s));
+            x[1] = __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, c));
+        }
+    } else if (e < qd + kvd) {
+        const int r = e - qd, j = r % hd;
+        float a = k[(int64_t)t * kvd + r], b = k[(int64_t)t * kvd + r + 1];
+        if (j < n_rot) {
+            const float c = rt[j], s = rt[j + 1], a0 = a, b0 = b;
+            a = __fsub_rn(__fmul_rn(a0, c), __fmul_rn(b0, s));
+            b = __fadd_rn(__fmul_rn(a0, s), __fmul_rn(b0, c));
+        }
+        *reinterpret_cast<uint32_t*>(kc + cbase + r) = (uint32_t)f2h(a) | ((uint32_t)f2h(b) << 16);
+    } else {
+        const int r = e - qd - kvd;
+        const float a = v[(int64_t)t * kvd + r], b = v[(int64_t)t * kvd + r + 1];
+        *reinterpret_cast<uint32_t*>(vc + cbase + r) = (uint32_t)f2h(a) | ((uint32_t)f2h(b) << 16);
+    }
+}
+
+extern "C" int ggb_rope_kv_batch(float* q, const float* k, const float* v, int nb, const int32_t* pos_dev, const int32_t* slot_dev,
+                                 int64_t slot_stride, int n_head, int n_kv, int head_dim, int n_rot, const float* rope_tab,
+                                 uint16_t* kcache, uint16_t* vcache, void* stream) {
+    if (nb < 0 || n_head <= 0 || n_kv <= 0 || head_dim <= 0 || (head_dim & 1) || (n_rot & 1) || n_rot > head_dim || slot_stride < 0)
+        GGB_FAIL(GGB_ERR_ARG, "ggb_rope_kv_batch: bad shape");
+    if (nb == 0) return GGB_OK;
+    if (!q || !k || !v || !pos_dev || !slot_dev || !rope_tab || !kcache || !vcache) GGB_FAIL(GGB_ERR_ARG, "ggb_rope_kv_batch: null pointer");
+    const int64_t total = (int64_t)nb * ((n_head + 2 * n_kv) * head_dim / 2);
+    rope_kv_batch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, k, v, nb, pos_dev, slot_dev, slot_stride, n_head, n_kv,
+                                                                                          head_dim, n_rot, rope_tab, kcache, vcache);
+    GGB_CHECK_LAUNCH("ggb_rope_kv_batch");
+    return GGB_OK;
+}
+
+// first index of the maximum of every row of x [nb][n]: one CTA per row
+__global__ void argmax_rows_kernel(const float* __restrict__ x, int64_t n, int32_t* __restrict__ out) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const float* xr = x + (int64_t)blockIdx.x * n;
+    float v = -FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float o = xr[i];
+        if (o > v || (o == v && (int)i < idx)) { v = o; idx = (int)i; }
+    }
+    auto comb = [&](float ov, int oi) { if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; } };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) comb(__shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -FLT_MAX;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) comb(__shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+        if (threadIdx.x == 0) out[blockIdx.x] = idx;
+    }
+}
+extern "C" int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_idx, void* stream) {
+    if (n <= 0 || nb < 0 || (nb && (!x || !out_idx))) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_rows: bad argument");
+    if (nb == 0) return GGB_OK;
+    argmax_rows_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(x, n, out_idx);
+    GGB_CHECK_LAUNCH("ggb_argmax_rows");
+    return GGB_OK;
+}
+
 // Causal attention for T query tokens at positions pos0..pos0+T-1 over the f16 cache.
 // CTA = one KV head x a block of query tokens: 16 warps = G query heads x (16/G) tokens, so a K/V tile staged in
 // shared memory is reused by every warp.  Warp = one (head, token) query: lanes own head_dim/32 dims, online softmax.

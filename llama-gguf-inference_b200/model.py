@@ -96,8 +96,8 @@ class Slot:
         tp = eng.tp_size
         self.nh, self.nkv, self.ffl, self.vl = hp.n_head // tp, hp.n_kv // tp, hp.ff // tp, hp.vocab // tp   # this rank's share
         kvd = self.nkv * hp.head_dim
-        self.kc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
-        self.vc = torch.zeros((hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=dev)
+        self.kc, self.vc = eng.k_all[index], eng.v_all[index]   # [n_layer][n_ctx][kvd] views of the engine's cache pool
+        self.chain_valid = True   # device-side (token, position, x) describe this slot's next decode step
         f32 = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
         i32 = lambda n: torch.zeros(n, dtype=torch.int32, device=dev)  # noqa: E731
         self.x, self.q, self.attn = f32(hp.d), f32(self.nh * hp.head_dim), f32(self.nh * hp.head_dim)
@@ -293,6 +293,7 @@ class Slot:
             self._enqueue_head(s)
             self.stream.synchronize()
         self.n_past = start + T
+        self.chain_valid = True
 
     def prefill(self, tokens: list[int], start_pos: int | None = None):
         """Feed tokens at positions start_pos.. (default: append).  Long prompts go through the tcgen05 GEMM path
@@ -315,11 +316,14 @@ class Slot:
                 self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
                 self.stream.synchronize()  # host_i32 is reused for the next token
         self.n_past = start + len(tokens)
+        self.chain_valid = True
 
     def decode(self, n_steps: int):
         """Enqueue n greedy decode steps (no host synchronisation); tokens land in out_tokens."""
         if self.n_past + n_steps >= self.n_ctx + 1:
             raise ValueError("context window exhausted")
+        if not self.chain_valid:
+            raise RuntimeError("this slot last advanced inside a batch: feed() its newest token before decode()")
         with self.torch.cuda.stream(self.stream):
             for _ in range(n_steps):
                 self._run("decode")
@@ -404,7 +408,15 @@ class Engine:
         self.gemm_prefill_min = int(os.environ.get("GGB_GEMM_PREFILL_MIN", "32"))   # prompts at least this long use the GEMM path
         self.prefill_chunk = 2048
         self._pf = None
-        self.slots = [Slot(self, i) for i in range(max(1, n_slots))]
+        n_slots = max(1, n_slots)
+        kvd = (self.hp.n_kv // self.tp_size) * self.hp.head_dim
+        # one cache pool for all slots, [slot][layer][position][kv dims]: the batched decode kernels address a token's
+        # cache as pool + slot * stride (csrc/attn.cu, ggb_rope_kv_batch)
+        self.k_all = torch.zeros((n_slots, self.hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=self.dev)
+        self.v_all = torch.zeros((n_slots, self.hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=self.dev)
+        self.slots = [Slot(self, i) for i in range(n_slots)]
+        self._batch = None
+        self.batch_capable = self.tp_size == 1 and n_slots > 1
         if verbose:
             print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
 
@@ -488,6 +500,14 @@ class Engine:
                         "att": f32(qd), "gate": f32(hp.ff), "up": f32(hp.ff),
                         "xb": torch.empty(cap * max(hp.d, hp.ff, qd), dtype=torch.bfloat16, device=dev)}
         return self._pf
+
+    @property
+    def batch(self):
+        """Batched decode over the slots (batch.py); built on first use."""
+        if self._batch is None:
+            from .batch import BatchDecoder
+            self._batch = BatchDecoder(self)
+        return self._batch
 
     def launches_per_step(self) -> int:
         """kernels of libggufb200 launched by one decode step (layers + head); NCCL kernels are not counted."""

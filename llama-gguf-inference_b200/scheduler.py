@@ -120,8 +120,12 @@ class Scheduler(threading.Thread):
                         free = next(i for i in range(len(self.engine.slots)) if i not in self.active)
                         self.active[free] = _Active(req, self.engine.slots[free], self.tok)
                         self._start(free)
-                for i in list(self.active):
-                    self._step(i)
+                live = list(self.active)
+                if len(live) >= 2 and getattr(self.engine, "batch_capable", False):
+                    self._step_batch(live)
+                else:
+                    for i in live:
+                        self._step(i)
         except Exception as e:  # a CUDA error is fatal: surface it to every waiter, then let the process die loudly
             self.fatal = f"engine failure: {e!r}"
             self.log(self.fatal)
@@ -165,11 +169,30 @@ class Scheduler(threading.Thread):
         if a.req.cancelled.is_set():
             self._finish(i, "cancelled")
             return
-        if a.req.sampling.greedy:
-            a.slot.decode(1)
+        if a.req.sampling.greedy and getattr(a.slot, "chain_valid", True):
+            a.slot.decode(1)            # the device already holds the next token, its position and embedding
         else:
-            a.slot.feed(a.last_tok)
+            a.slot.feed(a.last_tok)     # sampled on the host, or the slot last advanced inside a batch
         self._emit(i, self._pick(a))
+
+    def _step_batch(self, live: list[int]):
+        """Two or more busy slots: their next tokens form one batch -- one pass over the weights (batch.py)."""
+        for i in live:
+            if self.active[i].req.cancelled.is_set():
+                self._finish(i, "cancelled")
+        live = [i for i in live if i in self.active]
+        if len(live) < 2:
+            for i in live:
+                self._step(i)
+            return
+        bd = self.engine.batch
+        acts = [self.active[i] for i in live]
+        toks = bd.step([(a.slot.index, a.last_tok, a.slot.n_past) for a in acts])
+        self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
+        self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
+        for b, (i, a) in enumerate(zip(live, acts)):
+            tok = toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng)
+            self._emit(i, tok)
 
     def _emit(self, i: int, tok: int):
         a = self.active[i]

@@ -9,9 +9,10 @@ import numpy as np
 
 
 class OracleSlot:
-    def __init__(self, model, n_ctx):
-        self.m, self.n_ctx = model, n_ctx
+    def __init__(self, model, n_ctx, index=0):
+        self.m, self.n_ctx, self.index = model, n_ctx, index
         self.n_past, self.logits, self.last = 0, None, 0
+        self.chain_valid = True
 
     def reset(self):
         self.m.reset()
@@ -24,8 +25,10 @@ class OracleSlot:
             self.logits = self.m.forward(int(t), self.n_past)
             self.n_past += 1
         self.last = int(np.argmax(self.logits))
+        self.chain_valid = True
 
     def decode(self, n):
+        assert self.chain_valid, "decode() after a batch step without feed()"
         for _ in range(n):
             self.prefill([self.last])
 
@@ -42,4 +45,29 @@ class OracleSlot:
 class OracleEngine:
     def __init__(self, path, n_ctx=128, n_slots=1):
         from oracle import oracle as O
-        self.slots = [OracleSlot(O.OracleLlama(path, n_ctx=n_ctx, mode="canon"), n_ctx) for _ in range(n_slots)]
+        self.slots = [OracleSlot(O.OracleLlama(path, n_ctx=n_ctx, mode="canon"), n_ctx, i) for i in range(n_slots)]
+        self.batch_capable = n_slots > 1
+        self.batch = OracleBatch(self)
+
+
+class OracleBatch:
+    """the duck-typed BatchDecoder (llama-gguf-inference_b200/batch.py): one oracle forward per entry"""
+
+    def __init__(self, eng):
+        self.eng, self.rows, self.steps = eng, [], 0
+
+    def step(self, entries):
+        assert len({e[0] for e in entries}) == len(entries)
+        self.rows, out = [], []
+        for sl, tok, pos in entries:
+            s = self.eng.slots[sl]
+            assert pos == s.n_past
+            s.logits = s.m.forward(int(tok), pos)
+            s.n_past, s.chain_valid = pos + 1, False
+            self.rows.append(s.logits)
+            out.append(int(np.argmax(s.logits)))
+        self.steps += 1
+        return out
+
+    def logits_row(self, b):
+        return self.rows[b]

@@ -170,3 +170,74 @@ def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_di
     toks = eng.tokens(9)
     assert len(toks) == 9 and all(0 <= t < eng.hp.vocab for t in toks)
     eng.close()
+
+
+# ----------------------------------------------------------------------------- batched decode (BASELINE.json config 5)
+@pytest.mark.parametrize("preset,ftype,n_seq", [("tiny", "Q4_K_M", 3), ("small", "Q4_K_M", 5), ("small", "Q8_0", 2), ("medium", "Q4_K_M", 11),
+                                                ("medium", "Q6_K", 16)])
+def test_batched_decode_is_bit_identical_to_single_sequence_decode(oracle, model_dir, preset, ftype, n_seq):
+    """n_seq sequences with different prompts (so different positions) advance together through gemv_batch.cu;
+    each must produce exactly the tokens and logits it produces alone -- and sequence 0 those of the canon oracle."""
+    from ggufb200.model import Engine
+    path = _model(model_dir, preset, ftype)
+    n_new = 20
+    prompts = [[1] + [300 + 7 * s + j for j in range(2 + (s * 3) % 7)] for s in range(n_seq)]
+    eng = Engine(path, n_ctx=128, n_slots=n_seq)
+    eng.warmup()
+    alone_t, alone_l = [], []
+    for s, p in enumerate(prompts):          # every sequence alone, on slot 0 (device-side greedy chain)
+        sl = eng.slots[0]
+        sl.reset()
+        sl.prefill(p)
+        sl.decode(n_new - 1)
+        alone_t.append(sl.tokens(n_new))
+        alone_l.append(sl.last_logits().copy())
+    for s, p in enumerate(prompts):
+        eng.slots[s].reset()
+        eng.slots[s].prefill(p)
+    last = [eng.slots[s].read_last_token() for s in range(n_seq)]
+    got = [[t] for t in last]
+    for _ in range(n_new - 1):
+        nxt = eng.batch.step([(s, last[s], eng.slots[s].n_past) for s in range(n_seq)])
+        for s in range(n_seq):
+            got[s].append(nxt[s])
+        last = nxt
+    for s in range(n_seq):
+        assert got[s] == alone_t[s], f"sequence {s}"
+        assert np.array_equal(_bits(eng.batch.logits_row(s)), _bits(alone_l[s])), f"sequence {s}"
+    want = oracle.OracleLlama(path, n_ctx=128, mode="canon").greedy(prompts[0], n_new)
+    assert got[0] == want
+    # a slot that advanced inside batches goes back to the single-sequence path through feed()
+    sl = eng.slots[1]
+    with pytest.raises(RuntimeError):
+        sl.decode(1)
+    sl.feed(last[1])
+    tok_after = sl.read_last_token()
+    s0 = eng.slots[0]
+    s0.reset(); s0.prefill(prompts[1]); s0.decode(n_new)
+    assert s0.tokens(n_new + 1)[-1] == tok_after
+    eng.close()
+
+
+def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
+    from ggufb200.model import Engine
+    path = _model(model_dir, "tiny", "Q4_K_M")
+    eng = Engine(path, n_ctx=64, n_slots=4)
+    eng.warmup()
+    for s in (1, 3):
+        eng.slots[s].reset()
+        eng.slots[s].prefill(PROMPT + [310 + s])
+    last = {s: eng.slots[s].read_last_token() for s in (1, 3)}
+    out = eng.batch.step([(3, last[3], eng.slots[3].n_past), (1, last[1], eng.slots[1].n_past)])   # any order, any subset
+    ref = []
+    for s in (3, 1):
+        m = oracle.OracleLlama(path, n_ctx=64, mode="canon")
+        ref.append(m.greedy(PROMPT + [310 + s], 2)[1])
+    assert out == ref
+    with pytest.raises(ValueError):
+        eng.batch.step([(1, 5, 3), (1, 6, 4)])            # the same slot twice
+    with pytest.raises(ValueError):
+        eng.batch.step([(0, 5, 64)])                      # position outside the context
+    with pytest.raises(ValueError):
+        eng.batch.step([])
+    eng.close()

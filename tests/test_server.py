@@ -183,6 +183,27 @@ def test_concurrent_requests_and_health_during_generation(backend):
     [t.join() for t in ts]
     assert not errs and all(o[0] == 200 for o in out)
     assert len({o[1]["choices"][0]["message"]["content"] for o in out}) == 1   # same prompt, greedy -> same text on every slot
+    # two busy slots advance together: the scheduler batched their decode steps
+    assert backend["state"].sched.stats.get("batched_steps", 0) > 0
+
+
+def test_batched_and_single_steps_interleave(oracle, backend):
+    """a long request keeps running alone after a short one that shared batches with it has finished (the slot goes
+    batch -> feed -> device-side chain), and a sampled request rides in the same batches as a greedy one"""
+    p = backend["port"]
+    want, _ = expected_text(oracle, backend, MSG, 40)
+    res = {}
+
+    def worker(name, body):
+        res[name] = call(p, "POST", "/v1/chat/completions", body)
+
+    ts = [threading.Thread(target=worker, args=("long", {"messages": MSG, "max_tokens": 40, "temperature": 0})),
+          threading.Thread(target=worker, args=("short", {"messages": MSG, "max_tokens": 6, "temperature": 1.2, "seed": 3}))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert res["long"][0] == 200 and res["short"][0] == 200
+    assert res["long"][1]["choices"][0]["message"]["content"] == want
+    assert res["short"][1]["usage"]["completion_tokens"] == 6
 
 
 def test_cli_version_and_argv_contract():
