@@ -5,7 +5,7 @@
 // Same arithmetic as gemv.cu, token by token: identical int8 activation codes (ggb_act_prep below restates the
 // GEMV prologue), identical integer dots, identical f32 unit terms, summed in f64 -- so a sequence decoded inside a
 // batch produces bit-identical logits to the same sequence decoded alone.  What changes is the data movement:
-//   * weights stream from HBM ONCE per launch for up to 8 tokens (the batch-1 kernel would read them once per token);
+//   * weights stream from HBM ONCE per launch for up to 16 tokens (8 when the images of 16 do not fit shared memory) (the batch-1 kernel would read them once per token);
 //   * the per-CTA quantisation prologue is replaced by a bulk copy of pre-quantised activation "images"
 //     (ggb_act_prep, one small launch per phase) -- quantising 8 vectors redundantly in 148 CTAs would cost more
 //     than the GEMV;
@@ -25,7 +25,7 @@
 
 #define GB_NW 8
 #define GB_THREADS (GB_NW * 32)
-#define GB_R 2          /* rows per warp group */
+#define GB_MAX_R 4      /* rows per warp group: 2, or 4 for pure Q4_K launches (halves the activation loads per row) */
 #define GB_STEPS 2      /* ring stages per warp */
 #define GB_MAX_SMEM (226 * 1024)
 
@@ -109,7 +109,7 @@ __device__ __forceinline__ double term_q80_w(const W8& w, const Act& A) {
 // full sum of value index l / (32/N) in v[0].
 template <int N>
 __device__ __forceinline__ void warp_reduce_many(double (&v)[N], int lane) {
-    static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "value count");
+    static_assert(N == 4 || N == 8 || N == 16 || N == 32, "value count");
     int off = 16;
 #pragma unroll
     for (int n = N; n > 1; n >>= 1) {
@@ -130,9 +130,9 @@ __device__ __forceinline__ void warp_reduce_many(double (&v)[N], int lane) {
 
 // MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0 segments present; NBT = tokens per launch (compile-time upper bound, the
 // images of tokens >= nb are zero-filled by the prologue)
-template <int MASK, int NBT>
+template <int MASK, int NBT, int R>
 __global__ void __launch_bounds__(GB_THREADS, 1) gemv_batch_kernel(const __grid_constant__ GemvBK P) {
-    constexpr int R = GB_R, STEPS = GB_STEPS;
+    constexpr int STEPS = GB_STEPS;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[GB_NW][STEPS];
     __shared__ __align__(8) uint64_t s_abar;
@@ -302,11 +302,23 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gemv_batch_kernel(const __grid_
             __syncwarp();
             if (lane == 0 && ip < npairs) issue_step();
         }
-        warp_reduce_many<R * NBT>(acc, lane);
-        constexpr int LPV = 32 / (R * NBT);   /* lanes per value */
-        if ((lane & (LPV - 1)) == 0) {
-            const int idx = lane / LPV, r = idx / NBT, b = idx % NBT;
-            if (r < nv) rowv[(lr + r) * NBT + b] = acc[0];
+        if constexpr (R * NBT <= 32) {
+            warp_reduce_many<R * NBT>(acc, lane);
+            constexpr int LPV = 32 / (R * NBT);   /* lanes per value */
+            if ((lane & (LPV - 1)) == 0) {
+                const int idx = lane / LPV, r = idx / NBT, b = idx % NBT;
+                if (r < nv) rowv[(lr + r) * NBT + b] = acc[0];
+            }
+        } else {                                  /* 64 values: two rounds of 32 (rows 0,1 then rows 2,3) */
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                double v[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = acc[hf * 32 + i];
+                warp_reduce_many<32>(v, lane);
+                const int idx = hf * 32 + lane, r = idx / NBT, b = idx % NBT;
+                if (r < nv) rowv[(lr + r) * NBT + b] = v[0];
+            }
         }
     }
     __syncthreads();
@@ -420,27 +432,42 @@ extern "C" int ggb_act_prep(const float* x, const float* norm_w, float eps, int6
 }
 
 // ------------------------------------------------------------------ host side of the batched GEMV
-template <int MASK, int NBT>
+template <int MASK, int NBT, int R>
 static int launch_b(const GemvBK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        GGB_CUDA(cudaFuncSetAttribute(gemv_batch_kernel<MASK, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_MAX_SMEM));
+        GGB_CUDA(cudaFuncSetAttribute(gemv_batch_kernel<MASK, NBT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_MAX_SMEM));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     launch_cfg(cfg, at, dim3(grid), dim3(GB_THREADS), smem, use_pdl, st);
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_batch_kernel<MASK, NBT>, P));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_batch_kernel<MASK, NBT, R>, P));
     return GGB_OK;
 }
 
 template <int MASK>
-static int launch_nbt(int nbt, const GemvBK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
-    switch (nbt) {
-        case 2: return launch_b<MASK, 2>(P, grid, smem, use_pdl, st);
-        case 4: return launch_b<MASK, 4>(P, grid, smem, use_pdl, st);
-        default: return launch_b<MASK, 8>(P, grid, smem, use_pdl, st);
+static int launch_nbt(int nbt, int R, const GemvBK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
+    if constexpr (MASK == 1) {
+        if (R == 4) {
+            switch (nbt) {
+                case 2: return launch_b<MASK, 2, 4>(P, grid, smem, use_pdl, st);
+                case 4: return launch_b<MASK, 4, 4>(P, grid, smem, use_pdl, st);
+                default: return launch_b<MASK, 8, 4>(P, grid, smem, use_pdl, st);   /* 16 tokens x 4 rows would spill */
+            }
+        }
     }
+    switch (nbt) {
+        case 2: return launch_b<MASK, 2, 2>(P, grid, smem, use_pdl, st);
+        case 4: return launch_b<MASK, 4, 2>(P, grid, smem, use_pdl, st);
+        case 8: return launch_b<MASK, 8, 2>(P, grid, smem, use_pdl, st);
+        default: return launch_b<MASK, 16, 2>(P, grid, smem, use_pdl, st);
+    }
+}
+
+static int env_int_b(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 static size_t batch_smem(const GemvBK& P, int nbt, int64_t max_local) {
@@ -499,23 +526,25 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
     P.n_seg = a->n_seg; P.k = a->k; P.T = ggb_tiles_per_row(a->k);
     P.epi = a->epilogue; P.residual = a->residual;
     P.slot_bytes = (max_tile + 15) & ~15;
-    P.ring_bytes = GB_R * GB_STEPS * P.slot_bytes;
+    static const int r_q4k = env_int_b("GGB_BATCH_R_Q4K", 2), cap_max = env_int_b("GGB_BATCH_CAP", 16);
+    const int R = (mask == 1 && r_q4k == 4) ? 4 : 2;
+    P.ring_bytes = R * GB_STEPS * P.slot_bytes;
     P.image = a->k + a->k / 4;
     const int grid = a->grid > 0 ? a->grid : ggb_num_sms();
     int64_t max_local = 0;
     for (int s = 0; s < a->n_seg; s++) {
         P.rq[s] = a->seg[s].rows / grid; P.rr[s] = a->seg[s].rows % grid;
-        max_local += (a->seg[s].rows + grid - 1) / grid + 2 * GB_R;
+        max_local += (a->seg[s].rows + grid - 1) / grid + 2 * GB_MAX_R;
     }
     // tokens per pass: what fits in shared memory next to the ring, at most 8
-    int cap = 8;
+    int cap = (cap_max >= 16 && R == 2) ? 16 : 8;
     while (cap > 1 && batch_smem(P, cap, max_local) > GB_MAX_SMEM) cap >>= 1;
     if (cap < 2 || batch_smem(P, 2, max_local) > GB_MAX_SMEM)
         GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: k=%d rows=%lld does not fit shared memory", a->k, (long long)total_rows);
     cudaStream_t st = (cudaStream_t)stream;
     for (int b0 = 0; b0 < a->nb; b0 += cap) {
         const int nb = a->nb - b0 < cap ? a->nb - b0 : cap;
-        const int nbt = nb <= 2 ? 2 : (nb <= 4 ? 4 : 8);
+        const int nbt = nb <= 2 ? 2 : (nb <= 4 ? 4 : (nb <= 8 ? 8 : 16));
         GemvBK Q = P;
         Q.nb = nb;
         Q.act = (const uint8_t*)a->act + (int64_t)b0 * P.image;
@@ -527,10 +556,10 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
         const size_t smem = batch_smem(Q, nbt, max_local);
         int rc;
         switch (mask) {
-            case 1: rc = launch_nbt<1>(nbt, Q, grid, smem, a->use_pdl, st); break;
-            case 2: rc = launch_nbt<2>(nbt, Q, grid, smem, a->use_pdl, st); break;
-            case 3: rc = launch_nbt<3>(nbt, Q, grid, smem, a->use_pdl, st); break;
-            default: rc = launch_nbt<4>(nbt, Q, grid, smem, a->use_pdl, st); break;
+            case 1: rc = launch_nbt<1>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
+            case 2: rc = launch_nbt<2>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
+            case 3: rc = launch_nbt<3>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
+            default: rc = launch_nbt<4>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
         }
         if (rc) return rc;
     }
