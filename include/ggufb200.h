@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GGB_ABI_VERSION 1
+#define GGB_ABI_VERSION 2
 
 /* ggml tensor type ids (gguf/constants.py:4059-4093) */
 #define GGB_TYPE_F32 0
@@ -79,6 +79,9 @@ int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m,
  *                       vcache[pos]  (ggml_rope NORM mode + ggml_cpy into the KV cache); pos is read from
  *                       device memory so a captured graph can be replayed for every position
  *     GGB_EPI_ARGMAX    y_0[r] = dot and per-CTA (max, first index) partials for the greedy sampler
+ *     GGB_EPI_PEER_F64  tensor parallel, fused with the exchange: the f64 row sums go straight into every rank's
+ *                       exchange region over NVLink peer memory and the launch's last CTA publishes the epoch;
+ *                       ggb_peer_reduce_residual on each rank then adds the cross-rank sum to x
  *     GGB_EPI_STORE_F64 y_0 is a double*: the unrounded f64 row sums.  Tensor-parallel ranks that hold a K-slice of
  *                       W exchange these (all-reduce in f64) so the single rounding to f32 happens after the
  *                       cross-rank sum and the result is bit-identical with the unsharded GEMV.
@@ -92,6 +95,8 @@ int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m,
 #define GGB_EPI_ROPE_KV 3
 #define GGB_EPI_ARGMAX 4
 #define GGB_EPI_STORE_F64 5
+#define GGB_EPI_PEER_F64 6
+#define GGB_PEER_MAX 8
 
 typedef struct ggb_gemv_seg {
     const void* w;   /* tile-SoA weights [rows][row_stride] */
@@ -121,6 +126,10 @@ typedef struct ggb_gemv_args {
     float* part_val;           /* [grid] */
     int32_t* part_idx;         /* [grid] */
     int32_t grid;              /* 0 = library default (a multiple of the SM count) */
+    /* GGB_EPI_PEER_F64: exchange regions of all ranks as mapped in THIS process (ggb_peer_alloc / ggb_peer_open) */
+    int32_t peer_n, peer_rank;
+    int64_t peer_d_cap;
+    uint64_t peer_base[GGB_PEER_MAX];
 } ggb_gemv_args;
 
 int ggb_gemv(const ggb_gemv_args* args, void* stream);
@@ -163,6 +172,16 @@ int ggb_residual_add_f64(float* x, const double* y64, int64_t n, int use_pdl, vo
  * row_offset = first vocabulary row of the shard) to ONE sortable 64-bit key (larger logit wins, then smaller index);
  * the host all-reduces the keys with MAX; unpack turns the winner into the token id and does the rest of
  * ggb_argmax_next (append to out_tokens, advance pos/step, gather the next embedding row). */
+/* Exchange over peer memory (csrc/peer.cu): each rank allocates a region of ggb_peer_region_bytes(n, d_cap) bytes
+ * with ggb_peer_alloc (cudaMalloc, zeroed; handle64 = its 64-byte cudaIpc handle), sends the handle to its peers,
+ * and maps theirs with ggb_peer_open.  ggb_peer_reduce_residual waits until all n ranks have published the epoch
+ * this rank just produced, then x[i] += (float)(sum over ranks, in rank order, of their f64 partial i). */
+int64_t ggb_peer_region_bytes(int n, int64_t d_cap);
+int ggb_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int ggb_peer_open(const unsigned char* handle64, void** ptr);
+int ggb_peer_close(void* ptr);
+int ggb_peer_free(void* ptr);
+int ggb_peer_reduce_residual(float* x, const void* own_region, int n, int64_t d, int64_t d_cap, int use_pdl, void* stream);
 int ggb_argmax_pack(const float* part_val, const int32_t* part_idx, int n_part, int32_t row_offset, int64_t* key, void* stream);
 int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_dev, int32_t* step_dev, int32_t* out_tokens,
                            int32_t out_cap, int emb_type, const void* token_embd, int64_t k, float* x, void* stream);

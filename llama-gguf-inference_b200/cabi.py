@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "libggufb200.so")
 F32, F16, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 8, 12, 13, 14
 MAX_SEG = 3
 PRO_PLAIN, PRO_RMSNORM = 0, 1
-EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU, EPI_ROPE_KV, EPI_ARGMAX, EPI_STORE_F64 = 0, 1, 2, 3, 4, 5
+EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU, EPI_ROPE_KV, EPI_ARGMAX, EPI_STORE_F64, EPI_PEER_F64 = 0, 1, 2, 3, 4, 5, 6
+PEER_MAX = 8
 
 # every symbol include/ggufb200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
@@ -26,6 +27,7 @@ EXPORTS = [
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
+    "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
     "ggb_act_image_bytes", "ggb_act_prep", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows",
 ]
 
@@ -51,6 +53,7 @@ class GemvArgs(C.Structure):
         ("kcache", C.c_void_p), ("vcache", C.c_void_p),
         ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
         ("grid", C.c_int32),
+        ("peer_n", C.c_int32), ("peer_rank", C.c_int32), ("peer_d_cap", C.c_int64), ("peer_base", C.c_uint64 * PEER_MAX),
     ]
 
 
@@ -102,6 +105,12 @@ def lib() -> C.CDLL:
         "ggb_rope_kv_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
         "ggb_attn_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "ggb_add_f32": ([vp, vp, i64, vp], i32),
+        "ggb_peer_region_bytes": ([i32, i64], i64),
+        "ggb_peer_alloc": ([sz, C.POINTER(vp), C.c_char_p], i32),
+        "ggb_peer_open": ([C.c_char_p, C.POINTER(vp)], i32),
+        "ggb_peer_close": ([vp], i32),
+        "ggb_peer_free": ([vp], i32),
+        "ggb_peer_reduce_residual": ([vp, vp, i32, i64, i64, i32, vp], i32),
         "ggb_act_image_bytes": ([i64], i64),
         "ggb_act_prep": ([vp, vp, f32, i64, i32, i32, vp, i32, vp], i32),
         "ggb_gemv_batch": ([C.POINTER(GemvBatchArgs), vp], i32),
@@ -133,7 +142,8 @@ def device_info() -> dict:
 
 
 def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w=0, eps=0.0, use_pdl=0, residual=0,
-                   pos_dev=0, rope_tab=0, n_rot=0, head_dim=0, kcache=0, vcache=0, part_val=0, part_idx=0, grid=0) -> GemvArgs:
+                   pos_dev=0, rope_tab=0, n_rot=0, head_dim=0, kcache=0, vcache=0, part_val=0, part_idx=0, grid=0,
+                   peer=None) -> GemvArgs:
     """segs: list of (w_ptr, type, rows, y_ptr)."""
     a = GemvArgs()
     a.n_seg = len(segs)
@@ -147,6 +157,11 @@ def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w
     a.x, a.norm_w, a.eps, a.use_pdl, a.residual = x, norm_w, eps, use_pdl, residual
     a.pos_dev, a.rope_tab, a.n_rot, a.head_dim = pos_dev, rope_tab, n_rot, head_dim
     a.kcache, a.vcache, a.part_val, a.part_idx, a.grid = kcache, vcache, part_val, part_idx, grid
+    if peer is not None:    # (bases of every rank's exchange region in this process, own rank, capacity in rows)
+        bases, rank, d_cap = peer
+        a.peer_n, a.peer_rank, a.peer_d_cap = len(bases), rank, d_cap
+        for i, b in enumerate(bases):
+            a.peer_base[i] = b
     return a
 
 

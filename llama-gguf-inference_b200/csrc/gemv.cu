@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "layout.cuh"
 #include "gemv_common.cuh"
+#include "peer.cuh"
 
 #ifndef GEMV_NW
 #define GEMV_NW 8                          /* warps per CTA */
@@ -75,6 +76,9 @@ struct GemvK {
     uint16_t* vcache;
     float* part_val;
     int32_t* part_idx;
+    int peer_n, peer_rank;
+    int64_t peer_d_cap;
+    uint64_t peer_base[GGB_PEER_MAX];
 };
 
 // ------------------------------------------------------------------ optional in-kernel timeline (debug builds only)
@@ -352,6 +356,30 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     } else if (P.epi == GGB_EPI_STORE_F64) {
         double* y64 = reinterpret_cast<double*>(P.seg[0].y);   /* tensor-parallel partial: summed across ranks before rounding */
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) y64[r0_0 + lr] = rowv[lr];
+    } else if (P.epi == GGB_EPI_PEER_F64) {
+        // tensor-parallel exchange fused into the GEMV: partial sums go to every rank's region, slot = my rank
+        const int n = P.peer_n;
+        uint8_t* own = reinterpret_cast<uint8_t*>(P.peer_base[P.peer_rank]);
+        int* state = reinterpret_cast<int*>(own + ggb_peer_state_off(n, P.peer_d_cap));
+        const int e = *reinterpret_cast<volatile int*>(state + 1) + 1;           /* epoch of this exchange */
+        const size_t slot = ((size_t)(e & 1) * n + P.peer_rank) * (size_t)P.peer_d_cap;
+        for (int p = 0; p < n; p++) {
+            double* dst = reinterpret_cast<double*>(P.peer_base[p]) + slot;
+            for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) dst[r0_0 + lr] = rowv[lr];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const int prev = atomicAdd(state, 1);
+            if (prev == (int)gridDim.x - 1) {                                   /* every CTA's partials are on their way */
+                *reinterpret_cast<volatile int*>(state) = 0;
+                *reinterpret_cast<volatile int*>(state + 1) = e;
+                __threadfence_system();
+                for (int p = 0; p < n; p++)
+                    st_release_sys(reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(P.peer_base[p]) + ggb_peer_flags_off(n, P.peer_d_cap)) + P.peer_rank, e);
+            }
+        }
     } else if (P.epi == GGB_EPI_RESIDUAL) {
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {
             const int r = r0_0 + lr;
@@ -499,6 +527,12 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
         case GGB_EPI_RESIDUAL:
             if (a->n_seg != 1 || !a->residual || !a->seg[0].y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: RESIDUAL needs one segment, y and residual");
             break;
+        case GGB_EPI_PEER_F64:
+            if (a->n_seg != 1 || a->peer_n < 1 || a->peer_n > GGB_PEER_MAX || a->peer_rank < 0 || a->peer_rank >= a->peer_n ||
+                a->peer_d_cap < a->seg[0].rows)
+                GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: PEER_F64 needs one segment, 1..%d ranks and a region sized for the rows", GGB_PEER_MAX);
+            for (int p = 0; p < a->peer_n; p++) if (!a->peer_base[p]) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: PEER_F64: region of rank %d is not mapped", p);
+            break;
         case GGB_EPI_SWIGLU:
             if (a->n_seg != 2 || a->seg[0].rows != a->seg[1].rows || !a->seg[0].y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: SWIGLU needs gate/up segments of equal rows and y on segment 0");
             break;
@@ -518,6 +552,8 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     P.x = a->x; P.norm_w = a->norm_w; P.eps = a->eps; P.residual = a->residual;
     P.pos_dev = a->pos_dev; P.rope_tab = a->rope_tab; P.n_rot = a->n_rot; P.head_dim = a->head_dim;
     P.kcache = a->kcache; P.vcache = a->vcache; P.part_val = a->part_val; P.part_idx = a->part_idx;
+    P.peer_n = a->peer_n; P.peer_rank = a->peer_rank; P.peer_d_cap = a->peer_d_cap;
+    for (int p = 0; p < GGB_PEER_MAX; p++) P.peer_base[p] = a->peer_base[p];
     // ring geometry: RING_SLOTS slots sized for the largest tile of the launch
     P.slot_bytes = (max_tile + 15) & ~15;
     const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;

@@ -139,10 +139,13 @@ class Slot:
                 rope_tab=e.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
                 kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
             tp = e.tp_size > 1
+            # row-split projections: partial sums leave through the fused peer exchange, or as a local f64 vector (NCCL)
+            epi_rs = (cabi.EPI_PEER_F64 if e.peer else cabi.EPI_STORE_F64) if tp else cabi.EPI_RESIDUAL
+            peer = (e.peer["bases"], e.tp_rank, hp.d) if (tp and e.peer) else None
             o = cabi.make_gemv_args(
                 [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wo"].k,
-                self.attn.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_STORE_F64 if tp else cabi.EPI_RESIDUAL,
-                residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+                self.attn.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=epi_rs,
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer)
             gu = cabi.make_gemv_args(
                 [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
                  (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
@@ -150,8 +153,8 @@ class Slot:
                 norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
             dn = cabi.make_gemv_args(
                 [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wd"].k,
-                self.h.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=cabi.EPI_STORE_F64 if tp else cabi.EPI_RESIDUAL,
-                residual=self.x.data_ptr(), use_pdl=self.use_pdl)
+                self.h.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=epi_rs,
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer)
             self._layer_args.append((qkv, o, gu, dn))
         self._head = self._head_args()
 
@@ -164,6 +167,10 @@ class Slot:
     def _allreduce_residual(self, s: int):
         """x += (float) sum over ranks of the f64 partials (the exchange step of a row-split projection)"""
         e = self.eng
+        if e.peer:   # the GEMV already pushed its partials into every rank's region (GGB_EPI_PEER_F64)
+            cabi.check(self.lib.ggb_peer_reduce_residual(self.x.data_ptr(), e.peer["own"], e.tp_size, self.hp.d, self.hp.d,
+                                                         self.use_pdl, s), "peer_reduce_residual")
+            return
         e.dist.all_reduce(self.y64, op=e.dist.ReduceOp.SUM, group=e.pg)
         cabi.check(self.lib.ggb_residual_add_f64(self.x.data_ptr(), self.y64.data_ptr(), self.hp.d, 0, s), "residual_add_f64")
 
@@ -401,6 +408,9 @@ class Engine:
             self.dist = dist
         self.n_ctx = int(n_ctx)
         self.max_new = max_new
+        self.peer = None
+        if self.tp_size > 1 and os.environ.get("GGB_TP_EXCHANGE", "peer") != "nccl":
+            self._setup_peer_exchange()
         self.stream = torch.cuda.Stream(device=self.dev)
         t0 = time.time()
         self._load_weights()
@@ -419,6 +429,29 @@ class Engine:
         self.batch_capable = self.tp_size == 1 and n_slots > 1
         if verbose:
             print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
+
+    def _setup_peer_exchange(self):
+        """Map every rank's exchange region into this process (CUDA IPC over NVLink): the all-reduce after the
+        row-split projections then happens inside the GEMV epilogue + one small reduce kernel (csrc/peer.cu).
+        GGB_TP_EXCHANGE=nccl keeps the library collective instead (the baseline the fused path is measured against)."""
+        lib, dist, n = self.lib, self.dist, self.tp_size
+        if n > cabi.PEER_MAX:
+            raise cabi.GGBError(f"peer exchange supports up to {cabi.PEER_MAX} ranks (GGB_TP_EXCHANGE=nccl for more)")
+        nbytes = lib.ggb_peer_region_bytes(n, self.hp.d)
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        cabi.check(lib.ggb_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
+        handles = [None] * n
+        dist.all_gather_object(handles, handle.raw, group=self.pg)
+        bases = []
+        for r in range(n):
+            if r == self.tp_rank:
+                bases.append(own.value)
+                continue
+            p = C.c_void_p()
+            cabi.check(lib.ggb_peer_open(handles[r], C.byref(p)), f"peer_open(rank {r}) -- set GGB_TP_EXCHANGE=nccl if CUDA IPC is unavailable")
+            bases.append(p.value)
+        dist.barrier(group=self.pg)
+        self.peer = {"own": own.value, "bases": bases}
 
     # ------------------------------------------------------------------ loading
     def _sptr(self) -> int:
@@ -557,4 +590,13 @@ class Engine:
     def close(self):
         for s in self.slots:
             s._graphs.clear()
+        if self._batch is not None:
+            self._batch._graphs.clear()
+        if self.peer:
+            self.torch.cuda.synchronize()
+            for r, b in enumerate(self.peer["bases"]):
+                if r != self.tp_rank:
+                    self.lib.ggb_peer_close(b)
+            self.lib.ggb_peer_free(self.peer["own"])
+            self.peer = None
         self.file.close()

@@ -135,14 +135,16 @@ def test_shard_plan_covers_every_weight_once_and_rejects_bad_sizes():
     parallel.check_divisible(hp8, 8)
 
 
-def _tp_gpu_worker(rank, world, port, path, n_new, out_dir):
+def _tp_gpu_worker(rank, world, port, path, n_new, out_dir, exchange):
     sys.path.insert(0, ROOT)
+    os.environ["GGB_TP_EXCHANGE"] = exchange
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from ggufb200.model import Engine
     eng = Engine(path, n_ctx=128, device=rank, tp_rank=rank, tp_size=world)
+    assert (eng.peer is not None) == (exchange == "peer")
     eng.warmup()
     eng.reset()
     eng.prefill([1, 300, 301, 302, 303])
@@ -158,7 +160,10 @@ def _tp_gpu_worker(rank, world, port, path, n_new, out_dir):
 
 
 @pytest.mark.gpu
-def test_tensor_parallel_engine_bit_exact_vs_oracle(oracle, model_dir, tmp_path):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_tensor_parallel_engine_bit_exact_vs_oracle(oracle, model_dir, tmp_path, exchange):
+    """exchange = peer: the all-reduce fused into the row-split GEMVs over NVLink peer memory (csrc/peer.cu);
+    nccl: the library collective.  Both must reproduce the single-process canon oracle bit for bit."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -172,7 +177,7 @@ def test_tensor_parallel_engine_bit_exact_vs_oracle(oracle, model_dir, tmp_path)
     if not os.path.exists(path):
         synth.write_gguf(path, cfg, "Q4_K_M", seed=0xB200)
     n_new = 24
-    mp.spawn(_tp_gpu_worker, args=(world, _free_port(), path, n_new, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_tp_gpu_worker, args=(world, _free_port(), path, n_new, str(tmp_path), exchange), nprocs=world, join=True)
     ref = oracle.OracleLlama(path, n_ctx=128, mode="canon")
     ref_toks, ref_logits = ref.greedy([1, 300, 301, 302, 303], n_new, return_logits=True)
     parts = [np.load(tmp_path / f"gpu{r}.npz") for r in range(world)]
