@@ -80,7 +80,7 @@ int ggb_quantize_q8_0(const float* x, int8_t* qs, uint16_t* d, int64_t k, int m,
  *                       device memory so a captured graph can be replayed for every position
  *     GGB_EPI_ARGMAX    y_0[r] = dot and per-CTA (max, first index) partials for the greedy sampler
  *     GGB_EPI_PEER_F64  tensor parallel, fused with the exchange: the f64 row sums go straight into every rank's
- *                       exchange region over NVLink peer memory and the launch's last CTA publishes the epoch;
+ *                       exchange region over NVLink peer memory as {data, epoch} words (the data is its own arrival flag);
  *                       ggb_peer_reduce_residual on each rank then adds the cross-rank sum to x
  *     GGB_EPI_STORE_F64 y_0 is a double*: the unrounded f64 row sums.  Tensor-parallel ranks that hold a K-slice of
  *                       W exchange these (all-reduce in f64) so the single rounding to f32 happens after the
@@ -174,8 +174,8 @@ int ggb_residual_add_f64(float* x, const double* y64, int64_t n, int use_pdl, vo
  * ggb_argmax_next (append to out_tokens, advance pos/step, gather the next embedding row). */
 /* Exchange over peer memory (csrc/peer.cu): each rank allocates a region of ggb_peer_region_bytes(n, d_cap) bytes
  * with ggb_peer_alloc (cudaMalloc, zeroed; handle64 = its 64-byte cudaIpc handle), sends the handle to its peers,
- * and maps theirs with ggb_peer_open.  ggb_peer_reduce_residual waits until all n ranks have published the epoch
- * this rank just produced, then x[i] += (float)(sum over ranks, in rank order, of their f64 partial i). */
+ * and maps theirs with ggb_peer_open.  ggb_peer_reduce_residual polls until all n ranks' partials of the current
+ * exchange have arrived, then x[i] += (float)(sum over ranks, in rank order, of their f64 partial i). */
 int64_t ggb_peer_region_bytes(int n, int64_t d_cap);
 int ggb_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int ggb_peer_open(const unsigned char* handle64, void** ptr);

@@ -357,28 +357,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
         double* y64 = reinterpret_cast<double*>(P.seg[0].y);   /* tensor-parallel partial: summed across ranks before rounding */
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) y64[r0_0 + lr] = rowv[lr];
     } else if (P.epi == GGB_EPI_PEER_F64) {
-        // tensor-parallel exchange fused into the GEMV: partial sums go to every rank's region, slot = my rank
+        // tensor-parallel exchange fused into the GEMV: {partial, epoch} words go to every rank's region, slot = my
+        // rank (peer.cuh); the data is its own arrival flag, so nothing else is needed on this side
         const int n = P.peer_n;
-        uint8_t* own = reinterpret_cast<uint8_t*>(P.peer_base[P.peer_rank]);
-        int* state = reinterpret_cast<int*>(own + ggb_peer_state_off(n, P.peer_d_cap));
-        const int e = *reinterpret_cast<volatile int*>(state + 1) + 1;           /* epoch of this exchange */
+        const uint8_t* own = reinterpret_cast<const uint8_t*>(P.peer_base[P.peer_rank]);
+        const uint32_t e = (uint32_t)(*reinterpret_cast<const volatile int*>(own + ggb_peer_state_off(n, P.peer_d_cap) + 4) + 1);
         const size_t slot = ((size_t)(e & 1) * n + P.peer_rank) * (size_t)P.peer_d_cap;
-        for (int p = 0; p < n; p++) {
-            double* dst = reinterpret_cast<double*>(P.peer_base[p]) + slot;
-            for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) dst[r0_0 + lr] = rowv[lr];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            const int prev = atomicAdd(state, 1);
-            if (prev == (int)gridDim.x - 1) {                                   /* every CTA's partials are on their way */
-                *reinterpret_cast<volatile int*>(state) = 0;
-                *reinterpret_cast<volatile int*>(state + 1) = e;
-                __threadfence_system();
-                for (int p = 0; p < n; p++)
-                    st_release_sys(reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(P.peer_base[p]) + ggb_peer_flags_off(n, P.peer_d_cap)) + P.peer_rank, e);
-            }
+        for (int i = tid; i < cnt0 * n; i += GEMV_THREADS) {
+            const int p = i / cnt0, lr = i - p * cnt0;
+            st_ll_f64(reinterpret_cast<uint8_t*>(P.peer_base[p]) + (slot + r0_0 + lr) * 16, rowv[lr], e);
         }
     } else if (P.epi == GGB_EPI_RESIDUAL) {
         for (int lr = tid; lr < cnt0; lr += GEMV_THREADS) {

@@ -1,12 +1,13 @@
 // peer.cu -- the exchange step of tensor parallelism (the all-reduce after attn_output and ffn_down,
 // BASELINE.json north_star) done over NVLink peer memory instead of a library collective:
 //   producer  the row-split GEMV's epilogue (gemv.cu, GGB_EPI_PEER_F64) stores its f64 partial sums straight into
-//             EVERY rank's exchange region (slot = own rank), and the last CTA of the launch publishes the epoch in
-//             every rank's flag word -- the transfer rides on the GEMV, tile by tile, there is no separate send;
-//   consumer  peer_reduce_residual_kernel waits for the n flags of the epoch, then x[i] += (float)(sum over ranks of
-//             partial[r][i]) in rank order -- the same f64 sum on every rank, so the replicas stay bit-identical.
+//             EVERY rank's exchange region (slot = own rank) as {data, epoch} words -- the transfer rides on the
+//             GEMV, CTA by CTA, with no fence, no signal and no separate send;
+//   consumer  peer_reduce_residual_kernel polls the n slots of element i until they carry the epoch, then
+//             x[i] += (float)(sum over ranks, in rank order, of partial[r][i]) -- the same f64 sum on every rank, so
+//             the replicas stay bit-identical.  Its last CTA advances the epoch.
 // Two parities of the receive buffers are enough: a rank finishes the reduce of epoch e only after every peer has
-// published e, and a peer publishes e only after it finished its own reduce of e-1.
+// written e, and a peer writes e+1 only after it finished its own reduce of e.
 // The processes exchange cudaIpc handles of their regions once at start-up (host side: model.py).
 #include "common.cuh"
 #include "peer.cuh"
@@ -46,34 +47,42 @@ extern "C" int ggb_peer_free(void* ptr) {
     return GGB_OK;
 }
 
-struct PeerBases { uint64_t base[GGB_PEER_MAX]; };
-
 __global__ void __launch_bounds__(256) peer_reduce_residual_kernel(float* __restrict__ x, uint64_t own_base, int n, int64_t d, int64_t d_cap) {
     pdl_launch_dependents();
     pdl_wait();
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(own_base);
-    const int* flags = reinterpret_cast<const int*>(base + ggb_peer_flags_off(n, d_cap));
-    const int e = *reinterpret_cast<const volatile int*>(base + ggb_peer_state_off(n, d_cap) + 4);   /* epoch this rank just produced */
-    if (threadIdx.x < n) {
-        unsigned long long t0 = 0;
-        int spins = 0;
-        while ((int)(ld_acquire_sys(flags + threadIdx.x) - e) < 0) {
-            if (++spins == 4096) {   /* a dead peer must not hang the GPU: give up after ~20 s and kill the context */
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                if (!t0) t0 = t;
-                else if (t - t0 > 20000000000ull) { printf("ggufb200: peer all-reduce timed out waiting for rank %d (epoch %d)\n", (int)threadIdx.x, e); __trap(); }
-                spins = 0;
+    uint8_t* base = reinterpret_cast<uint8_t*>(own_base);
+    int* state = reinterpret_cast<int*>(base + ggb_peer_state_off(n, d_cap));
+    const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int*>(state + 1) + 1);   /* the exchange this rank just fed */
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d) {
+        const uint8_t* recv = base + (size_t)(e & 1) * n * d_cap * 16;
+        double s = 0.0;
+        for (int r = 0; r < n; r++) {
+            const void* src = recv + ((size_t)r * d_cap + i) * 16;
+            double v;
+            unsigned long long t0 = 0;
+            int spins = 0;
+            while (!ld_ll_f64(src, e, v)) {
+                if (++spins == 4096) {   /* a dead peer must not hang the GPU: give up after ~20 s and kill the context */
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                    if (!t0) t0 = t;
+                    else if (t - t0 > 20000000000ull) { printf("ggufb200: peer exchange timed out waiting for rank %d (epoch %u)\n", r, e); __trap(); }
+                    spins = 0;
+                }
             }
+            s += v;
         }
+        x[i] = __fadd_rn(x[i], (float)s);
     }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d) return;
-    const double* recv = reinterpret_cast<const double*>(base) + (size_t)(e & 1) * n * d_cap;
-    double s = 0.0;
-    for (int r = 0; r < n; r++) s += ld_cg_f64(recv + (size_t)r * d_cap + i);
-    x[i] = __fadd_rn(x[i], (float)s);
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(state, 1);
+        if (prev == (int)gridDim.x - 1) {          /* every CTA has consumed epoch e: the next exchange may reuse e's parity after one more */
+            *reinterpret_cast<volatile int*>(state) = 0;
+            *reinterpret_cast<volatile int*>(state + 1) = (int)e;
+        }
+    }
 }
 
 extern "C" int ggb_peer_reduce_residual(float* x, const void* own_region, int n, int64_t d, int64_t d_cap, int use_pdl, void* stream) {
