@@ -26,7 +26,7 @@ class BatchDecoder:
             raise cabi.GGBError("batched decode is single-GPU (tensor-parallel engines time-slice their slots)")
         self.eng, self.torch, self.lib, self.hp = eng, torch, eng.lib, eng.hp
         hp, dev = eng.hp, eng.dev
-        self.nb_max = NB = int(max_batch or len(eng.slots))
+        self.nb_max = NB = int(max_batch or max(len(eng.slots), 16))   # >= 16 so that prompts prefill 16 tokens per pass
         self.stream = eng.stream
         self.use_pdl = eng.use_pdl
         qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
@@ -44,7 +44,7 @@ class BatchDecoder:
         self._graphs = {}
 
     # ------------------------------------------------------------------ one forward pass for nb tokens
-    def _enqueue(self, nb: int, s: int):
+    def _enqueue(self, nb: int, s: int, head: bool = True):
         lib, hp, e, pdl = self.lib, self.hp, self.eng, self.use_pdl
         qd = hp.n_head * hp.head_dim
         ids, pos, slot = (self.meta[i].data_ptr() for i in range(3))
@@ -77,6 +77,8 @@ class BatchDecoder:
                   (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)], hp.d, cabi.EPI_SWIGLU)
             prep(self.h, None, hp.ff, L["wd"])
             gemv([(L["wd"].ptr, L["wd"].type, L["wd"].rows, xp)], hp.ff, cabi.EPI_RESIDUAL, residual=xp)
+        if not head:      # prompt tokens whose logits nobody reads: the pass only fills the KV cache
+            return
         prep(self.x, e.out_norm, hp.d, e.w_out)
         gemv([(e.w_out.ptr, e.w_out.type, e.w_out.rows, self.logits.data_ptr())], hp.d, cabi.EPI_STORE)
         cabi.check(lib.ggb_argmax_rows(self.logits.data_ptr(), hp.vocab, nb, self.next_tok.data_ptr(), s), "argmax_rows")
@@ -87,17 +89,22 @@ class BatchDecoder:
         return nb + self.hp.n_layer * per_layer + 1 + passes(0) + 1
 
     # ------------------------------------------------------------------ public
-    def step(self, entries) -> list[int]:
-        """entries: [(slot index, token id, position)], distinct slots.  Runs the tokens through the model, writes
-        their K/V at the given positions and returns the greedy next token of each entry (logits stay on the
-        device: logits_row)."""
+    def step(self, entries, head: bool = True) -> list[int]:
+        """entries: [(slot index, token id, position)].  Runs the tokens through the model, writes their K/V at the
+        given positions and returns the greedy next token of each entry (logits stay on the device: logits_row).
+        A slot may appear several times with CONSECUTIVE positions (a prompt chunk): all K/V of the batch are written
+        before attention runs and entry j attends positions <= pos[j], so the result is the token-by-token one.
+        head=False skips the lm-head (prompt chunks whose logits nobody reads); returns []."""
         nb = len(entries)
         if not 0 < nb <= self.nb_max:
             raise ValueError(f"batch of {nb} entries (1..{self.nb_max})")
         e, torch = self.eng, self.torch
         slots = [en[0] for en in entries]
-        if len(set(slots)) != nb:
-            raise ValueError("a slot appears twice in one batch")
+        seen = {}
+        for sl, _, pos in entries:
+            if sl in seen and pos != seen[sl] + 1:
+                raise ValueError("entries of one slot must be consecutive positions in ascending order")
+            seen[sl] = pos
         for sl, tok, pos in entries:
             if not (0 <= sl < len(e.slots) and 0 <= pos < e.n_ctx and 0 <= tok < self.hp.vocab):
                 raise ValueError(f"bad batch entry (slot {sl}, token {tok}, position {pos})")
@@ -108,23 +115,31 @@ class BatchDecoder:
         with torch.cuda.stream(self.stream):
             self.meta.copy_(mh, non_blocking=True)
             if not e.use_graph:
-                self._enqueue(nb, self.stream.cuda_stream)
+                self._enqueue(nb, self.stream.cuda_stream, head)
             else:
-                g = self._graphs.get(nb)
+                g = self._graphs.get((nb, head))
                 if g is None:
-                    self._enqueue(nb, self.stream.cuda_stream)      # first use: sets kernel attributes outside capture
+                    self._enqueue(nb, self.stream.cuda_stream, head)   # first use: sets kernel attributes outside capture
                     self.stream.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.stream):
-                        self._enqueue(nb, torch.cuda.current_stream().cuda_stream)
-                    self._graphs[nb] = g
+                        self._enqueue(nb, torch.cuda.current_stream().cuda_stream, head)
+                    self._graphs[(nb, head)] = g
                 g.replay()
-            self.next_host.copy_(self.next_tok, non_blocking=True)
+            if head:
+                self.next_host.copy_(self.next_tok, non_blocking=True)
         self.stream.synchronize()
         for sl, _, pos in entries:
             e.slots[sl].n_past = pos + 1
             e.slots[sl].chain_valid = False     # the slot's own device-side (token, position, x) no longer match
-        return self.next_host[:nb].tolist()
+        return self.next_host[:nb].tolist() if head else []
+
+    def prefill(self, slot: int, tokens: list[int], start: int):
+        """Write the K/V of `tokens` at positions start.. of one slot, 16 tokens per pass over the weights (bit-identical
+        to feeding them one by one)."""
+        for c0 in range(0, len(tokens), self.nb_max):
+            chunk = tokens[c0:c0 + self.nb_max]
+            self.step([(slot, int(t), start + c0 + j) for j, t in enumerate(chunk)], head=False)
 
     def logits_row(self, b: int) -> np.ndarray:
         if self.logits_host is None:

@@ -317,9 +317,14 @@ class Slot:
             for c0 in range(0, len(tokens), e.prefill_chunk):
                 self._prefill_gemm(tokens[c0:c0 + e.prefill_chunk], start + c0)
             return
+        first = 0
+        if e.tp_size == 1 and len(tokens) >= 4:
+            # all but the last token only fill the KV cache: 16 per pass through the batched kernels (same arithmetic)
+            e.batch.prefill(self.index, tokens[:-1], start)
+            first = len(tokens) - 1
         with self.torch.cuda.stream(self.stream):
-            for i, t in enumerate(tokens):
-                self._set_tok_pos(int(t), start + i)
+            for i in range(first, len(tokens)):
+                self._set_tok_pos(int(tokens[i]), start + i)
                 self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
                 self.stream.synchronize()  # host_i32 is reused for the next token
         self.n_past = start + len(tokens)
@@ -415,7 +420,7 @@ class Engine:
         t0 = time.time()
         self._load_weights()
         self.load_seconds = time.time() - t0
-        self.gemm_prefill_min = int(os.environ.get("GGB_GEMM_PREFILL_MIN", "32"))   # prompts at least this long use the GEMM path
+        self.gemm_prefill_min = int(os.environ.get("GGB_GEMM_PREFILL_MIN", "64"))   # prompts at least this long use the GEMM path
         self.prefill_chunk = 2048
         self._pf = None
         n_slots = max(1, n_slots)

@@ -235,9 +235,15 @@ def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
         ref.append(m.greedy(PROMPT + [310 + s], 2)[1])
     assert out == ref
     with pytest.raises(ValueError):
-        eng.batch.step([(1, 5, 3), (1, 6, 4)])            # the same slot twice
+        eng.batch.step([(1, 5, 3), (1, 6, 7)])            # one slot twice, positions not consecutive
     with pytest.raises(ValueError):
         eng.batch.step([(0, 5, 64)])                      # position outside the context
     with pytest.raises(ValueError):
         eng.batch.step([])
+    # a prompt chunk = one slot at consecutive positions: same result as feeding the tokens one by one
+    toks = PROMPT + [320, 321, 322, 323, 324, 325]
+    eng.slots[2].reset()
+    eng.batch.prefill(2, toks[:-1], 0)
+    nxt = eng.batch.step([(2, toks[-1], len(toks) - 1)])
+    assert nxt == [oracle.OracleLlama(path, n_ctx=64, mode="canon").greedy(toks, 1)[0]]
     eng.close()
