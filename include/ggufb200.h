@@ -136,6 +136,33 @@ int ggb_gemv(const ggb_gemv_args* args, void* stream);
 /* number of CTAs ggb_gemv will launch for these args (size of part_val/part_idx) */
 int ggb_gemv_grid(const ggb_gemv_args* args);
 
+/* ---- K7: one persistent cooperative launch per decoded token (csrc/mega.cu): the GEMV phases described by
+ * `phases` (exactly the ggb_gemv_args the multi-kernel path would launch, in order; epilogues STORE, RESIDUAL, SWIGLU,
+ * ROPE_KV, ARGMAX), the attention after every phase i with attn_out[i] != NULL (q = that phase's segment-0 output,
+ * caches = its kcache/vcache, position = *pos_dev), all separated by grid barriers; weights keep streaming into the
+ * per-warp rings across phase boundaries.  Bit-identical to launching the phases one by one.
+ *   ggb_mega_plan   converts the phase list into the device table `plan_dev` (ggb_mega_plan_bytes(n) bytes;
+ *                   synchronous copy, set-up time only) and reports the weight-type mask to pass to ggb_mega_run;
+ *   ggb_mega_run    memset of the barrier word + the launch (CUDA-graph capturable).  k_max / rows_max = largest inner
+ *                   dimension / largest total row count of any phase (shared-memory sizing). */
+typedef struct ggb_mega_args {
+    const void* plan;
+    int32_t n_phases, type_mask;
+    void* barrier;             /* 4 bytes of device memory */
+    const int32_t* pos_dev;
+    const float* rope_tab;
+    int32_t n_rot, head_dim, n_head, n_kv, n_ctx;
+    int32_t k_max;
+    int64_t rows_max;
+    float* part_val;           /* [SM count] arg-max partials of the GGB_EPI_ARGMAX phase */
+    int32_t* part_idx;
+    void* timeline;            /* debug: NULL, or n_phases * SM count * 6 u64 %globaltimer stamps per launch */
+} ggb_mega_args;
+struct ggb_gemv_args;
+int64_t ggb_mega_plan_bytes(int n_phases);
+int ggb_mega_plan(const struct ggb_gemv_args* phases, const float* const* attn_out, int n_phases, void* plan_dev, int* mask_out);
+int ggb_mega_run(const ggb_mega_args* args, void* stream);
+
 /* ---- K2: dequant-GEMM on tcgen05 / TMEM (ggml mul_mat with many activation columns: prefill, large batches)
  *   Y[tokens][y_stride >= rows] (f32) = X[tokens][k] (bf16) . W[rows][k]^T,  W in tile-SoA layout, k % 128 == 0.
  * Weights are dequantised exactly (f32) and rounded to bf16 inside the kernel; accumulation is f32 in TMEM. */

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libggufb200.so")
+LIB_PATH = os.environ.get("GGB_LIB_PATH") or os.path.join(HERE, "libggufb200.so")   # override: experiment builds (tools/)
 
 F32, F16, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 8, 12, 13, 14
 MAX_SEG = 3
@@ -27,6 +27,7 @@ EXPORTS = [
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
+    "ggb_mega_plan_bytes", "ggb_mega_plan", "ggb_mega_run",
     "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
     "ggb_act_image_bytes", "ggb_act_prep", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows",
 ]
@@ -64,6 +65,16 @@ class GemvBatchArgs(C.Structure):
         ("epilogue", C.c_int32), ("nb", C.c_int32),
         ("act", C.c_void_p), ("residual", C.c_void_p),
         ("use_pdl", C.c_int32), ("grid", C.c_int32),
+    ]
+
+
+class MegaArgs(C.Structure):
+    _fields_ = [
+        ("plan", C.c_void_p), ("n_phases", C.c_int32), ("type_mask", C.c_int32),
+        ("barrier", C.c_void_p), ("pos_dev", C.c_void_p), ("rope_tab", C.c_void_p),
+        ("n_rot", C.c_int32), ("head_dim", C.c_int32), ("n_head", C.c_int32), ("n_kv", C.c_int32), ("n_ctx", C.c_int32),
+        ("k_max", C.c_int32), ("rows_max", C.c_int64),
+        ("part_val", C.c_void_p), ("part_idx", C.c_void_p), ("timeline", C.c_void_p),
     ]
 
 
@@ -105,6 +116,9 @@ def lib() -> C.CDLL:
         "ggb_rope_kv_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
         "ggb_attn_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "ggb_add_f32": ([vp, vp, i64, vp], i32),
+        "ggb_mega_plan_bytes": ([i32], i64),
+        "ggb_mega_plan": ([C.POINTER(GemvArgs), C.POINTER(vp), i32, vp, C.POINTER(i32)], i32),
+        "ggb_mega_run": ([C.POINTER(MegaArgs), vp], i32),
         "ggb_peer_region_bytes": ([i32, i64], i64),
         "ggb_peer_alloc": ([sz, C.POINTER(vp), C.c_char_p], i32),
         "ggb_peer_open": ([C.c_char_p, C.POINTER(vp)], i32),

@@ -5,8 +5,9 @@
 // One CTA computes a 128 (weight rows) x 256 (tokens) output tile:
 //   * 8 producer warps unpack the packed weights of the current 128-wide K block straight into shared memory as
 //     bf16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
-//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5), and copy the matching
-//     bf16 activation block next to it; fence.proxy.async + mbarrier hand the stage to the MMA warp;
+//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5); the matching bf16
+//     activation block arrives next to it by cp.async, issued one K block ahead; weight tiles are prefetched into
+//     L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
 //   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) eight
 //     times per K block from shared-memory descriptors; the f32 accumulator (128 lanes x 256 columns) lives in
 //     TMEM; tcgen05.commit releases the shared-memory stage back to the producers and, after the last block,
@@ -199,23 +200,48 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
 
     if (warp < GM_PRODUCER_WARPS) {
         // ===== producers: dequantise A, copy B =====
+        // The activation block travels global -> shared with cp.async (no registers, swizzle applied per 16-byte
+        // chunk) one K block AHEAD, so its latency hides behind the dequantisation of the current block; the weight
+        // tiles (2048 elements per row) are pulled into L2 one tile ahead so the dequantiser's loads are L2 hits.
         const int pt = tid;                                   /* 0..255 */
+        const int tile_bytes = ggb_sb_bytes(TYPE) * GGB_TILE_SB;
+        auto issue_b = [&](int kb) {
+            uint8_t* sB = stage_base + (kb % GM_STAGES) * GM_STAGE_BYTES + GM_A_BYTES;
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int id = i * 256 + pt;
+                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 bf16 = 128 K */
+                const bool live = tok0 + tk < tokens;
+                const __nv_bfloat16* src = X + (int64_t)(live ? tok0 + tk : 0) * K + kb * GM_BK + kc * 8;
+                const uint32_t dst = gm_smem_u32(sB + (kc >> 3) * (GM_BN * 128) + gm_sw(tk, kc & 7));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(live ? 16 : 0) : "memory");   /* src-size 0: zero fill */
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto prefetch_tile = [&](int t) {                      /* one thread per row pulls tile t of its row into L2 */
+            if (pt < GM_BM && row0 + pt < rows && t * GGB_TILE_ELEMS < K) {
+                const uint8_t* p = W + (int64_t)(row0 + pt) * w_stride + (int64_t)t * tile_bytes;
+                for (int o = 0; o < tile_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            }
+        };
+        prefetch_tile(0);
+        prefetch_tile(1);
+        gm_mbar_wait(gm_smem_u32(&bar_empty[0]), 1);           /* fresh barrier: returns at once */
+        issue_b(0);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % GM_STAGES;
-            const uint32_t ph = (kb / GM_STAGES) & 1;
-            gm_mbar_wait(gm_smem_u32(&bar_empty[s]), ph ^ 1);   /* first pass over a fresh barrier returns at once */
             uint8_t* sA = stage_base + s * GM_STAGE_BYTES;
-            uint8_t* sB = sA + GM_A_BYTES;
-            // A: thread -> (row, 64-element half of the K block)
+            // A: thread -> (row, 64-element half of the K block); stage s is free (waited for when B(kb) was issued)
             {
                 const int r = pt & 127, hk = pt >> 7;         /* hk = which 64-wide atom of the 128-wide block */
                 const int k0 = kb * GM_BK + hk * 64;
+                if ((kb * GM_BK) % GGB_TILE_ELEMS == 0) prefetch_tile(kb * GM_BK / GGB_TILE_ELEMS + 2);
                 Chunk8 ch;
                 const int grow = row0 + r;
                 if (grow < rows) {
                     const int t = k0 / GGB_TILE_ELEMS, ek = k0 - t * GGB_TILE_ELEMS;
                     const int nsb = ggb_tile_nsb(K, t), U = 4 * nsb;
-                    const uint8_t* tile = W + (int64_t)grow * w_stride + (int64_t)t * (ggb_sb_bytes(TYPE) * GGB_TILE_SB);
+                    const uint8_t* tile = W + (int64_t)grow * w_stride + (int64_t)t * tile_bytes;
                     if (TYPE == GGB_TYPE_Q4_K) dq_unit_q4k(tile, U, ek >> 6, ch);
                     else if (TYPE == GGB_TYPE_Q6_K) dq_block64_q6k(tile, U, nsb, ek >> 8, (ek >> 6) & 3, ch);
                     else dq_unit_q8_0(tile, U, ek >> 6, ch);
@@ -227,15 +253,13 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
 #pragma unroll
                 for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(atom + gm_sw(r, c)) = ch.c[c];
             }
-            // B: 256 tokens x 128 K bf16 = 4096 chunks of 16 B, 16 per thread; chunk id -> (token, k chunk)
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {
-                const int id = i * 256 + pt;
-                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 bf16 = 128 K */
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (tok0 + tk < tokens) v = __ldg(reinterpret_cast<const uint4*>(X + (int64_t)(tok0 + tk) * K + kb * GM_BK + kc * 8));
-                uint8_t* atom = sB + (kc >> 3) * (GM_BN * 128);
-                *reinterpret_cast<uint4*>(atom + gm_sw(tk, kc & 7)) = v;
+            if (kb + 1 < nkb) {
+                const int s1 = (kb + 1) % GM_STAGES;
+                gm_mbar_wait(gm_smem_u32(&bar_empty[s1]), (((kb + 1) / GM_STAGES) & 1) ^ 1);
+                issue_b(kb + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");    /* B(kb) has landed; B(kb+1) may still fly */
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the tensor core */
             __syncwarp();
