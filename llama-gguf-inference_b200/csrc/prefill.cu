@@ -2,6 +2,7 @@
 // RoPE + f16 KV-cache write for T tokens, causal GQA attention over the cache, and residual add.
 // Stands in for the batch forms of ggml's get_rows / rope / cpy / flash_attn_ext / add [UPSTREAM-MEM].
 // Numerics: f32 with an online softmax -- the tolerance-level path (the GEMM feeding it is bf16 x bf16).
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -153,71 +154,173 @@ extern "C" int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_i
     return GGB_OK;
 }
 
-// Causal attention for T query tokens at positions pos0..pos0+T-1 over the f16 cache.
-// CTA = one KV head x a block of query tokens: 16 warps = G query heads x (16/G) tokens, so a K/V tile staged in
-// shared memory is reused by every warp.  Warp = one (head, token) query: lanes own head_dim/32 dims, online softmax.
-#define AP_WARPS 16
-#define AP_TILE 64
+// Causal attention for T query tokens at positions pos0..pos0+T-1 over the f16 cache, flash-attention style on the
+// tensor cores (mma.sync m16n8k16, f16 operands, f32 accumulate): CTA = one query head x 64 query tokens, 4 warps of
+// 16 query rows each; K/V tiles of 64 positions are staged in shared memory by cp.async; S = Q.K^T and O += P.V are
+// MMAs fed by ldmatrix (K non-transposed, V transposed); online softmax in registers.  q is rounded to f16 first (as
+// the decode kernel and the CPU path do for the K.Q operand).  Tolerance-level numerics, like the GEMM feeding it.
+#define AP_BM 64           /* query tokens per CTA */
+#define AP_BN 64           /* cache positions per tile */
+#define AP_WARPS 4
+
+__device__ __forceinline__ void ap_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ap_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ap_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ap_pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 template <int HD>
 __global__ void __launch_bounds__(AP_WARPS * 32) attn_prefill_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
                                                                    const uint16_t* __restrict__ vc, int T, int pos0, int n_head, int n_kv,
                                                                    float* __restrict__ out) {
-    constexpr int DPL = HD / 32;                 /* dims per lane: 4 (hd 128) or 2 (hd 64) */
-    __shared__ __align__(16) uint16_t sk[AP_TILE][HD];
-    __shared__ __align__(16) uint16_t sv[AP_TILE][HD];
-    const int G = n_head / n_kv;
-    const int tpb = AP_WARPS / G;                /* query tokens per CTA */
-    const int kvh = blockIdx.x, tb = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = warp % G, tq = tb * tpb + warp / G;
-    const bool live = tq < T && warp < G * tpb;
-    const int head = kvh * G + g;
-    const int pq = pos0 + tq;                    /* this query attends positions 0..pq */
-    const int64_t kvd = (int64_t)n_kv * HD;
-    const int last_tok = min(T, (tb + 1) * tpb) - 1;
-    const int n_pos = pos0 + last_tok + 1;       /* positions the CTA needs */
+    constexpr int LD = HD + 8;                   /* padded row (halves): 16-byte rows land in distinct banks for ldmatrix */
+    constexpr int KS = HD / 16;                  /* k-steps of Q.K^T */
+    constexpr int NT = HD / 8;                   /* n-tiles (8 dims) of the output */
+    extern __shared__ __align__(16) uint16_t ap_sm[];
+    uint16_t* sq = ap_sm;                        /* [AP_BM][LD] */
+    uint16_t* sk = sq + AP_BM * LD;              /* [AP_BN][LD] */
+    uint16_t* sv = sk + AP_BN * LD;              /* [AP_BN][LD] */
+    const int head = blockIdx.x, qb = blockIdx.y;
+    const int kvh = head / (n_head / n_kv);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int q0 = qb * AP_BM;
+    const int64_t qd = (int64_t)n_head * HD, kvd = (int64_t)n_kv * HD;
 
-    float qr[DPL];
-    if (live) {
+    // Q tile -> shared memory as f16 (rows beyond T are zero)
+    for (int i = tid; i < AP_BM * (HD / 4); i += AP_WARPS * 32) {
+        const int r = i / (HD / 4), c4 = i % (HD / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < T) v = *reinterpret_cast<const float4*>(q + (int64_t)(q0 + r) * qd + (int64_t)head * HD + c4 * 4);
+        uint2 pk;
+        pk.x = ap_pack_h2(v.x, v.y); pk.y = ap_pack_h2(v.z, v.w);
+        *reinterpret_cast<uint2*>(sq + r * LD + c4 * 4) = pk;
+    }
+    __syncthreads();
+    uint32_t qa[KS][4];
+    {
+        const int m = lane >> 3, rr = lane & 7;  /* matrix m of the x4 load: rows +8*(m&1), cols +8*(m>>1) */
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(sq + (warp * 16 + 8 * (m & 1) + rr) * LD + 8 * (m >> 1));
 #pragma unroll
-        for (int i = 0; i < DPL; i++) qr[i] = h2f(f2h(q[(int64_t)tq * n_head * HD + (int64_t)head * HD + lane * DPL + i]));
+        for (int ks = 0; ks < KS; ks++) ap_ldsm_x4(base + ks * 32, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
     }
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
-    float m = -FLT_MAX, l = 0.f, acc[DPL];
+    float o[NT][4];
 #pragma unroll
-    for (int i = 0; i < DPL; i++) acc[i] = 0.f;
+    for (int n = 0; n < NT; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+    const int tq0 = q0 + warp * 16 + g, tq1 = tq0 + 8;                 /* this thread's two query tokens */
+    const int lim0 = pos0 + tq0, lim1 = pos0 + tq1;                    /* last position each may attend */
+    const int n_pos = pos0 + min(T, q0 + AP_BM);                       /* positions the CTA needs */
 
-    for (int p0 = 0; p0 < n_pos; p0 += AP_TILE) {
-        const int np = min(AP_TILE, n_pos - p0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < np * (HD / 8); i += AP_WARPS * 32) {
-            const int r = i / (HD / 8), c = i % (HD / 8);
-            *reinterpret_cast<uint4*>(&sk[r][c * 8]) = *reinterpret_cast<const uint4*>(kc + (int64_t)(p0 + r) * kvd + (int64_t)kvh * HD + c * 8);
-            *reinterpret_cast<uint4*>(&sv[r][c * 8]) = *reinterpret_cast<const uint4*>(vc + (int64_t)(p0 + r) * kvd + (int64_t)kvh * HD + c * 8);
+    for (int p0 = 0; p0 < n_pos; p0 += AP_BN) {
+        __syncthreads();                                               /* previous tile fully consumed */
+        for (int i = tid; i < AP_BN * (HD / 8); i += AP_WARPS * 32) {
+            const int r = i / (HD / 8), c8 = i % (HD / 8);
+            const bool live = p0 + r < n_pos;
+            const int64_t off = (int64_t)(live ? p0 + r : 0) * kvd + (int64_t)kvh * HD + c8 * 8;
+            const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sk + r * LD + c8 * 8), dv = (uint32_t)__cvta_generic_to_shared(sv + r * LD + c8 * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(kc + off), "r"(live ? 16 : 0) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(vc + off), "r"(live ? 16 : 0) : "memory");
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        if (live) {
-            const int lim = min(np, pq - p0 + 1);
-            for (int r = 0; r < lim; r++) {
-                float s = 0.f;
+        if (p0 > pos0 + q0 + warp * 16 + 15) continue;                 /* the whole tile is in this warp's future */
+
+        // S = Q.K^T : 16 query rows x 64 positions per warp
+        float sc[AP_BN / 8][4];
 #pragma unroll
-                for (int i = 0; i < DPL; i++) s += h2f(sk[r][lane * DPL + i]) * qr[i];
-                s = warp_sum(s) * scale;
-                const float mn = fmaxf(m, s);
-                const float corr = __expf(m - mn), pw = __expf(s - mn);
-                l = l * corr + pw;
+        for (int n = 0; n < AP_BN / 8; n++) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f; }
+        {
+            const int m = lane >> 3, rr = lane & 7;                    /* matrix m: positions n*8 + rr, dims +8*m */
 #pragma unroll
-                for (int i = 0; i < DPL; i++) acc[i] = acc[i] * corr + pw * h2f(sv[r][lane * DPL + i]);
-                m = mn;
+            for (int n = 0; n < AP_BN / 8; n++) {
+                const uint32_t base = (uint32_t)__cvta_generic_to_shared(sk + (n * 8 + rr) * LD + 8 * m);
+#pragma unroll
+                for (int kp = 0; kp < KS / 2; kp++) {                  /* two k-steps per x4 load */
+                    uint32_t b0, b1, b2, b3;
+                    ap_ldsm_x4(base + kp * 64, b0, b1, b2, b3);
+                    ap_mma(sc[n], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+                    ap_mma(sc[n], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+                }
+            }
+        }
+        // scale, causal mask, online softmax (rows g and g+8; a row's 64 scores live in the 4 lanes of a quad)
+        float mx0 = mrow[0], mx1 = mrow[1];
+#pragma unroll
+        for (int n = 0; n < AP_BN / 8; n++) {
+            const int pc = p0 + n * 8 + 2 * t4;
+            sc[n][0] = (pc <= lim0) ? sc[n][0] * scale : -INFINITY;
+            sc[n][1] = (pc + 1 <= lim0) ? sc[n][1] * scale : -INFINITY;
+            sc[n][2] = (pc <= lim1) ? sc[n][2] * scale : -INFINITY;
+            sc[n][3] = (pc + 1 <= lim1) ? sc[n][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // position 0 is visible to every query, so after the first tile the running maxima are finite
+        const float c0 = __expf(mrow[0] - mx0), c1 = __expf(mrow[1] - mx1);
+        mrow[0] = mx0; mrow[1] = mx1;
+        lrow[0] *= c0; lrow[1] *= c1;
+#pragma unroll
+        for (int n = 0; n < NT; n++) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+        uint32_t pa[AP_BN / 16][4];                                    /* P as f16 A-fragments: k-step j = n-tiles 2j, 2j+1 */
+#pragma unroll
+        for (int n = 0; n < AP_BN / 8; n++) {
+            const float e0 = __expf(sc[n][0] - mx0), e1 = __expf(sc[n][1] - mx0), e2 = __expf(sc[n][2] - mx1), e3 = __expf(sc[n][3] - mx1);
+            lrow[0] += e0 + e1; lrow[1] += e2 + e3;
+            pa[n >> 1][(n & 1) * 2 + 0] = ap_pack_h2(e0, e1);
+            pa[n >> 1][(n & 1) * 2 + 1] = ap_pack_h2(e2, e3);
+        }
+        // O += P.V : V fragments by transposed ldmatrix (matrix m: positions +8*(m&1), dims +8*(m>>1))
+        {
+            const int m = lane >> 3, rr = lane & 7;
+#pragma unroll
+            for (int j = 0; j < AP_BN / 16; j++) {
+                const uint32_t base = (uint32_t)__cvta_generic_to_shared(sv + (j * 16 + 8 * (m & 1) + rr) * LD + 8 * (m >> 1));
+#pragma unroll
+                for (int np = 0; np < NT / 2; np++) {                  /* two output n-tiles per x4 load */
+                    uint32_t b0, b1, b2, b3;
+                    ap_ldsm_x4_t(base + np * 32, b0, b1, b2, b3);
+                    ap_mma(o[2 * np], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b0, b1);
+                    ap_mma(o[2 * np + 1], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b2, b3);
+                }
             }
         }
     }
-    if (live) {
-        const float inv = __fdiv_rn(1.0f, l);
+    lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 1); lrow[0] += __shfl_xor_sync(0xffffffffu, lrow[0], 2);
+    lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 1); lrow[1] += __shfl_xor_sync(0xffffffffu, lrow[1], 2);
+    const float i0 = __fdiv_rn(1.0f, lrow[0]), i1 = __fdiv_rn(1.0f, lrow[1]);
 #pragma unroll
-        for (int i = 0; i < DPL; i++) out[(int64_t)tq * n_head * HD + (int64_t)head * HD + lane * DPL + i] = acc[i] * inv;
+    for (int n = 0; n < NT; n++) {
+        const int d = n * 8 + 2 * t4;
+        if (tq0 < T) *reinterpret_cast<float2*>(out + (int64_t)tq0 * qd + (int64_t)head * HD + d) = make_float2(o[n][0] * i0, o[n][1] * i0);
+        if (tq1 < T) *reinterpret_cast<float2*>(out + (int64_t)tq1 * qd + (int64_t)head * HD + d) = make_float2(o[n][2] * i1, o[n][3] * i1);
     }
+}
+
+template <int HD>
+static int launch_attn_prefill(const float* q, const uint16_t* kc, const uint16_t* vc, int tokens, int pos0, int n_head, int n_kv, float* out,
+                               cudaStream_t st) {
+    const size_t smem = (size_t)(AP_BM + 2 * AP_BN) * (HD + 8) * sizeof(uint16_t);
+    static bool attr = false;
+    if (!attr) {
+        GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(n_head, (tokens + AP_BM - 1) / AP_BM);
+    attn_prefill_kernel<HD><<<grid, AP_WARPS * 32, smem, st>>>(q, kc, vc, tokens, pos0, n_head, n_kv, out);
+    GGB_CHECK_LAUNCH("ggb_attn_prefill");
+    return GGB_OK;
 }
 
 extern "C" int ggb_attn_prefill(const float* q, const uint16_t* kcache, const uint16_t* vcache, int tokens, int pos0, int n_head, int n_kv,
@@ -225,16 +328,10 @@ extern "C" int ggb_attn_prefill(const float* q, const uint16_t* kcache, const ui
     if (tokens < 0 || pos0 < 0 || n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_prefill: bad shape");
     if (tokens == 0) return GGB_OK;
     if (!q || !kcache || !vcache || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_prefill: null pointer");
-    const int G = n_head / n_kv;
-    if (G > AP_WARPS || (AP_WARPS % G)) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_prefill: GQA group %d not supported (1, 2, 4, 8, 16)", G);
-    const int tpb = AP_WARPS / G;
-    dim3 grid(n_kv, (tokens + tpb - 1) / tpb);
     cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128) attn_prefill_kernel<128><<<grid, AP_WARPS * 32, 0, st>>>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out);
-    else if (head_dim == 64) attn_prefill_kernel<64><<<grid, AP_WARPS * 32, 0, st>>>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out);
-    else GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_prefill: head_dim=%d (supported: 64, 128)", head_dim);
-    GGB_CHECK_LAUNCH("ggb_attn_prefill");
-    return GGB_OK;
+    if (head_dim == 128) return launch_attn_prefill<128>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out, st);
+    if (head_dim == 64) return launch_attn_prefill<64>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out, st);
+    GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_prefill: head_dim=%d (supported: 64, 128)", head_dim);
 }
 
 // embedding gather for a list of tokens: out[t][k] = dequant(token_embd row ids[t]) -- one launch per token would do,

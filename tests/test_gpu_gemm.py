@@ -59,3 +59,27 @@ def test_gemm_rejects_bad_arguments():
     assert L.ggb_gemm(12, t.data_ptr(), 4, 100, t.data_ptr(), 4, t.data_ptr(), 4, 0) == -1
     assert L.ggb_gemm(2, t.data_ptr(), 4, 256, t.data_ptr(), 4, t.data_ptr(), 4, 0) == -3
     assert L.ggb_gemm(12, t.data_ptr(), 0, 256, t.data_ptr(), 4, t.data_ptr(), 4, 0) == 0
+
+
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 8, 2), (64, 4, 4), (128, 4, 1)])
+@pytest.mark.parametrize("T,pos0", [(1, 0), (150, 37), (64, 0), (200, 300)])
+def test_attn_prefill_tensor_core_matches_oracle(oracle, hd, n_head, n_kv, T, pos0):
+    """flash-attention on mma.sync (csrc/prefill.cu) against the oracle's one-token attention, token by token"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    n_ctx = pos0 + T
+    rng = np.random.default_rng(hd + T + pos0)
+    q = rng.standard_normal((T, n_head * hd)).astype(np.float32)
+    kc = (rng.standard_normal((n_ctx, n_kv * hd)) * 0.5).astype(np.float16)
+    vc = rng.standard_normal((n_ctx, n_kv * hd)).astype(np.float16)
+    qd, kd, vd = U.to_dev(q), U.to_dev(kc.view(np.int16)), U.to_dev(vc.view(np.int16))
+    out = torch.zeros((T, n_head * hd), dtype=torch.float32, device=U.DEV)
+    cabi.check(L.ggb_attn_prefill(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), T, pos0, n_head, n_kv, hd, out.data_ptr(), U.stream_ptr()))
+    U.sync()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    for t in sorted({min(x, T - 1) for x in (0, 1, T // 2, max(T - 2, 0), T - 1, 63, 64)}):
+        ref = oracle.attn_decode(q[t], kc.view(np.uint16), vc.view(np.uint16), n_head, n_kv, hd, pos0 + t + 1)
+        assert np.abs(got[t] - ref).max() <= 3e-3 * max(np.abs(ref).max(), 1e-3), f"token {t}"
