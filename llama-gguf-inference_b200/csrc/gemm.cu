@@ -75,24 +75,41 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// small unsigned integer -> float without the (quarter-rate) I2F unit: 2^23 + n as a bit pattern, minus the bias (exact)
+__device__ __forceinline__ float u2f(uint32_t n) { return __fsub_rn(__uint_as_float(0x4B000000u | n), 8388608.0f); }
+__device__ __forceinline__ float u2f_bias(uint32_t n, float bias) { return __fsub_rn(__uint_as_float(0x4B000000u | n), bias); }   /* n - (bias - 2^23) */
+
 // dequantise 64 consecutive elements (one "unit") of a weight row into 8 chunks of 8 bf16
 struct Chunk8 { uint4 c[8]; };
 
-__device__ __forceinline__ void dq_unit_q4k(const uint8_t* tile, int U, int u, Chunk8& o) {
-    const uint4 q0 = ldg_stream(tile + 16 * u), q1 = ldg_stream(tile + 16 * U + 16 * u);
-    const uint8_t* hdr = tile + 32 * U + 16 * (u >> 2);
-    const uint4 h = ldg_cached(hdr);
+// The dequantiser is split into "fetch the packed bytes of my 64 elements" (issued one K block ahead, so the L2 /
+// HBM latency hides behind the conversion of the current block) and "convert them to 8 chunks of 8 bf16".
+template <int TYPE> struct Raw;
+template <> struct Raw<GGB_TYPE_Q4_K> { uint4 q0, q1, h; int g; };
+template <> struct Raw<GGB_TYPE_Q6_K> { uint4 ql[4], qh[2]; uint2 sc8; uint32_t d16; int rp; };
+template <> struct Raw<GGB_TYPE_Q8_0> { uint4 w[4]; uint32_t dd; };
+
+// ek = element offset of the 64-element group inside its 2048-element tile
+__device__ __forceinline__ void dq_fetch(Raw<GGB_TYPE_Q4_K>& R, const uint8_t* tile, int U, int nsb, int ek) {
+    const int u = ek >> 6;
+    R.q0 = ldg_stream(tile + 16 * u);
+    R.q1 = ldg_stream(tile + 16 * U + 16 * u);
+    R.h = ldg_cached(tile + 32 * U + 16 * (u >> 2));
+    R.g = u & 3;
+}
+__device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q4_K>& R, Chunk8& o) {
     int s0, m0, s1, m1;
     {
-        const int g = u & 3;
-        const uint8_t* p = reinterpret_cast<const uint8_t*>(&h) + 4 + 3 * g;
-        const uint32_t f = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+        const uint32_t hw[4] = {R.h.x, R.h.y, R.h.z, R.h.w};
+        const int bo = 4 + 3 * R.g;                              /* byte offset of the 24-bit field inside the header */
+        const uint64_t two = (uint64_t)hw[bo >> 2] | ((uint64_t)hw[min((bo >> 2) + 1, 3)] << 32);
+        const uint32_t f = (uint32_t)(two >> (8 * (bo & 3))) & 0xFFFFFFu;
         s0 = f & 63; s1 = (f >> 6) & 63; m0 = (f >> 12) & 63; m1 = (f >> 18) & 63;
     }
-    const float d = h2f((uint16_t)(h.x & 0xFFFF)), dmin = h2f((uint16_t)(h.x >> 16));
+    const float d = h2f((uint16_t)(R.h.x & 0xFFFF)), dmin = h2f((uint16_t)(R.h.x >> 16));
     const float d0 = __fmul_rn(d, (float)s0), d1 = __fmul_rn(d, (float)s1);
     const float n0 = __fmul_rn(dmin, (float)m0), n1 = __fmul_rn(dmin, (float)m1);
-    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};   /* bytes 0..31 of the 32-byte group */
+    const uint32_t w[8] = {R.q0.x, R.q0.y, R.q0.z, R.q0.w, R.q1.x, R.q1.y, R.q1.z, R.q1.w};   /* bytes 0..31 of the 32-byte group */
     // elements 0..31 = low nibbles (sub-block 2g), 32..63 = high nibbles (sub-block 2g+1)
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -103,9 +120,9 @@ __device__ __forceinline__ void dq_unit_q4k(const uint8_t* tile, int U, int u, C
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t word = w[2 * c + (j >> 1)];
-                const int b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
-                const int b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
-                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, (float)b0), nn), __fsub_rn(__fmul_rn(dd, (float)b1), nn));
+                const uint32_t b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
+                const uint32_t b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
+                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
             }
             o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
         }
@@ -113,19 +130,29 @@ __device__ __forceinline__ void dq_unit_q4k(const uint8_t* tile, int U, int u, C
 }
 
 // Q6_K: a 64-element K block j (0..3) of a super-block = elements 64j..64j+63 = half n=j>>1, r in {2*(j&1), 2*(j&1)+1}
-__device__ __forceinline__ void dq_block64_q6k(const uint8_t* tile, int U, int nsb, int sb, int j, Chunk8& o) {
-    const int n = j >> 1, rp = (j & 1) * 2;
-    const float d = h2f(__ldg(reinterpret_cast<const uint16_t*>(tile + 48 * U + 16 * nsb + 2 * sb)));
-    const int8_t* sc = reinterpret_cast<const int8_t*>(tile + 48 * U + 16 * sb + 8 * n);
+__device__ __forceinline__ void dq_fetch(Raw<GGB_TYPE_Q6_K>& R, const uint8_t* tile, int U, int nsb, int ek) {
+    const int sb = ek >> 8, j = (ek >> 6) & 3, n = j >> 1;
+    R.rp = (j & 1) * 2;
+    R.d16 = __ldg(reinterpret_cast<const uint16_t*>(tile + 48 * U + 16 * nsb + 2 * sb));
+    R.sc8 = __ldg(reinterpret_cast<const uint2*>(tile + 48 * U + 16 * sb + 8 * n));
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int u = 4 * sb + 2 * n + t;
+        R.qh[t] = ldg_stream(tile + 32 * U + 16 * u);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) R.ql[2 * rr + t] = ldg_stream(tile + (((R.rp + rr) & 1) ? 16 * U : 0) + 16 * u);
+    }
+}
+__device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q6_K>& R, Chunk8& o) {
+    const float d = h2f((uint16_t)R.d16);
+    const uint64_t sc64 = (uint64_t)R.sc8.x | ((uint64_t)R.sc8.y << 32);
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
-        const int r = rp + rr;
+        const int r = R.rp + rr;
 #pragma unroll
         for (int t = 0; t < 2; t++) {       /* 16 elements l = 16t..16t+15 of row-group r */
-            const int u = 4 * sb + 2 * n + t;
-            const uint4 ql = ldg_stream(tile + ((r & 1) ? 16 * U : 0) + 16 * u);
-            const uint4 qh = ldg_stream(tile + 32 * U + 16 * u);
-            const float ds = __fmul_rn(d, (float)sc[2 * r + t]);
+            const uint4 ql = R.ql[2 * rr + t], qh = R.qh[t];
+            const float ds = __fmul_rn(d, (float)(int8_t)((sc64 >> (8 * (2 * r + t))) & 0xFF));
             const uint32_t lw[4] = {ql.x, ql.y, ql.z, ql.w}, hw[4] = {qh.x, qh.y, qh.z, qh.w};
 #pragma unroll
             for (int c = 0; c < 2; c++) {
@@ -137,9 +164,9 @@ __device__ __forceinline__ void dq_block64_q6k(const uint8_t* tile, int U, int n
                     for (int e = 0; e < 2; e++) {
                         const int i = 8 * c + 2 * jj + e;                 /* byte index 0..15 */
                         const uint32_t lb = (lw[i >> 2] >> (8 * (i & 3))) & 0xFF, hb = (hw[i >> 2] >> (8 * (i & 3))) & 0xFF;
-                        const int lo = (r & 2) ? (lb >> 4) : (lb & 0xF);
-                        const int q = (lo | (((hb >> (2 * r)) & 3) << 4)) - 32;
-                        v[e] = __fmul_rn(ds, (float)q);
+                        const uint32_t lo = (r & 2) ? (lb >> 4) : (lb & 0xF);
+                        const uint32_t q6 = lo | (((hb >> (2 * r)) & 3) << 4);
+                        v[e] = __fmul_rn(ds, u2f_bias(q6, 8388640.0f));      /* (float)(q6 - 32), exactly */
                     }
                     pk[jj] = pack_bf16(v[0], v[1]);
                 }
@@ -149,21 +176,26 @@ __device__ __forceinline__ void dq_block64_q6k(const uint8_t* tile, int U, int n
     }
 }
 
-__device__ __forceinline__ void dq_unit_q8_0(const uint8_t* tile, int U, int u, Chunk8& o) {
-    const uint32_t dd = __ldg(reinterpret_cast<const uint32_t*>(tile + 64 * U + 4 * u));
+__device__ __forceinline__ void dq_fetch(Raw<GGB_TYPE_Q8_0>& R, const uint8_t* tile, int U, int nsb, int ek) {
+    const int u = ek >> 6;
+    R.dd = __ldg(reinterpret_cast<const uint32_t*>(tile + 64 * U + 4 * u));
+#pragma unroll
+    for (int i = 0; i < 4; i++) R.w[i] = ldg_stream(tile + i * 16 * U + 16 * u);
+}
+__device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q8_0>& R, Chunk8& o) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const uint4 q = ldg_stream(tile + i * 16 * U + 16 * u);
-        const float d = h2f((uint16_t)((i >> 1) ? (dd >> 16) : (dd & 0xFFFF)));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const float d = h2f((uint16_t)((i >> 1) ? (R.dd >> 16) : (R.dd & 0xFFFF)));
+        const uint32_t w[4] = {R.w[i].x, R.w[i].y, R.w[i].z, R.w[i].w};
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i0 = 8 * c + 2 * j;
-                const float a = __fmul_rn((float)(int8_t)((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xFF), d);
-                const float b = __fmul_rn((float)(int8_t)((w[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFF), d);
+                /* int8 -> float: flip the sign bit (value + 128 as unsigned), then subtract 2^23 + 128 (exact) */
+                const float a = __fmul_rn(u2f_bias(((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
+                const float b = __fmul_rn(u2f_bias(((w[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
                 pk[j] = pack_bf16(a, b);
             }
             o.c[2 * i + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -226,25 +258,30 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         };
         prefetch_tile(0);
         prefetch_tile(1);
+        const int r = pt & 127, hk = pt >> 7;                 /* A: thread -> (row, which 64-wide atom of the 128-wide K block) */
+        const int grow = row0 + r;
+        const bool arow = grow < rows;
+        Raw<TYPE> raw;
+        auto fetch_a = [&](int kb) {
+            const int k0 = kb * GM_BK + hk * 64;
+            const int t = k0 / GGB_TILE_ELEMS, ek = k0 - t * GGB_TILE_ELEMS;
+            const int nsb = ggb_tile_nsb(K, t);
+            dq_fetch(raw, W + (int64_t)grow * w_stride + (int64_t)t * tile_bytes, 4 * nsb, nsb, ek);
+        };
+        if (arow) fetch_a(0);
         gm_mbar_wait(gm_smem_u32(&bar_empty[0]), 1);           /* fresh barrier: returns at once */
         issue_b(0);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % GM_STAGES;
             uint8_t* sA = stage_base + s * GM_STAGE_BYTES;
-            // A: thread -> (row, 64-element half of the K block); stage s is free (waited for when B(kb) was issued)
+            // stage s is free (waited for when B(kb) was issued)
             {
-                const int r = pt & 127, hk = pt >> 7;         /* hk = which 64-wide atom of the 128-wide block */
-                const int k0 = kb * GM_BK + hk * 64;
                 if ((kb * GM_BK) % GGB_TILE_ELEMS == 0) prefetch_tile(kb * GM_BK / GGB_TILE_ELEMS + 2);
                 Chunk8 ch;
-                const int grow = row0 + r;
-                if (grow < rows) {
-                    const int t = k0 / GGB_TILE_ELEMS, ek = k0 - t * GGB_TILE_ELEMS;
-                    const int nsb = ggb_tile_nsb(K, t), U = 4 * nsb;
-                    const uint8_t* tile = W + (int64_t)grow * w_stride + (int64_t)t * tile_bytes;
-                    if (TYPE == GGB_TYPE_Q4_K) dq_unit_q4k(tile, U, ek >> 6, ch);
-                    else if (TYPE == GGB_TYPE_Q6_K) dq_block64_q6k(tile, U, nsb, ek >> 8, (ek >> 6) & 3, ch);
-                    else dq_unit_q8_0(tile, U, ek >> 6, ch);
+                if (arow) {
+                    const Raw<TYPE> cur = raw;
+                    if (kb + 1 < nkb) fetch_a(kb + 1);        /* next block's bytes are in flight while this one is converted */
+                    dq_convert(cur, ch);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; c++) ch.c[c] = make_uint4(0, 0, 0, 0);
@@ -269,7 +306,7 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         gm_mbar_wait(gm_smem_u32(&bar_acc), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, colh = warp >> 2;              /* TMEM lane quarter, column half */
-        const int grow = row0 + 32 * q + lane;
+        const int erow = row0 + 32 * q + lane;
 #pragma unroll 1
         for (int cb = 0; cb < 4; cb++) {                       /* 4 x 32 columns = this warp's 128 tokens */
             const int col = colh * 128 + cb * 32;
@@ -284,11 +321,11 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
                   "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (grow < rows) {
+            if (erow < rows) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int tk = tok0 + col + j;
-                    if (tk < tokens) Y[(int64_t)tk * y_stride + grow] = __uint_as_float(v[j]);
+                    if (tk < tokens) Y[(int64_t)tk * y_stride + erow] = __uint_as_float(v[j]);
                 }
             }
         }
