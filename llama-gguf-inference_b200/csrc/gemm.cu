@@ -278,9 +278,14 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
             {
                 if ((kb * GM_BK) % GGB_TILE_ELEMS == 0) prefetch_tile(kb * GM_BK / GGB_TILE_ELEMS + 2);
                 Chunk8 ch;
+                // Where the next block's packed bytes are requested is a measured choice per format: the loads of two
+                // iterations share a scoreboard, so requesting early makes the first use of the CURRENT bytes wait for the
+                // new loads too (ncu: stall_long_sb).  Q4_K (3 loads, short conversion) is better off requesting after the
+                // conversion; Q6_K / Q8_0 (long conversions) before it.
+                constexpr bool FETCH_EARLY = (TYPE != GGB_TYPE_Q4_K);
                 if (arow) {
                     const Raw<TYPE> cur = raw;
-                    if (kb + 1 < nkb) fetch_a(kb + 1);        /* next block's bytes are in flight while this one is converted */
+                    if (FETCH_EARLY && kb + 1 < nkb) fetch_a(kb + 1);
                     dq_convert(cur, ch);
                 } else {
 #pragma unroll
@@ -289,6 +294,7 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
                 uint8_t* atom = sA + hk * (GM_BM * 128);
 #pragma unroll
                 for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(atom + gm_sw(r, c)) = ch.c[c];
+                if (!FETCH_EARLY && arow && kb + 1 < nkb) fetch_a(kb + 1);
             }
             if (kb + 1 < nkb) {
                 const int s1 = (kb + 1) % GM_STAGES;

@@ -47,7 +47,10 @@ def test_llama_server_process_contract_and_parity(oracle, model_dir, tmp_path):
     port = free_port()
     argv = [os.path.join(ROOT, "bin", "llama-server"), "-m", path, "--host", "127.0.0.1", "--port", str(port), "-c", "256",
             "-ngl", "99", "--api-key-file", str(keyfile), "-t", "4", "--parallel", "2", "--temp", "0", "--ignore-eos"]
-    proc = subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # parity run: keep the prompt on the bit-exact integer path (prompts >= 64 tokens otherwise take the bf16 tensor-core
+    # prefill, whose logits agree with the reference only to tolerance -- tests/test_gpu_engine.py covers that path)
+    env = dict(os.environ, GGB_GEMM_PREFILL_MIN="1000000")
+    proc = subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     try:
         ok = False
         for _ in range(120):                    # start.sh polls /health for ~30 s; 503 while loading, then 200
