@@ -69,25 +69,35 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     }
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
 
-    // ---- pass 1: scores of my slice + slice maximum
+    // ---- pass 1: scores of my slice + slice maximum.  AU positions per lane group are in flight at once (the loop is
+    // a chain of L2 round trips otherwise: one 16-byte load, then its dependent arithmetic)
+    constexpr int AU = 4;
     float mx = -INFINITY;
-    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += SLOTS) {
-        const int p = p0 + sub;
-        const bool live = p < p_end;
-        const uint4 kraw = *reinterpret_cast<const uint4*>(kc + (live ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
-        const uint32_t kw[4] = {kraw.x, kraw.y, kraw.z, kraw.w};
-        double s = 0.0;
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        uint4 kraw[AU];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            s += (double)__fmul_rn(h2f((uint16_t)(kw[i] & 0xFFFF)), qr[2 * i]);      // exact products
-            s += (double)__fmul_rn(h2f((uint16_t)(kw[i] >> 16)), qr[2 * i + 1]);
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            kraw[u] = *reinterpret_cast<const uint4*>(kc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
         }
 #pragma unroll
-        for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float sf = __fmul_rn((float)s, scale);
-        if (live) {
-            if (li == 0) s_scores[p - p_begin] = sf;
-            mx = fmaxf(mx, sf);
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            const bool live = p < p_end;
+            const uint32_t kw[4] = {kraw[u].x, kraw[u].y, kraw[u].z, kraw[u].w};
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                s += (double)__fmul_rn(h2f((uint16_t)(kw[i] & 0xFFFF)), qr[2 * i]);      // exact products
+                s += (double)__fmul_rn(h2f((uint16_t)(kw[i] >> 16)), qr[2 * i + 1]);
+            }
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float sf = __fmul_rn((float)s, scale);
+            if (live) {
+                if (li == 0) s_scores[p - p_begin] = sf;
+                mx = fmaxf(mx, sf);
+            }
         }
     }
     mx = warp_max(mx);
@@ -108,17 +118,25 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     double acc[8], sum = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0;
-    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += SLOTS) {
-        const int p = p0 + sub;
-        if (p < p_end) {
-            const float e = exp_ref(__fsub_rn(s_scores[p - p_begin], M));
-            const uint4 vraw = *reinterpret_cast<const uint4*>(vc + p * kv_stride + (int64_t)kvh * HD + li * 8);
-            const uint32_t vw[4] = {vraw.x, vraw.y, vraw.z, vraw.w};
-            sum += (double)e;
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        uint4 vraw[AU];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                acc[2 * i] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] & 0xFFFF)));
-                acc[2 * i + 1] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] >> 16)));
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            vraw[u] = *reinterpret_cast<const uint4*>(vc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            if (p < p_end) {
+                const float e = exp_ref(__fsub_rn(s_scores[p - p_begin], M));
+                const uint32_t vw[4] = {vraw[u].x, vraw[u].y, vraw[u].z, vraw[u].w};
+                sum += (double)e;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    acc[2 * i] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] & 0xFFFF)));
+                    acc[2 * i + 1] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] >> 16)));
+                }
             }
         }
     }
