@@ -300,48 +300,8 @@ class Slot:
         self.reset()
 
     def _prefill_gemm(self, tokens: list[int], start: int):
-        """Many tokens at once: tcgen05 dequant-GEMMs + batched attention (csrc/gemm.cu, csrc/prefill.cu).  The last
-        token's hidden state then goes through the decode head (arg-max, next embedding), like the GEMV path."""
-        torch, lib, hp, e = self.torch, self.lib, self.hp, self.eng
-        T = len(tokens)
-        B = e.prefill_buffers(T)
-        s = self.stream.cuda_stream
-        qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
-
-        def gemm(w, xb, y):
-            cabi.check(lib.ggb_gemm(w.type, w.ptr, w.rows, w.k, xb.data_ptr(), T, y.data_ptr(), w.rows, s), "gemm")
-
-        def to_bf16(x, n):
-            cabi.check(lib.ggb_f32_to_bf16(x.data_ptr(), B["xb"].data_ptr(), n, s), "f32_to_bf16")
-
-        with torch.cuda.stream(self.stream):
-            ids = torch.tensor(tokens, dtype=torch.int32).to(e.dev)
-            X, XN, Y = B["x"], B["xn"], B["y"]
-            cabi.check(lib.ggb_embed_rows(e.emb_type, e.emb_canon.data_ptr(), hp.d, ids.data_ptr(), T, X.data_ptr(), s), "embed_rows")
-            for i, L in enumerate(e.layers):
-                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["attn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_bf16(XN, T * hp.d)
-                gemm(L["wq"], B["xb"], B["q"]); gemm(L["wk"], B["xb"], B["k"]); gemm(L["wv"], B["xb"], B["v"])
-                cabi.check(lib.ggb_rope_kv_prefill(B["q"].data_ptr(), B["k"].data_ptr(), B["v"].data_ptr(), T, start, hp.n_head, hp.n_kv,
-                                                   hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), s), "rope_kv_prefill")
-                cabi.check(lib.ggb_attn_prefill(B["q"].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), T, start, hp.n_head, hp.n_kv,
-                                                hp.head_dim, B["att"].data_ptr(), s), "attn_prefill")
-                to_bf16(B["att"], T * qd)
-                gemm(L["wo"], B["xb"], Y)
-                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
-                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["ffn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_bf16(XN, T * hp.d)
-                gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
-                cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
-                to_bf16(B["gate"], T * hp.ff)
-                gemm(L["wd"], B["xb"], Y)
-                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
-            self.x.copy_(X[(T - 1) * hp.d:T * hp.d], non_blocking=True)
-            self._set_tok_pos(int(tokens[-1]), start + T - 1)
-            self._enqueue_head(s)
-            self.stream.synchronize()
-        self.n_past = start + T
-        self.chain_valid = True
+        """Many tokens at once: tcgen05 dequant-GEMMs + tensor-core attention (Engine.prefill_many with one job)."""
+        self.eng.prefill_many([(self.index, tokens, start)])
 
     def prefill(self, tokens: list[int], start_pos: int | None = None):
         """Feed tokens at positions start_pos.. (default: append).  Long prompts go through the tcgen05 GEMM path
@@ -569,6 +529,74 @@ class Engine:
         if "rope_freqs.weight" in f.tensors:
             ff = self._load_f32("rope_freqs.weight").cpu().numpy()
         self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
+
+    def prefill_many(self, jobs):
+        """jobs = [(slot index, tokens, start position)]: the prompt chunks of SEVERAL sequences in one pass through the
+        tcgen05 dequant-GEMMs (csrc/gemm.cu) -- the GEMMs, norms and element-wise ops run on the concatenated tokens, RoPE
+        and the KV write take per-token (slot, position), attention runs per sequence (csrc/prefill.cu).  Each sequence's
+        last hidden state then goes through the decode head (arg-max, next embedding), like the GEMV path."""
+        torch, lib, hp = self.torch, self.lib, self.hp
+        if self.tp_size != 1:
+            raise cabi.GGBError("the GEMM prefill path is single-GPU")
+        T = sum(len(j[1]) for j in jobs)
+        if T == 0 or T > self.prefill_chunk:
+            raise ValueError(f"prefill_many: {T} tokens (1..{self.prefill_chunk})")
+        for sl, toks, start in jobs:
+            if start + len(toks) >= self.n_ctx or not toks:
+                raise ValueError("prompt does not fit the context")
+        B = self.prefill_buffers(T)
+        s = self.stream.cuda_stream
+        qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
+        slot_stride = hp.n_layer * self.n_ctx * kvd
+
+        def gemm(w, xb, y):
+            cabi.check(lib.ggb_gemm(w.type, w.ptr, w.rows, w.k, xb.data_ptr(), T, y.data_ptr(), w.rows, s), "gemm")
+
+        def to_bf16(x, n):
+            cabi.check(lib.ggb_f32_to_bf16(x.data_ptr(), B["xb"].data_ptr(), n, s), "f32_to_bf16")
+
+        ids, pos, slots = [], [], []
+        for sl, toks, start in jobs:
+            ids += [int(t) for t in toks]
+            pos += list(range(start, start + len(toks)))
+            slots += [sl] * len(toks)
+        with torch.cuda.stream(self.stream):
+            meta = torch.tensor([ids, pos, slots], dtype=torch.int32).to(self.dev)
+            X, XN, Y = B["x"], B["xn"], B["y"]
+            cabi.check(lib.ggb_embed_rows(self.emb_type, self.emb_canon.data_ptr(), hp.d, meta[0].data_ptr(), T, X.data_ptr(), s), "embed_rows")
+            for i, L in enumerate(self.layers):
+                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["attn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
+                to_bf16(XN, T * hp.d)
+                gemm(L["wq"], B["xb"], B["q"]); gemm(L["wk"], B["xb"], B["k"]); gemm(L["wv"], B["xb"], B["v"])
+                cabi.check(lib.ggb_rope_kv_batch(B["q"].data_ptr(), B["k"].data_ptr(), B["v"].data_ptr(), T, meta[1].data_ptr(), meta[2].data_ptr(),
+                                                 slot_stride, hp.n_head, hp.n_kv, hp.head_dim, hp.n_rot, self.rope_tab.data_ptr(),
+                                                 self.k_all[0, i].data_ptr(), self.v_all[0, i].data_ptr(), s), "rope_kv_batch")
+                off = 0
+                for sl, toks, start in jobs:
+                    cabi.check(lib.ggb_attn_prefill(B["q"].data_ptr() + off * qd * 4, self.k_all[sl, i].data_ptr(), self.v_all[sl, i].data_ptr(),
+                                                    len(toks), start, hp.n_head, hp.n_kv, hp.head_dim, B["att"].data_ptr() + off * qd * 4, s), "attn_prefill")
+                    off += len(toks)
+                to_bf16(B["att"], T * qd)
+                gemm(L["wo"], B["xb"], Y)
+                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
+                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["ffn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
+                to_bf16(XN, T * hp.d)
+                gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
+                cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
+                to_bf16(B["gate"], T * hp.ff)
+                gemm(L["wd"], B["xb"], Y)
+                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
+            off = 0
+            for sl, toks, start in jobs:
+                slot = self.slots[sl]
+                off += len(toks)
+                slot.x.copy_(X[(off - 1) * hp.d:off * hp.d], non_blocking=True)
+                slot._set_tok_pos(int(toks[-1]), start + len(toks) - 1)
+                slot._enqueue_head(s)
+            self.stream.synchronize()
+        for sl, toks, start in jobs:
+            self.slots[sl].n_past = start + len(toks)
+            self.slots[sl].chain_valid = True
 
     def prefill_buffers(self, T: int) -> dict:
         """activation buffers of the GEMM prefill path, sized for the largest chunk seen so far (shared by the slots)"""

@@ -115,11 +115,13 @@ class Scheduler(threading.Thread):
                         self.cv.wait()
                     if self.stop_flag:
                         break
+                    fresh = []
                     while self.pending and len(self.active) < len(self.engine.slots):
                         req = self.pending.popleft()
                         free = next(i for i in range(len(self.engine.slots)) if i not in self.active)
                         self.active[free] = _Active(req, self.engine.slots[free], self.tok)
-                        self._start(free)
+                        fresh.append(free)
+                self._start_many(fresh)
                 live = list(self.active)
                 if len(live) >= 2 and getattr(self.engine, "batch_capable", False):
                     self._step_batch(live)
@@ -137,7 +139,40 @@ class Scheduler(threading.Thread):
                 self.pending.clear()
             raise
 
-    def _start(self, i: int):
+    def _start_many(self, fresh: list[int]):
+        """Requests admitted in the same scheduling round: prompts long enough for the tensor-core prefill are
+        processed TOGETHER (one pass of GEMMs over the concatenated tokens, Engine.prefill_many), the rest one by one."""
+        many = getattr(self.engine, "prefill_many", None)
+        group, group_tokens = [], 0
+        limit = getattr(self.engine, "prefill_chunk", 0)
+        floor = getattr(self.engine, "gemm_prefill_min", 1 << 30)
+
+        def flush():
+            nonlocal group, group_tokens
+            if len(group) > 1:
+                for i in group:
+                    self.active[i].slot.reset()
+                many([(self.active[i].slot.index, self.active[i].req.prompt_ids, 0) for i in group])
+                for i in group:
+                    self._start(i, prefilled=True)
+            else:
+                for i in group:
+                    self._start(i)
+            group, group_tokens = [], 0
+
+        for i in fresh:
+            a = self.active[i]
+            n = len(a.req.prompt_ids)
+            if many is None or n < floor or n + 1 >= a.slot.n_ctx or n > limit:
+                self._start(i)
+                continue
+            if group_tokens + n > limit:
+                flush()
+            group.append(i)
+            group_tokens += n
+        flush()
+
+    def _start(self, i: int, prefilled: bool = False):
         a = self.active[i]
         req, slot = a.req, a.slot
         n_ctx = slot.n_ctx
@@ -146,8 +181,9 @@ class Scheduler(threading.Thread):
             del self.active[i]
             return
         req.max_tokens = max(0, min(req.max_tokens, n_ctx - len(req.prompt_ids) - 1))
-        slot.reset()
-        slot.prefill(req.prompt_ids)
+        if not prefilled:
+            slot.reset()
+            slot.prefill(req.prompt_ids)
         self.stats["requests"] += 1
         self.stats["prompt_tokens"] += len(req.prompt_ids)
         a.t_decode0 = time.time()

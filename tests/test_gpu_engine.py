@@ -247,3 +247,46 @@ def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
     nxt = eng.batch.step([(2, toks[-1], len(toks) - 1)])
     assert nxt == [oracle.OracleLlama(path, n_ctx=64, mode="canon").greedy(toks, 1)[0]]
     eng.close()
+
+
+@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K")])
+def test_persistent_per_token_kernel_is_bit_identical(oracle, model_dir, preset, ftype, monkeypatch):
+    """csrc/mega.cu (GGB_MEGA=1): all phases of a token in one cooperative launch, grid barriers instead of kernel
+    boundaries, rings prefetching across phases -- same tokens, same logits as the oracle / the multi-kernel graph."""
+    path = _model(model_dir, preset, ftype)
+    n_new = 24
+    monkeypatch.setenv("GGB_MEGA", "1")
+    toks, logits = _gpu_run(path, n_new)
+    ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")
+    ref_toks, ref_logits = ref.greedy(PROMPT, n_new, return_logits=True)
+    assert toks == ref_toks
+    for got, want in zip(logits, ref_logits):
+        assert np.array_equal(_bits(got), _bits(want))
+
+
+def test_multi_sequence_gemm_prefill_equals_per_sequence_prefill(oracle, model_dir):
+    """Engine.prefill_many: the prompts of several requests in ONE pass of tensor-core GEMMs (per-token slot/position for
+    RoPE and the KV write, attention per sequence) must leave every slot where its own prefill would."""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "medium", "Q4_K_M")
+    eng = Engine(path, n_ctx=256, n_slots=3)
+    eng.warmup()
+    eng.gemm_prefill_min = 16
+    rng = np.random.default_rng(9)
+    prompts = [[1] + [int(t) for t in rng.integers(300, 2000, n)] for n in (40, 97, 23)]
+    single = []
+    for p in prompts:                              # each alone on slot 0
+        sl = eng.slots[0]
+        sl.reset(); sl.prefill(p); sl.decode(7)
+        single.append((sl.tokens(8), sl.last_logits().copy()))
+    for sl in eng.slots:
+        sl.reset()
+    eng.prefill_many([(i, p, 0) for i, p in enumerate(prompts)])
+    for i, p in enumerate(prompts):
+        sl = eng.slots[i]
+        assert sl.n_past == len(p)
+        sl.decode(7)
+        assert sl.tokens(8) == single[i][0], f"sequence {i}"
+        ref = single[i][1]
+        assert np.abs(sl.last_logits() - ref).max() <= 1e-4 * np.abs(ref).max()
+    eng.close()
