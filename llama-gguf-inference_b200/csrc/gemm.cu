@@ -86,6 +86,7 @@ struct Chunk8 { uint4 c[8]; };
 // HBM latency hides behind the conversion of the current block) and "convert them to 8 chunks of 8 bf16".
 template <int TYPE> struct Raw;
 template <> struct Raw<GGB_TYPE_Q4_K> { uint4 q0, q1, h; int g; };
+template <> struct Raw<GGB_TYPE_Q5_K> { uint4 q0, q1, h; uint2 qhu; int g; };
 template <> struct Raw<GGB_TYPE_Q6_K> { uint4 ql[4], qh[2]; uint2 sc8; uint32_t d16; int rp; };
 template <> struct Raw<GGB_TYPE_Q8_0> { uint4 w[4]; uint32_t dd; };
 
@@ -122,6 +123,48 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q4_K>& R, Chunk8& 
                 const uint32_t word = w[2 * c + (j >> 1)];
                 const uint32_t b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
                 const uint32_t b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
+                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
+            }
+            o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    }
+}
+
+// Q5_K: Q4_K plus the fifth bits (QHU[u]: bit l of word 0 / 1 = element l of sub-block 2g / 2g+1)
+__device__ __forceinline__ void dq_fetch(Raw<GGB_TYPE_Q5_K>& R, const uint8_t* tile, int U, int nsb, int ek) {
+    const int u = ek >> 6;
+    R.q0 = ldg_stream(tile + 16 * u);
+    R.q1 = ldg_stream(tile + 16 * U + 16 * u);
+    R.qhu = __ldg(reinterpret_cast<const uint2*>(tile + 32 * U + 8 * u));
+    R.h = ldg_cached(tile + 40 * U + 16 * (u >> 2));
+    R.g = u & 3;
+}
+__device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q5_K>& R, Chunk8& o) {
+    int s0, m0, s1, m1;
+    {
+        const uint32_t hw[4] = {R.h.x, R.h.y, R.h.z, R.h.w};
+        const int bo = 4 + 3 * R.g;
+        const uint64_t two = (uint64_t)hw[bo >> 2] | ((uint64_t)hw[min((bo >> 2) + 1, 3)] << 32);
+        const uint32_t f = (uint32_t)(two >> (8 * (bo & 3))) & 0xFFFFFFu;
+        s0 = f & 63; s1 = (f >> 6) & 63; m0 = (f >> 12) & 63; m1 = (f >> 18) & 63;
+    }
+    const float d = h2f((uint16_t)(R.h.x & 0xFFFF)), dmin = h2f((uint16_t)(R.h.x >> 16));
+    const float d0 = __fmul_rn(d, (float)s0), d1 = __fmul_rn(d, (float)s1);
+    const float n0 = __fmul_rn(dmin, (float)m0), n1 = __fmul_rn(dmin, (float)m1);
+    const uint32_t w[8] = {R.q0.x, R.q0.y, R.q0.z, R.q0.w, R.q1.x, R.q1.y, R.q1.z, R.q1.w};
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const float dd = half ? d1 : d0, nn = half ? n1 : n0;
+        const uint32_t bits = half ? R.qhu.y : R.qhu.x;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {       /* elements 8c..8c+7 of the sub-block */
+            uint32_t r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t word = w[2 * c + (j >> 1)];
+                const int e0 = 8 * c + 2 * j;
+                const uint32_t b0 = ((word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF) | (((bits >> e0) & 1) << 4);
+                const uint32_t b1 = ((word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF) | (((bits >> (e0 + 1)) & 1) << 4);
                 r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
             }
             o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
@@ -413,6 +456,7 @@ extern "C" int ggb_gemm(int type, const void* w, int rows, int k, const void* x_
     cudaStream_t st = (cudaStream_t)stream;
     switch (type) {
         case GGB_TYPE_Q4_K: return launch_gemm<GGB_TYPE_Q4_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q5_K: return launch_gemm<GGB_TYPE_Q5_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
         case GGB_TYPE_Q6_K: return launch_gemm<GGB_TYPE_Q6_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
         case GGB_TYPE_Q8_0: return launch_gemm<GGB_TYPE_Q8_0>(w, rows, k, x_bf16, tokens, y, y_stride, st);
         default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemm: unsupported weight type %d", type);

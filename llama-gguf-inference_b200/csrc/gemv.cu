@@ -99,7 +99,7 @@ __device__ __forceinline__ void argmax_comb(float& v, int& i, float ov, int oi) 
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
-// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0 segments present (dead-code elimination per launch shape)
+// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0, bit3 Q5_K segments present (dead-code elimination per launch shape)
 template <int MASK, int R, int STEPS>
 __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const __grid_constant__ GemvK P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -488,6 +488,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
             case GGB_TYPE_Q4_K: bit = 1; break;
             case GGB_TYPE_Q6_K: bit = 2; break;
             case GGB_TYPE_Q8_0: bit = 4; break;
+            case GGB_TYPE_Q5_K: bit = 8; break;
             default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: segment %d has unsupported weight type %d", s, g.type);
         }
         if (cls >= 0 && cls != act_class(g.type)) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: Q8_0 and K-quant segments cannot share a launch");
@@ -543,7 +544,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     for (int p = 0; p < GGB_PEER_MAX; p++) P.peer_base[p] = a->peer_base[p];
     // ring geometry: RING_SLOTS slots sized for the largest tile of the launch
     P.slot_bytes = (max_tile + 15) & ~15;
-    const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;
+    const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;   /* any mix with Q5_K: generic R=2, STEPS=2 */
     P.n_slots = R * STEPS;
     P.ring_bytes = P.n_slots * P.slot_bytes;
 #ifdef GGB_TIMELINE
@@ -564,6 +565,8 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
         case 2: return launch<2, 4, 2>(P, grid, smem, a->use_pdl, st);
         case 3: return launch<3, 2, 3>(P, grid, smem, a->use_pdl, st);
         case 4: return launch<4, 2, 2>(P, grid, smem, a->use_pdl, st);
-        default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: unsupported type mix (mask %d)", mask);
+        default:
+            if ((mask & 8) && !(mask & 4)) return launch<11, 2, 2>(P, grid, smem, a->use_pdl, st);   /* Q5_K alone or mixed with Q4_K / Q6_K */
+            GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: unsupported type mix (mask %d)", mask);
     }
 }

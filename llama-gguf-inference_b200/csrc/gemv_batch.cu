@@ -67,6 +67,16 @@ __device__ __forceinline__ W4 prep_q4k(uint4 q0, uint4 q1, uint4 hdr, const Lane
     w.d = h2f((uint16_t)(hdr.x & 0xFFFF)); w.dmin = h2f((uint16_t)(hdr.x >> 16));
     return w;
 }
+// Q5_K: the 5-bit codes as bytes (q5k_codes, gemv_common.cuh); from there on it is a Q4_K unit
+__device__ __forceinline__ W4 prep_q5k(uint4 q0, uint4 q1, uint2 qhu, uint4 hdr, const LaneK& L) {
+    W4 w;
+    q5k_codes(q0, q1, qhu, w.q0l, w.q1l, w.q0h, w.q1h);
+    const uint32_t fa = __byte_perm(hdr.y, hdr.z, L.selA), fb = __byte_perm(hdr.z, hdr.w, L.selB);
+    const uint32_t f = L.lowg ? fa : fb;
+    w.sc0 = (int)(f & 63); w.sc1 = (int)((f >> 6) & 63); w.m0 = (int)((f >> 12) & 63); w.m1 = (int)((f >> 18) & 63);
+    w.d = h2f((uint16_t)(hdr.x & 0xFFFF)); w.dmin = h2f((uint16_t)(hdr.x >> 16));
+    return w;
+}
 // same integers and the same f32 operation order as term_q4k (gemv_common.cuh)
 __device__ __forceinline__ float term_q4k_w(const W4& w, const Act& A) {
     const int dlo = dot16_us(w.q0l, A.a0) + dot16_us(w.q1l, A.a1);
@@ -128,7 +138,7 @@ __device__ __forceinline__ void warp_reduce_many(double (&v)[N], int lane) {
         if (o <= off) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
 }
 
-// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0 segments present; NBT = tokens per launch (compile-time upper bound, the
+// MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0, bit3 Q5_K segments present; NBT = tokens per launch (compile-time upper bound, the
 // images of tokens >= nb are zero-filled by the prologue)
 template <int MASK, int NBT, int R>
 __global__ void __launch_bounds__(GB_THREADS, 1) gemv_batch_kernel(const __grid_constant__ GemvBK P) {
@@ -278,6 +288,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gemv_batch_kernel(const __grid_
                         const Act A = load_act<MASK>(GGB_TYPE_Q6_K, gu, qb, qb + bs_off, qb + dsc_off);
 #pragma unroll
                         for (int r = 0; r < R; r++) acc[r * NBT + b] += (double)term_q6k_w(w[r], A);
+                    }
+                } else if ((MASK & 8) && type == GGB_TYPE_Q5_K) {
+                    W4 w[R];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const uint32_t sl = slot0 + r * SLOT;
+                        w[r] = prep_q5k(lds128(sl + L.o_q), lds128(sl + L.o_q + S), lds64(sl + 2 * S + 8u * (uint32_t)lane),
+                                        lds128(sl + L.o_h + 2 * S + S / 2), L);
+                    }
+#pragma unroll
+                    for (int b = 0; b < NBT; b++) {
+                        const uint32_t qb = act_s + b * P.image;
+                        const Act A = load_act<MASK>(GGB_TYPE_Q5_K, gu, qb, qb + bs_off, qb + dsc_off);
+#pragma unroll
+                        for (int r = 0; r < R; r++) acc[r * NBT + b] += (double)term_q4k_w(w[r], A);
                     }
                 } else if (MASK & 4) {
                     W8 w[R];
@@ -492,6 +517,7 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
             case GGB_TYPE_Q4_K: bit = 1; break;
             case GGB_TYPE_Q6_K: bit = 2; break;
             case GGB_TYPE_Q8_0: bit = 4; break;
+            case GGB_TYPE_Q5_K: bit = 8; break;
             default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: segment %d has unsupported weight type %d", s, g.type);
         }
         const int c = g.type == GGB_TYPE_Q8_0 ? 1 : 0;
@@ -522,7 +548,8 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
         default: GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: epilogue %d is not available in the batched kernel (STORE, RESIDUAL, SWIGLU)", a->epilogue);
     }
     if (total_rows == 0 || a->nb == 0) return GGB_OK;
-    if (mask != 1 && mask != 2 && mask != 3 && mask != 4) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: unsupported type mix (mask %d)", mask);
+    if (mask & 8) { if (mask & 4) mask = 0; else mask = 11; }   /* any mix with Q5_K runs the generic K-quant kernel */
+    if (mask != 1 && mask != 2 && mask != 3 && mask != 4 && mask != 11) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: unsupported type mix (mask %d)", mask);
     P.n_seg = a->n_seg; P.k = a->k; P.T = ggb_tiles_per_row(a->k);
     P.epi = a->epilogue; P.residual = a->residual;
     P.slot_bytes = (max_tile + 15) & ~15;
@@ -559,6 +586,7 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
             case 1: rc = launch_nbt<1>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
             case 2: rc = launch_nbt<2>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
             case 3: rc = launch_nbt<3>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
+            case 11: rc = launch_nbt<11>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
             default: rc = launch_nbt<4>(nbt, R, Q, grid, smem, a->use_pdl, st); break;
         }
         if (rc) return rc;

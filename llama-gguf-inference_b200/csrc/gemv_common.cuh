@@ -139,6 +139,34 @@ __device__ __forceinline__ float term_q4k(uint4 q0, uint4 q1, uint4 hdr, const A
     return __fsub_rn(__fmul_rn(__fmul_rn(d, A.dx0), (float)isum), __fmul_rn(__fmul_rn(dmin, A.dx0), (float)msum));
 }
 
+// Q5_K unit: Q4_K's layout plus one "fifth bit" per element (QHU[u] = two u32, bit l = element l of sub-blocks 2g / 2g+1).
+// The 5-bit codes are assembled as bytes (nibble | bit << 4; four bits are spread to four bytes with one multiply), then
+// the arithmetic is term_q4k's (oracle: vec_dot_q5_K_q8_K_f64).
+__device__ __forceinline__ uint32_t spread5(uint32_t bits, int sh) { return (((bits >> sh) & 0xFu) * 0x02040810u) & 0x10101010u; }
+__device__ __forceinline__ void q5k_codes(uint4 q0, uint4 q1, uint2 qhu, uint4& l0, uint4& l1, uint4& h0, uint4& h1) {
+    const uint32_t bl = qhu.x, bh = qhu.y;
+    l0 = make_uint4((q0.x & 0x0F0F0F0Fu) | spread5(bl, 0), (q0.y & 0x0F0F0F0Fu) | spread5(bl, 4),
+                    (q0.z & 0x0F0F0F0Fu) | spread5(bl, 8), (q0.w & 0x0F0F0F0Fu) | spread5(bl, 12));
+    l1 = make_uint4((q1.x & 0x0F0F0F0Fu) | spread5(bl, 16), (q1.y & 0x0F0F0F0Fu) | spread5(bl, 20),
+                    (q1.z & 0x0F0F0F0Fu) | spread5(bl, 24), (q1.w & 0x0F0F0F0Fu) | spread5(bl, 28));
+    h0 = make_uint4(((q0.x >> 4) & 0x0F0F0F0Fu) | spread5(bh, 0), ((q0.y >> 4) & 0x0F0F0F0Fu) | spread5(bh, 4),
+                    ((q0.z >> 4) & 0x0F0F0F0Fu) | spread5(bh, 8), ((q0.w >> 4) & 0x0F0F0F0Fu) | spread5(bh, 12));
+    h1 = make_uint4(((q1.x >> 4) & 0x0F0F0F0Fu) | spread5(bh, 16), ((q1.y >> 4) & 0x0F0F0F0Fu) | spread5(bh, 20),
+                    ((q1.z >> 4) & 0x0F0F0F0Fu) | spread5(bh, 24), ((q1.w >> 4) & 0x0F0F0F0Fu) | spread5(bh, 28));
+}
+__device__ __forceinline__ float term_q5k(uint4 q0, uint4 q1, uint2 qhu, uint4 hdr, const Act& A, const LaneK& L) {
+    uint4 l0, l1, h0, h1;
+    q5k_codes(q0, q1, qhu, l0, l1, h0, h1);
+    const int dlo = dot16_us(l0, A.a0) + dot16_us(l1, A.a1);
+    const int dhi = dot16_us(h0, A.a2) + dot16_us(h1, A.a3);
+    const uint32_t fa = __byte_perm(hdr.y, hdr.z, L.selA), fb = __byte_perm(hdr.z, hdr.w, L.selB);
+    const uint32_t f = L.lowg ? fa : fb;
+    const int isum = (int)(f & 63) * dlo + (int)((f >> 6) & 63) * dhi;
+    const int msum = (int)((f >> 12) & 63) * A.b0 + (int)((f >> 18) & 63) * A.b1;
+    const float d = h2f((uint16_t)(hdr.x & 0xFFFF)), dmin = h2f((uint16_t)(hdr.x >> 16));
+    return __fsub_rn(__fmul_rn(__fmul_rn(d, A.dx0), (float)isum), __fmul_rn(__fmul_rn(dmin, A.dx0), (float)msum));
+}
+
 // Q6_K unit (half n, column t): elements 128n + 32r + 16t + (0..15), r = 0..3; sc8 = the 8 scales of half n
 __device__ __forceinline__ float term_q6k(uint4 qla, uint4 qlb, uint4 qh, uint2 sc8, uint32_t dbits, const Act& A, int tt) {
     // sum (q-32)*a over a 16-group = nibble dot + 16*(2-bit dot) - 32*sum(a); masked bytes keep their position,
@@ -171,6 +199,12 @@ __device__ __forceinline__ double consume(int type, uint32_t slot, int lane, int
         const uint2 sc = lds64(slot + L.o_sc + 3 * S);
         const uint32_t db = lds16(slot + L.o_d + 3 * S + (FULL ? 128u : 16u * (uint32_t)nsb));
         return (double)term_q6k(qla, qlb, qh, sc, db, A, lane & 1);
+    } else if ((MASK & 8) && type == GGB_TYPE_Q5_K) {
+        const uint4 q0 = lds128(slot + L.o_q);
+        const uint4 q1 = lds128(slot + L.o_q + S);
+        const uint2 qhu = lds64(slot + 2 * S + 8u * (uint32_t)lane);
+        const uint4 hd = lds128(slot + L.o_h + 2 * S + S / 2);
+        return (double)term_q5k(q0, q1, qhu, hd, A, L);
     } else if (MASK & 4) {
         const uint4 w0 = lds128(slot + L.o_q);
         const uint4 w1 = lds128(slot + L.o_q + S);

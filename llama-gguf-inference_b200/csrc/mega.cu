@@ -508,7 +508,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------ host side
-static int mg_bit(int type) { return type == GGB_TYPE_Q4_K ? 1 : (type == GGB_TYPE_Q6_K ? 2 : (type == GGB_TYPE_Q8_0 ? 4 : 0)); }
+static int mg_bit(int type) {
+    return type == GGB_TYPE_Q4_K ? 1 : (type == GGB_TYPE_Q6_K ? 2 : (type == GGB_TYPE_Q8_0 ? 4 : (type == GGB_TYPE_Q5_K ? 8 : 0)));
+}
 
 extern "C" int64_t ggb_mega_plan_bytes(int n_phases) { return n_phases > 0 ? (int64_t)n_phases * (int64_t)sizeof(MgPhase) : -1; }
 
@@ -604,6 +606,8 @@ extern "C" int ggb_mega_run(const ggb_mega_args* a, void* stream) {
     switch (a->type_mask) {
         case 1: case 2: case 3: return mg_launch<3>(M, smem, st);
         case 4: return mg_launch<4>(M, smem, st);
-        default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_mega_run: unsupported weight type mix (mask %d)", a->type_mask);
+        default:
+            if ((a->type_mask & 8) && !(a->type_mask & 4)) return mg_launch<11>(M, smem, st);
+            GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_mega_run: unsupported weight type mix (mask %d)", a->type_mask);
     }
 }

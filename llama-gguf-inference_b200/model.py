@@ -26,7 +26,7 @@ from . import cabi
 from . import gguf_reader as G
 from . import parallel
 
-QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q6_K, G.GGML_Q8_0)
+QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q5_K, G.GGML_Q6_K, G.GGML_Q8_0)
 
 
 @dataclass
@@ -474,7 +474,7 @@ class Engine:
         torch = self.torch
         ti = self.file.tensors[name]
         if ti.ggml_type not in QUANT_TYPES:
-            raise G.GGUFError(f"{name}: tensor type {ti.type_name} is not supported by the GEMV path (supported: Q4_K, Q6_K, Q8_0)")
+            raise G.GGUFError(f"{name}: tensor type {ti.type_name} is not supported by the GEMV path (supported: Q4_K, Q5_K, Q6_K, Q8_0)")
         k, rows = ti.ne[0], ti.ne[1]
         if k % 256:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")

@@ -85,7 +85,7 @@ def _batch_gemv(segs, k, act, nb, **kw):
     return [y.cpu().numpy()[:nb * r].reshape(nb, r) for y, (_, _, r) in zip(ys, segs)]
 
 
-@pytest.mark.parametrize("name,qt", [("q8_0", 8), ("q4_k", 12), ("q6_k", 14)])
+@pytest.mark.parametrize("name,qt", [("q8_0", 8), ("q4_k", 12), ("q5_k", 13), ("q6_k", 14)])
 @pytest.mark.parametrize("rows,k,nb", [(1, 256, 1), (7, 512, 2), (300, 2048, 3), (64, 5632, 5), (1000, 4096, 8), (300, 14336, 11),
                                        (2048, 4096, 16)])
 def test_gemv_batch_store_matches_oracle(oracle, name, qt, rows, k, nb):
@@ -106,14 +106,14 @@ def test_gemv_batch_store_matches_oracle(oracle, name, qt, rows, k, nb):
 
 
 def test_gemv_batch_mixed_segments_rmsnorm(oracle):
-    """the QKV launch of a Q4_K_M file: q/k Q4_K + v Q6_K sharing rms-normed inputs, 6 tokens"""
+    """three formats in one launch (Q4_K | Q5_K | Q6_K: the generic K-quant kernel) sharing rms-normed inputs, 6 tokens"""
     import gpu_util as U
     k, nb, eps = 4096, 6, 1e-5
     rng = np.random.default_rng(71)
     x = (rng.standard_normal((nb, k)) * 3).astype(np.float32)
     g = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
     segs, raws = [], []
-    for qt, rows in ((12, 1024), (12, 256), (14, 256)):
+    for qt, rows in ((12, 1024), (13, 256), (14, 256)):
         raw = rand_blocks(qt, rows * k // 256, rng)
         raws.append((qt, raw, rows))
         segs.append((U.gpu_repack(qt, raw, rows, k), qt, rows))

@@ -56,7 +56,7 @@ def _gpu_run(path, n_new, n_ctx=256, **kw):
     return toks, logits
 
 
-@pytest.mark.parametrize("preset,ftype", [("tiny", "Q4_K_M"), ("tiny", "Q8_0"), ("tiny", "Q6_K"), ("small", "Q4_K_M"),
+@pytest.mark.parametrize("preset,ftype", [("tiny", "Q4_K_M"), ("tiny", "Q8_0"), ("tiny", "Q6_K"), ("small", "Q4_K_M"), ("small", "Q5_K_M"), ("medium", "Q5_K_M"),
                                           ("small", "Q8_0"), ("medium", "Q4_K_M"), ("medium", "Q6_K")])
 def test_greedy_64_tokens_identical_and_logits_bit_exact_vs_canon_oracle(oracle, model_dir, preset, ftype):
     path = _model(model_dir, preset, ftype)
@@ -139,7 +139,7 @@ def test_context_limits_and_errors(oracle, model_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K")])
+@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K"), ("medium", "Q5_K_M")])
 def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_dir, preset, ftype):
     """Long prompts take the tcgen05 GEMM path (bf16 operands, f32 accumulation) instead of the integer GEMV path:
     logits after the prompt must agree with the GEMV path and with the oracle inside the bf16 tolerance, the KV
@@ -173,7 +173,7 @@ def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_di
 
 
 # ----------------------------------------------------------------------------- batched decode (BASELINE.json config 5)
-@pytest.mark.parametrize("preset,ftype,n_seq", [("tiny", "Q4_K_M", 3), ("small", "Q4_K_M", 5), ("small", "Q8_0", 2), ("medium", "Q4_K_M", 11),
+@pytest.mark.parametrize("preset,ftype,n_seq", [("tiny", "Q4_K_M", 3), ("small", "Q4_K_M", 5), ("small", "Q5_K_M", 7), ("small", "Q8_0", 2), ("medium", "Q4_K_M", 11),
                                                 ("medium", "Q6_K", 16)])
 def test_batched_decode_is_bit_identical_to_single_sequence_decode(oracle, model_dir, preset, ftype, n_seq):
     """n_seq sequences with different prompts (so different positions) advance together through gemv_batch.cu;
@@ -249,7 +249,7 @@ def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K")])
+@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K"), ("small", "Q5_K_M")])
 def test_persistent_per_token_kernel_is_bit_identical(oracle, model_dir, preset, ftype, monkeypatch):
     """csrc/mega.cu (GGB_MEGA=1): all phases of a token in one cooperative launch, grid barriers instead of kernel
     boundaries, rings prefetching across phases -- same tokens, same logits as the oracle / the multi-kernel graph."""

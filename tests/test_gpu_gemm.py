@@ -10,7 +10,7 @@ import pytest
 from conftest import rand_blocks
 
 pytestmark = pytest.mark.gpu
-TYPES = {"q4_k": 12, "q6_k": 14, "q8_0": 8}
+TYPES = {"q4_k": 12, "q5_k": 13, "q6_k": 14, "q8_0": 8}
 
 
 def bf16_round(a: np.ndarray) -> np.ndarray:

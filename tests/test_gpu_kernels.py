@@ -16,7 +16,7 @@ from conftest import rand_blocks
 pytestmark = pytest.mark.gpu
 
 TYPES = {"q8_0": 8, "q4_k": 12, "q5_k": 13, "q6_k": 14}
-GEMV_TYPES = {"q8_0": 8, "q4_k": 12, "q6_k": 14}
+GEMV_TYPES = {"q8_0": 8, "q4_k": 12, "q5_k": 13, "q6_k": 14}
 
 
 def _bits(a):
@@ -178,6 +178,27 @@ def test_gemv_mixed_segments_rmsnorm_prologue(oracle):
     for got, (ref, canon) in zip(outs, refs):
         assert np.array_equal(_bits(got), _bits(canon))
         assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("mix", [((12, 1024), (12, 256), (13, 256)), ((13, 512), (13, 128), (14, 128)), ((13, 300), (13, 300))])
+def test_gemv_q5k_mixed_segments(oracle, mix):
+    """Q5_K next to Q4_K (attn_v of a real 70B Q4_K_M file) and next to Q6_K (a Q5_K_M file's QKV): the generic K-quant kernel"""
+    import gpu_util as U
+    from ggufb200 import cabi
+    k = 2304   # one full tile + a 1-super-block tail
+    rng = np.random.default_rng(len(mix) * 31 + mix[0][0])
+    x = (rng.standard_normal(k) * 2).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
+    h = oracle.rms_norm(x, g, 1e-5)
+    segs, refs = [], []
+    for qt, rows in mix:
+        raw = rand_blocks(qt, rows * k // 256, rng)
+        refs.append(oracle.matmul(qt, raw, rows, k, h, mode="canon"))
+        segs.append((U.gpu_repack(qt, raw, rows, k), qt, rows))
+    gd = U.to_dev(g)    # keep the gains alive across the launch
+    outs = U.gpu_gemv(segs, k, x, prologue=cabi.PRO_RMSNORM, norm_w=gd.data_ptr(), eps=1e-5)
+    for got, canon in zip(outs, refs):
+        assert np.array_equal(_bits(got), _bits(canon))
 
 
 def test_gemv_residual_and_swiglu_epilogues(oracle):
