@@ -501,6 +501,8 @@ static size_t batch_smem(const GemvBK& P, int nbt, int64_t max_local) {
     return off + (size_t)max_local * nbt * sizeof(double);
 }
 
+int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream);   /* gemv_batch_mma.cu: 1 = shape not handled there */
+
 extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
     if (!a) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: null args");
     if (a->n_seg < 1 || a->n_seg > GGB_MAX_SEG) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: n_seg=%d out of range", a->n_seg);
@@ -548,6 +550,13 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
         default: GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: epilogue %d is not available in the batched kernel (STORE, RESIDUAL, SWIGLU)", a->epilogue);
     }
     if (total_rows == 0 || a->nb == 0) return GGB_OK;
+    // from 5 tokens up the integer dots of pure Q4_K / Q6_K launches go to the tensor cores (same arithmetic, half the
+    // instructions); everything else stays on the dp4a kernel below
+    static const int use_mma = env_int_b("GGB_BATCH_MMA", 1);
+    if (use_mma && a->nb >= 5 && (mask == 1 || mask == 2 || mask == 3)) {
+        const int rc = ggb_gemv_batch_mma(a, stream);
+        if (rc != 1) return rc;
+    }
     if (mask & 8) { if (mask & 4) mask = 0; else mask = 11; }   /* any mix with Q5_K runs the generic K-quant kernel */
     if (mask != 1 && mask != 2 && mask != 3 && mask != 4 && mask != 11) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: unsupported type mix (mask %d)", mask);
     P.n_seg = a->n_seg; P.k = a->k; P.T = ggb_tiles_per_row(a->k);
