@@ -242,6 +242,8 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_all, e2e_ms_all = float(tmax[0]), float(tmax[1])
 
+    exchange = ("over NVLink peer memory, fused into the GEMV epilogue (csrc/peer.cu)" if getattr(eng, "peer", None)
+                else "by NCCL all-reduce")
     if rank == 0:
         peak, peak_src = load_peaks()
         streams = 1 if tp > 1 else world          # tensor parallel: one token stream over all GPUs; replicas: one per GPU
@@ -257,8 +259,8 @@ def run_ours(args):
             "config": {
                 "workload": f"{args.model} {args.ftype} synthetic GGUF (seed {args.seed:#x}), bs=1 greedy decode, {args.steps} tokens after a {len(PROMPT)}-token prompt",
                 "parallelism": "single GPU" if world == 1 else (
-                    f"tp{tp}: q/k/v/gate/up/lm-head column-split, attn_output/ffn_down row-split, NCCL all-reduce of f64 partials "
-                    f"after each row-split projection ({2 * cfg.n_layer} per token) + one 8-byte arg-max all-reduce" if tp > 1
+                    f"tp{tp}: q/k/v/gate/up/lm-head column-split, attn_output/ffn_down row-split, f64 partials exchanged "
+                    f"{exchange} after each row-split projection ({2 * cfg.n_layer} per token) + one 8-byte NCCL arg-max all-reduce" if tp > 1
                     else f"{world} independent replicas"),
                 "l2": f"inputs_larger_than_l2 ({bpt['weights'] / tp / 1e9:.1f} GB of weights per GPU per step vs 126 MB L2)",
                 "launch": "CUDA graph per step" + ("" if args.no_pdl else " + programmatic dependent launch"),
