@@ -14,16 +14,18 @@
 // The grid does not depend on the position (read from device memory): the launch replays inside a CUDA graph.
 #include <cooperative_groups.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
-#define ATTN_CL 8      /* CTAs per cluster = position slices per head */
+#define ATTN_CL 8      /* CTAs per cluster = position slices per head (batch-1 decode) */
+#define ATTN_CL_BATCH 2 /* batched decode: many (entry, head) clusters are in flight, fewer CTAs each is cheaper (measured) */
 #define ATTN_WARPS 4
 
-template <int HD>
-__global__ void __cluster_dims__(ATTN_CL, 1, 1) __launch_bounds__(ATTN_WARPS * 32)
+template <int HD, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ATTN_WARPS * 32)
 attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                    const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
                    const int32_t* __restrict__ slot_dev, int64_t slot_stride) {
@@ -40,7 +42,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
-    const int head = blockIdx.x / ATTN_CL;
+    const int head = blockIdx.x / CL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPG, li = lane % LPG;
     const int kvh = head / (n_head / n_kv);
@@ -55,7 +57,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     q += (int64_t)be * n_head * HD;
     out += (int64_t)be * n_head * HD;
     const int n = pos + 1;
-    int chunk = (n + ATTN_CL - 1) / ATTN_CL;
+    int chunk = (n + CL - 1) / CL;
     chunk = (chunk + 7) & ~7;
     const int p_begin = min(n, crank * chunk), p_end = min(n, p_begin + chunk);
 
@@ -112,7 +114,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     cluster.sync();
     float M = -INFINITY;
 #pragma unroll
-    for (int r = 0; r < ATTN_CL; r++) M = fmaxf(M, *cluster.map_shared_rank(&cl_max, r));
+    for (int r = 0; r < CL; r++) M = fmaxf(M, *cluster.map_shared_rank(&cl_max, r));
 
     // ---- pass 2: e = exp_ref(s - M), f64 partial sums
     double acc[8], sum = 0.0;
@@ -161,11 +163,11 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     if (crank == 0) {
         double S = 0.0;
 #pragma unroll
-        for (int r = 0; r < ATTN_CL; r++) S += *cluster.map_shared_rank(&cl_sum, r);
+        for (int r = 0; r < CL; r++) S += *cluster.map_shared_rank(&cl_sum, r);
         for (int d = threadIdx.x; d < HD; d += blockDim.x) {
             double a = 0.0;
 #pragma unroll
-            for (int r = 0; r < ATTN_CL; r++) a += cluster.map_shared_rank(cl_acc, r)[d];
+            for (int r = 0; r < CL; r++) a += cluster.map_shared_rank(cl_acc, r)[d];
             out[(int64_t)head * HD + d] = (float)(a / S);
         }
     }
@@ -177,21 +179,21 @@ extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
     return 16; /* the cluster kernel needs no global workspace; kept in the ABI for split-KV variants */
 }
 
-template <int HD>
+template <int HD, int CL>
 static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
                        int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev = nullptr, int64_t slot_stride = 0,
                        int nb = 1) {
-    int chunk_max = (n_ctx + ATTN_CL - 1) / ATTN_CL;
+    int chunk_max = (n_ctx + CL - 1) / CL;
     chunk_max = (chunk_max + 7) & ~7;
     const size_t smem = (size_t)chunk_max * sizeof(float);
     if (smem > 96 * 1024) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: n_ctx=%d too large for the cluster kernel", n_ctx);
     static size_t attr = 0;
     if (smem > attr) {
-        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = 96 * 1024;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_head * ATTN_CL, nb);
+    cfg.gridDim = dim3(n_head * CL, nb);
     cfg.blockDim = dim3(ATTN_WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -200,7 +202,7 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
     return GGB_OK;
 }
 
@@ -211,8 +213,11 @@ extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uin
     if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
     if (n_ctx <= 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_ctx must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128) return launch_attn<128>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
-    if (head_dim == 64) return launch_attn<64>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    static const int cl1 = []() { const char* v = getenv("GGB_ATTN_CL"); return v && *v ? atoi(v) : 0; }();
+    if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128) return launch_attn<128, ATTN_CL>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 64) return launch_attn<64, ATTN_CL>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: head_dim=%d (supported: 64, 128)", head_dim);
 }
 
@@ -225,7 +230,20 @@ extern "C" int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, con
     if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
     if (n_ctx <= 0 || slot_stride < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode_batch: n_ctx must be positive, slot_stride non-negative");
     cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128) return launch_attn<128>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
-    if (head_dim == 64) return launch_attn<64>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+    // cluster size per (entry, head): with many clusters in flight short contexts are cheaper with fewer CTAs each; long
+    // contexts still want the 8-way position split (GGB_ATTN_BATCH_CL overrides: 2, 4 or 8)
+    static const int cl_env = []() { const char* v = getenv("GGB_ATTN_BATCH_CL"); return v && *v ? atoi(v) : 0; }();
+    const int cl = cl_env ? cl_env : (n_ctx <= 4096 ? ATTN_CL_BATCH : (n_ctx <= 16384 ? 4 : 8));
+    if (head_dim == 128) {
+        if (cl == 1) return launch_attn<128, 1>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        if (cl == 2) return launch_attn<128, 2>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        if (cl == 4) return launch_attn<128, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        return launch_attn<128, 8>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+    }
+    if (head_dim == 64) {
+        if (cl == 2) return launch_attn<64, 2>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        if (cl == 4) return launch_attn<64, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        return launch_attn<64, 8>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+    }
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode_batch: head_dim=%d (supported: 64, 128)", head_dim);
 }
