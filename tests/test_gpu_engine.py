@@ -290,3 +290,34 @@ def test_multi_sequence_gemm_prefill_equals_per_sequence_prefill(oracle, model_d
         ref = single[i][1]
         assert np.abs(sl.last_logits() - ref).max() <= 1e-4 * np.abs(ref).max()
     eng.close()
+
+
+def test_chunked_long_prompt_prefill_matches_single_chunk(oracle, model_dir):
+    """prompts longer than Engine.prefill_chunk are fed in chunks: the later chunks attend the cache written by the
+    earlier ones (pos0 > 0 in the tensor-core attention).  Same logits (to tolerance) and the same next tokens as one
+    chunk, and as the exact integer path (prompts of 16 tokens per pass through the batched kernels)."""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "medium", "Q4_K_M")
+    rng = np.random.default_rng(21)
+    prompt = [1] + [int(t) for t in rng.integers(300, 2000, 299)]
+    eng = Engine(path, n_ctx=16384)          # the reference image's default context (Dockerfile:80)
+    eng.warmup()
+    out = {}
+    for name, chunk, floor in (("one", 2048, 16), ("chunked", 64, 16), ("exact", 2048, 10 ** 9)):
+        eng.prefill_chunk, eng.gemm_prefill_min = chunk, floor
+        eng.reset()
+        eng.prefill(prompt)
+        out[name] = (eng.last_logits().copy(), eng.read_last_token())
+    ref = out["exact"][0]
+    scale = np.abs(ref).max()
+    assert np.abs(out["one"][0] - out["chunked"][0]).max() <= 2e-3 * scale
+    # bf16 tensor-core path vs the integer path after 300 tokens of history on a random-init model: the documented
+    # <= 6e-2 band of any two arithmetic orders (module docstring); measured 3.2e-2 here
+    assert np.abs(out["one"][0] - ref).max() <= 6e-2 * scale
+    assert out["one"][1] == out["chunked"][1]
+    # the exact path equals the oracle bit for bit even at this context size
+    m = oracle.OracleLlama(path, n_ctx=512, mode="canon")
+    want = m.greedy(prompt, 1, return_logits=True)
+    assert out["exact"][1] == want[0][0]
+    assert np.array_equal(_bits(ref), _bits(want[1][0]))
+    eng.close()
