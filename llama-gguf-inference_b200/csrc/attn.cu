@@ -48,8 +48,10 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     const int kvh = head / (n_head / n_kv);
     const int64_t kv_stride = (int64_t)n_kv * HD;
 
-    pdl_wait();
-    // batch entry blockIdx.y: its own query row, position and (through slot_dev) cache
+    // (no griddepcontrol.launch_dependents here: letting the output projection become resident early was measured --
+    // 460 vs 504 tok/s -- its 148 fat CTAs get in the way of scheduling this kernel's 32 clusters)
+    // batch entry blockIdx.y: its own query row, position and (through slot_dev) cache.  The position is stable for the
+    // whole token (the sampler tail of the previous token wrote it and has completed before this token's first launch).
     const int be = blockIdx.y;
     const int pos = pos_dev[be];
     if (pos < 0) return;   /* idle batch entry: the whole cluster leaves before any cluster barrier */
@@ -60,6 +62,20 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     int chunk = (n + CL - 1) / CL;
     chunk = (chunk + 7) & ~7;
     const int p_begin = min(n, crank * chunk), p_end = min(n, p_begin + chunk);
+
+    // K and V rows of positions < pos were written by earlier tokens: request the first batch of them BEFORE waiting for
+    // the QKV launch that is producing q and row `pos` -- their L2 / HBM latency then hides behind that launch
+    constexpr int AU = 4;
+    uint4 kpre[AU], vpre[AU];
+#pragma unroll
+    for (int u = 0; u < AU; u++) {
+        const int p = p_begin + warp * PPW + u * SLOTS + sub;
+        const bool old_row = p < p_end && p < pos;
+        const int64_t off = (old_row ? p : 0) * kv_stride + (int64_t)kvh * HD + li * 8;
+        kpre[u] = *reinterpret_cast<const uint4*>(kc + off);
+        vpre[u] = *reinterpret_cast<const uint4*>(vc + off);
+    }
+    pdl_wait();
 
     float qr[8];
     {
@@ -73,14 +89,15 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 
     // ---- pass 1: scores of my slice + slice maximum.  AU positions per lane group are in flight at once (the loop is
     // a chain of L2 round trips otherwise: one 16-byte load, then its dependent arithmetic)
-    constexpr int AU = 4;
     float mx = -INFINITY;
     for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        const bool first = (p0 == p_begin + warp * PPW);
         uint4 kraw[AU];
 #pragma unroll
         for (int u = 0; u < AU; u++) {
             const int p = p0 + u * SLOTS + sub;
-            kraw[u] = *reinterpret_cast<const uint4*>(kc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+            if (first && p < pos) kraw[u] = kpre[u];           /* requested before the dependency wait */
+            else kraw[u] = *reinterpret_cast<const uint4*>(kc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
         }
 #pragma unroll
         for (int u = 0; u < AU; u++) {
@@ -121,11 +138,13 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0;
     for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        const bool first = (p0 == p_begin + warp * PPW);
         uint4 vraw[AU];
 #pragma unroll
         for (int u = 0; u < AU; u++) {
             const int p = p0 + u * SLOTS + sub;
-            vraw[u] = *reinterpret_cast<const uint4*>(vc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+            if (first && p < pos) vraw[u] = vpre[u];
+            else vraw[u] = *reinterpret_cast<const uint4*>(vc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
         }
 #pragma unroll
         for (int u = 0; u < AU; u++) {
