@@ -5,9 +5,10 @@
 //
 // One thread-block CLUSTER of 8 CTAs per query head (B200: distributed shared memory + cluster barrier):
 //   pass 1  every CTA scores its slice of positions (f16 x f16 products are exact in f32; summed in f64) and
-//           keeps them in shared memory; the slice maxima are exchanged through DSMEM -> global max M;
-//   pass 2  e = exp_ref(s - M); per-CTA f64 partial sums of e and of e*v; rank 0 gathers the eight partials
-//           through DSMEM in rank order and writes out = (float)(sum_ev / sum_e).
+//           keeps them in shared memory; every CTA PUSHES its slice maximum into all peers' shared memory (DSMEM
+//           stores), one cluster barrier -> global max M from a local array;
+//   pass 2  e = exp_ref(s - M); per-CTA f64 partial sums of e and of e*v, pushed into rank 0's shared memory; after the
+//           second (last) cluster barrier rank 0 adds them in rank order and writes out = (float)(sum_ev / sum_e).
 // A true two-pass softmax (one global max) in a single launch: no split-KV merge kernel, no running-max
 // rescaling, and -- because every sum is an f64 sum of f32 terms -- the result does not depend on how the
 // positions are split, so it is bit-identical with the oracle's gref_attn_decode_canon.
@@ -20,26 +21,40 @@
 
 namespace cg = cooperative_groups;
 
+#ifdef GGB_TIMELINE   /* debug builds: %globaltimer stamps of the LAST launch [cta][entry, wait done, pass 1 done, pass 2 done, exit] */
+__device__ unsigned long long ggb_tl_attn[512 * 8];
+#define ATL(i) do { if (threadIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); ggb_tl_attn[(blockIdx.x & 511) * 8 + (i)] = t_; } } while (0)
+extern "C" int ggb_debug_timeline_attn(unsigned long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, ggb_tl_attn, sizeof(ggb_tl_attn)) == cudaSuccess ? 0 : -2;
+}
+#else
+#define ATL(i) do { } while (0)
+#endif
+
 #define ATTN_CL 8      /* CTAs per cluster = position slices per head (batch-1 decode) */
 #define ATTN_CL_BATCH 2 /* batched decode: many (entry, head) clusters are in flight, fewer CTAs each is cheaper (measured) */
-#define ATTN_WARPS 4
+#define ATTN_WARPS 8        /* batch-1 decode: warps per CTA (4 / 8 / 16 measured: 516 / 527 / 456 tok/s) */
+#define ATTN_WARPS_BATCH 4  /* batched decode: leaner CTAs win when hundreds of clusters are in flight (measured) */
 
-template <int HD, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ATTN_WARPS * 32)
+template <int HD, int CL, int NW>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NW * 32)
 attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                    const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
                    const int32_t* __restrict__ slot_dev, int64_t slot_stride) {
     constexpr int LPG = HD / 8;        // lanes per position (each lane owns 8 consecutive dims = one 16-byte load)
     constexpr int PPW = 32 / LPG;      // positions per warp step
-    constexpr int SLOTS = ATTN_WARPS * PPW;
+    constexpr int SLOTS = NW * PPW;
     extern __shared__ __align__(16) float s_scores[];   // this CTA's slice of scores
     __shared__ double sm_acc[SLOTS][HD];
     __shared__ double sm_sum[SLOTS];
-    __shared__ float sm_max[ATTN_WARPS];
-    __shared__ float cl_max;            // read by the other CTAs of the cluster
-    __shared__ double cl_acc[HD];       // read by rank 0
-    __shared__ double cl_sum;
+    __shared__ float sm_max[NW];
+    // exchange areas, WRITTEN by the peers through distributed shared memory (pushing costs one cluster barrier;
+    // pulling after the barrier would add a remote-read round trip on the critical path)
+    __shared__ float cl_max[CL];        // slice maxima of all ranks (every CTA holds a full copy)
+    __shared__ double cl_acc[CL][HD];   // rank 0 only: the partial e*v sums of all ranks
+    __shared__ double cl_sum[CL];       // rank 0 only: the partial e sums
 
+    ATL(0);
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int head = blockIdx.x / CL;
@@ -74,6 +89,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
         vpre[u] = *reinterpret_cast<const uint4*>(vc + off);
     }
     pdl_wait();
+    ATL(1);
     // No griddepcontrol.launch_dependents in this kernel: letting the output projection become resident while the
     // attention runs was measured twice (trigger before the wait: 460 tok/s; after it: 458; without: 504).
 
@@ -122,16 +138,17 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     mx = warp_max(mx);
     if (lane == 0) sm_max[warp] = mx;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < CL) {                     /* thread r hands this slice's maximum to rank r */
         float m = sm_max[0];
 #pragma unroll
-        for (int w = 1; w < ATTN_WARPS; w++) m = fmaxf(m, sm_max[w]);
-        cl_max = m;
+        for (int w = 1; w < NW; w++) m = fmaxf(m, sm_max[w]);
+        cluster.map_shared_rank(cl_max, threadIdx.x)[crank] = m;
     }
     cluster.sync();
+    ATL(2);
     float M = -INFINITY;
 #pragma unroll
-    for (int r = 0; r < CL; r++) M = fmaxf(M, *cluster.map_shared_rank(&cl_max, r));
+    for (int r = 0; r < CL; r++) M = fmaxf(M, cl_max[r]);
 
     // ---- pass 2: e = exp_ref(s - M), f64 partial sums
     double acc[8], sum = 0.0;
@@ -166,31 +183,35 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 #pragma unroll
     for (int i = 0; i < 8; i++) sm_acc[slot][li * 8 + i] = acc[i];
     __syncthreads();
-    for (int d = threadIdx.x; d < HD; d += blockDim.x) {
-        double a = 0.0;
-#pragma unroll
-        for (int s2 = 0; s2 < SLOTS; s2++) a += sm_acc[s2][d];
-        cl_acc[d] = a;
-    }
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int s2 = 0; s2 < SLOTS; s2++) t += sm_sum[s2];
-        cl_sum = t;
-    }
-    cluster.sync();
-    if (crank == 0) {
-        double S = 0.0;
-#pragma unroll
-        for (int r = 0; r < CL; r++) S += *cluster.map_shared_rank(&cl_sum, r);
+    {   /* this slice's partial sums go straight into rank 0's shared memory */
+        double* acc0 = &cluster.map_shared_rank(&cl_acc[0][0], 0)[crank * HD];
         for (int d = threadIdx.x; d < HD; d += blockDim.x) {
             double a = 0.0;
 #pragma unroll
-            for (int r = 0; r < CL; r++) a += cluster.map_shared_rank(cl_acc, r)[d];
+            for (int s2 = 0; s2 < SLOTS; s2++) a += sm_acc[s2][d];
+            acc0[d] = a;
+        }
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int s2 = 0; s2 < SLOTS; s2++) t += sm_sum[s2];
+            cluster.map_shared_rank(cl_sum, 0)[crank] = t;
+        }
+    }
+    cluster.sync();
+    ATL(3);
+    if (crank == 0) {                           /* rank order, as before: the same f64 sums */
+        double S = 0.0;
+#pragma unroll
+        for (int r = 0; r < CL; r++) S += cl_sum[r];
+        for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < CL; r++) a += cl_acc[r][d];
             out[(int64_t)head * HD + d] = (float)(a / S);
         }
     }
-    cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+    ATL(4);
 }
 
 extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
@@ -198,7 +219,7 @@ extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
     return 16; /* the cluster kernel needs no global workspace; kept in the ABI for split-KV variants */
 }
 
-template <int HD, int CL>
+template <int HD, int CL, int NW = ATTN_WARPS_BATCH>
 static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
                        int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev = nullptr, int64_t slot_stride = 0,
                        int nb = 1) {
@@ -208,12 +229,12 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     if (smem > 96 * 1024) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: n_ctx=%d too large for the cluster kernel", n_ctx);
     static size_t attr = 0;
     if (smem > attr) {
-        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD, CL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = 96 * 1024;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_head * CL, nb);
-    cfg.blockDim = dim3(ATTN_WARPS * 32);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -221,7 +242,7 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL, NW>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
     return GGB_OK;
 }
 
@@ -233,10 +254,10 @@ extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uin
     if (n_ctx <= 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_ctx must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     static const int cl1 = []() { const char* v = getenv("GGB_ATTN_CL"); return v && *v ? atoi(v) : 0; }();
-    if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
-    if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
-    if (head_dim == 128) return launch_attn<128, ATTN_CL>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
-    if (head_dim == 64) return launch_attn<64, ATTN_CL>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128) return launch_attn<128, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 64) return launch_attn<64, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: head_dim=%d (supported: 64, 128)", head_dim);
 }
 

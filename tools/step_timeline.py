@@ -37,4 +37,16 @@ for i in range(8):
     ex = (t[i, :, 5].max() - t0) / 1e3
     nxt = (np.median(t[i + 1, :, 2]) - t0) / 1e3 if i + 1 < 8 else float("nan")
     print(f"{names[i]:9s} " + " ".join(f"{v:10.2f}" for v in med) + f" {ex:10.2f} | {ex - med[2]:8.2f}   {nxt - ex:8.2f}")
+try:
+    L.ggb_debug_timeline_attn.argtypes = [C.c_void_p]
+    L.ggb_debug_timeline_attn.restype = C.c_int
+    ab = np.zeros(512 * 8, dtype=np.uint64)
+    assert L.ggb_debug_timeline_attn(ab.ctypes.data) == 0
+    a = ab.reshape(512, 8)[:256, :5].astype(np.int64)
+    print("attention of the last layer (256 CTAs), us relative to the same origin: [entry, dependency wait done, max exchanged, sums exchanged, exit]")
+    print("   min   ", " ".join(f"{(a[:, i].min() - t0) / 1e3:9.2f}" for i in range(5)))
+    print("   median", " ".join(f"{(np.median(a[:, i]) - t0) / 1e3:9.2f}" for i in range(5)))
+    print("   max   ", " ".join(f"{(a[:, i].max() - t0) / 1e3:9.2f}" for i in range(5)))
+except AttributeError:
+    pass
 eng.close()
