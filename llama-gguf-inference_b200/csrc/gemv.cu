@@ -206,8 +206,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     }
 
     TL_STAMP(1);
-    pdl_launch_dependents();
     pdl_wait();
+    // Trigger the dependent launch only NOW (not before the wait): at most the next launch is then resident while this
+    // one works, filling its ring.  Triggering before the wait lets launches pile up three deep once co-residency really
+    // works (equal shared-memory carveouts, see the host side), and their ring fills then slow the latency-bound
+    // prologues of the running launch: 505 vs 543 tok/s.  Triggering after the prologue instead: no difference.
+    pdl_launch_dependents();
     TL_STAMP(2);
 
     // epilogue operands that only depend on the previous phase: request them now, use them at the end
@@ -455,6 +459,10 @@ static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream
     static bool attr_done = false;
     if (!attr_done) {
         GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK, R, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMV_MAX_SMEM));
+        // every decode kernel asks for the SAME (maximal) shared-memory carveout: an SM whose L1/shared split differs from
+        // what the next launch prefers must drain before it is reconfigured, which silently defeats the PDL co-residency
+        // (in-situ timeline: only launches with equal footprints overlapped)
+        GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK, R, STEPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
