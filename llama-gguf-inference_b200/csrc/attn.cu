@@ -92,7 +92,8 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     ATL(1);
     // No griddepcontrol.launch_dependents in this kernel: letting the output projection become resident while the
     // attention runs was measured repeatedly (before the carveout fix: trigger before the wait 460 tok/s, after it 458,
-    // without 504; after the fix: 485 with, 543 without).
+    // without 504; after the fix: 485 with, 543 without -- the projection then enters 4 us earlier, but the GATE/UP launch
+    // behind it runs 5 us longer: tools/step_timeline.py).
 
     float qr[8];
     {
