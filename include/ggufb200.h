@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GGB_ABI_VERSION 2
+#define GGB_ABI_VERSION 3
 
 /* ggml tensor type ids (gguf/constants.py:4059-4093) */
 #define GGB_TYPE_F32 0
@@ -130,9 +130,16 @@ typedef struct ggb_gemv_args {
     int32_t peer_n, peer_rank;
     int64_t peer_d_cap;
     uint64_t peer_base[GGB_PEER_MAX];
+    /* ask for at least this much dynamic shared memory (0 = what the launch needs): with more than half of an SM's shared
+     * memory two CTAs of the launch can never share an SM, which keeps the placement even when it becomes resident while
+     * another kernel's small CTAs are still running (the output projection behind the attention) */
+    int32_t min_smem;
 } ggb_gemv_args;
 
 int ggb_gemv(const ggb_gemv_args* args, void* stream);
+/* dynamic shared memory ggb_gemv would request for these args (the host uses it to decide which adjacent launches can
+ * be co-resident); negative = error code */
+int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* args);
 /* number of CTAs ggb_gemv will launch for these args (size of part_val/part_idx) */
 int ggb_gemv_grid(const ggb_gemv_args* args);
 
@@ -215,6 +222,8 @@ int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_de
 
 /* ---- KV-cache attention, one query token (ggml flash_attn_ext / soft_max path, GQA)
  * q [n_head*hd] f32 (already rotated); caches [n_ctx][n_kv*hd] f16; attends positions 0..*pos_dev inclusive.
+ * use_pdl: bit 0 = launch with programmatic stream serialisation; bit 1 = also release the NEXT launch once this one
+ * has passed its dependency wait (only useful when that launch cannot land twice on an SM: ggb_gemv_args.min_smem).
  * ws: workspace of ggb_attn_decode_ws_bytes() bytes.  out [n_head*hd] f32. */
 size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim);
 int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,

@@ -22,7 +22,7 @@ EXPORTS = [
     "ggb_abi_version", "ggb_last_error", "ggb_device_info",
     "ggb_dequant", "ggb_repacked_row_stride", "ggb_repack", "ggb_dequant_repacked",
     "ggb_quantize_q8_K", "ggb_quantize_q8_0",
-    "ggb_gemv", "ggb_gemv_grid", "ggb_gemm", "ggb_f32_to_bf16",
+    "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemm", "ggb_f32_to_bf16",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
@@ -55,6 +55,7 @@ class GemvArgs(C.Structure):
         ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
         ("grid", C.c_int32),
         ("peer_n", C.c_int32), ("peer_rank", C.c_int32), ("peer_d_cap", C.c_int64), ("peer_base", C.c_uint64 * PEER_MAX),
+        ("min_smem", C.c_int32),
     ]
 
 
@@ -102,6 +103,7 @@ def lib() -> C.CDLL:
         "ggb_quantize_q8_0": ([vp, vp, vp, i64, i32, vp], i32),
         "ggb_gemv": ([C.POINTER(GemvArgs), vp], i32),
         "ggb_gemv_grid": ([C.POINTER(GemvArgs)], i32),
+        "ggb_gemv_smem_bytes": ([C.POINTER(GemvArgs)], i64),
         "ggb_gemm": ([i32, vp, i32, i32, vp, i32, vp, i64, vp], i32),
         "ggb_f32_to_bf16": ([vp, vp, i64, vp], i32),
         "ggb_embed_row": ([i32, vp, i64, vp, vp, vp], i32),
@@ -157,7 +159,7 @@ def device_info() -> dict:
 
 def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w=0, eps=0.0, use_pdl=0, residual=0,
                    pos_dev=0, rope_tab=0, n_rot=0, head_dim=0, kcache=0, vcache=0, part_val=0, part_idx=0, grid=0,
-                   peer=None) -> GemvArgs:
+                   peer=None, min_smem=0) -> GemvArgs:
     """segs: list of (w_ptr, type, rows, y_ptr)."""
     a = GemvArgs()
     a.n_seg = len(segs)
@@ -171,6 +173,7 @@ def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w
     a.x, a.norm_w, a.eps, a.use_pdl, a.residual = x, norm_w, eps, use_pdl, residual
     a.pos_dev, a.rope_tab, a.n_rot, a.head_dim = pos_dev, rope_tab, n_rot, head_dim
     a.kcache, a.vcache, a.part_val, a.part_idx, a.grid = kcache, vcache, part_val, part_idx, grid
+    a.min_smem = min_smem
     if peer is not None:    # (bases of every rank's exchange region in this process, own rank, capacity in rows)
         bases, rank, d_cap = peer
         a.peer_n, a.peer_rank, a.peer_d_cap = len(bases), rank, d_cap

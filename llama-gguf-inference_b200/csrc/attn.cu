@@ -40,7 +40,7 @@ template <int HD, int CL, int NW>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NW * 32)
 attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                    const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
-                   const int32_t* __restrict__ slot_dev, int64_t slot_stride) {
+                   const int32_t* __restrict__ slot_dev, int64_t slot_stride, int trigger) {
     constexpr int LPG = HD / 8;        // lanes per position (each lane owns 8 consecutive dims = one 16-byte load)
     constexpr int PPW = 32 / LPG;      // positions per warp step
     constexpr int SLOTS = NW * PPW;
@@ -90,10 +90,12 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     }
     pdl_wait();
     ATL(1);
-    // No griddepcontrol.launch_dependents in this kernel: letting the output projection become resident while the
-    // attention runs was measured repeatedly (before the carveout fix: trigger before the wait 460 tok/s, after it 458,
-    // without 504; after the fix: 485 with, 543 without -- the projection then enters 4 us earlier, but the GATE/UP launch
-    // behind it runs 5 us longer: tools/step_timeline.py).
+    // Releasing the output projection here lets it become resident (and fill its weight ring) while the attention runs:
+    // 543 -> 555 tok/s -- but ONLY if the projection's CTAs cannot land twice on one SM (ggb_gemv_args.min_smem).
+    // Otherwise they are placed unevenly around this kernel's small CTAs -- two here, none there -- the launch behind
+    // them inherits the imbalance, and the step gets 10 % slower (485 tok/s; tools/step_timeline.py shows entry times
+    // spread over 20 us).  Hence a flag, set by the host when it has padded the projection.
+    if (trigger) pdl_launch_dependents();
 
     float qr[8];
     {
@@ -225,6 +227,7 @@ template <int HD, int CL, int NW = ATTN_WARPS_BATCH>
 static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
                        int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev = nullptr, int64_t slot_stride = 0,
                        int nb = 1) {
+    const int trigger = (use_pdl & 2) ? 1 : 0;
     int chunk_max = (n_ctx + CL - 1) / CL;
     chunk_max = (chunk_max + 7) & ~7;
     const size_t smem = (size_t)chunk_max * sizeof(float);
@@ -232,6 +235,7 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     static size_t attr = 0;
     if (smem > attr) {
         GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD, CL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<HD, CL, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   /* see gemv.cu */
         attr = 96 * 1024;
     }
     cudaLaunchConfig_t cfg = {};
@@ -243,8 +247,8 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL, NW>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride));
+    cfg.numAttrs = (use_pdl & 1) ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL, NW>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride, trigger));
     return GGB_OK;
 }
 

@@ -479,6 +479,8 @@ static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream
     return GGB_OK;
 }
 
+static thread_local int64_t* g_smem_query = nullptr;   /* ggb_gemv_smem_bytes: plan only, report the shared memory, do not launch */
+
 extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     if (!a) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: null args");
     if (a->n_seg < 1 || a->n_seg > GGB_MAX_SEG) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: n_seg=%d out of range", a->n_seg);
@@ -565,8 +567,13 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     size_t off = (size_t)GEMV_NW * P.ring_bytes + (size_t)a->k + a->k / 8 + a->k / 8;
     off = (off + 15) & ~(size_t)15;
     P.rowv_off = (int)off;
-    const size_t smem = off + (size_t)max_local * sizeof(double);
+    size_t smem = off + (size_t)max_local * sizeof(double);
+    // min_smem: the caller may ask for MORE shared memory than the launch needs, so that two CTAs of it can never land on
+    // one SM.  A launch that becomes resident while small CTAs of another kernel (the attention) still occupy some SMs
+    // is otherwise placed unevenly -- two CTAs here, none there -- and so is everything launched behind it.
+    if (a->min_smem > 0 && smem < (size_t)a->min_smem && (size_t)a->min_smem <= GEMV_MAX_SMEM) smem = (size_t)a->min_smem;
     if (smem > GEMV_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
+    if (g_smem_query) { *g_smem_query = (int64_t)smem; return GGB_OK; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (mask) {
         case 1: return launch<1, 4, 2>(P, grid, smem, a->use_pdl, st);
@@ -578,3 +585,12 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
             GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: unsupported type mix (mask %d)", mask);
     }
 }
+
+extern "C" int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* a) {
+    int64_t v = 0;
+    g_smem_query = &v;
+    const int rc = ggb_gemv(a, nullptr);
+    g_smem_query = nullptr;
+    return rc == GGB_OK ? v : (int64_t)rc;
+}
+

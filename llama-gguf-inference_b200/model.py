@@ -26,6 +26,9 @@ from . import cabi
 from . import gguf_reader as G
 from . import parallel
 
+SM_SMEM = 227 * 1024            # shared memory an SM can hand out to CTAs (B200)
+HALF_SM_SMEM = SM_SMEM // 2 + 512
+
 QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q5_K, G.GGML_Q6_K, G.GGML_Q8_0)
 
 
@@ -129,6 +132,7 @@ class Slot:
     def _build_args(self):
         hp, e = self.hp, self.eng
         self._layer_args = []
+        self._attn_pdl = []
         for i, L in enumerate(e.layers):
             qkv = cabi.make_gemv_args(
                 [(L["wq"].ptr, L["wq"].type, L["wq"].rows, self.q.data_ptr()),
@@ -155,6 +159,18 @@ class Slot:
                 [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wd"].k,
                 self.h.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=epi_rs,
                 residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer)
+            # The attention releases the output projection early (it then fills its weight ring while the attention runs)
+            # only if two CTAs of the projection cannot land on one SM: pad its shared memory past half an SM's when the
+            # gate/up launch behind it still fits next to it (csrc/attn.cu, csrc/gemv.cu: min_smem).
+            so, sg = self.lib.ggb_gemv_smem_bytes(C.byref(o)), self.lib.ggb_gemv_smem_bytes(C.byref(gu))
+            trig = 0
+            if self.use_pdl and so > 0 and sg > 0:
+                if so >= HALF_SM_SMEM:
+                    trig = 2
+                elif HALF_SM_SMEM + 2048 + sg + 2048 <= SM_SMEM:
+                    o.min_smem = HALF_SM_SMEM + 2048
+                    trig = 2
+            self._attn_pdl.append(self.use_pdl | trig)
             self._layer_args.append((qkv, o, gu, dn))
         self._head = self._head_args()
         self._mega = None
@@ -211,7 +227,7 @@ class Slot:
             cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
             cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
                                            self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
-                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self.use_pdl, s), "attn_decode")
+                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i], s), "attn_decode")
             cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
             if tp:
                 self._allreduce_residual(s)

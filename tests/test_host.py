@@ -196,7 +196,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ggb_abi_version() == 2
+    assert L.ggb_abi_version() == 3
     # entry points validate their arguments before touching the GPU (no compute call is made here)
     assert L.ggb_repacked_row_stride(12, 4096) == 2304 and L.ggb_repacked_row_stride(14, 5632) == 4624
     assert L.ggb_repacked_row_stride(12, 100) == -1 and L.ggb_repacked_row_stride(2, 4096) == -1

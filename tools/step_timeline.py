@@ -36,7 +36,8 @@ for i in range(8):
     med = (np.median(t[i], axis=0) - t0) / 1e3
     ex = (t[i, :, 5].max() - t0) / 1e3
     nxt = (np.median(t[i + 1, :, 2]) - t0) / 1e3 if i + 1 < 8 else float("nan")
-    print(f"{names[i]:9s} " + " ".join(f"{v:10.2f}" for v in med) + f" {ex:10.2f} | {ex - med[2]:8.2f}   {nxt - ex:8.2f}")
+    print(f"{names[i]:9s} " + " ".join(f"{v:10.2f}" for v in med) + f" {ex:10.2f} | {ex - med[2]:8.2f}   {nxt - ex:8.2f}"
+          f"   entry min/max {(t[i, :, 0].min() - t0) / 1e3:.2f}/{(t[i, :, 0].max() - t0) / 1e3:.2f}  main_done max {(t[i, :, 4].max() - t0) / 1e3:.2f}")
 try:
     L.ggb_debug_timeline_attn.argtypes = [C.c_void_p]
     L.ggb_debug_timeline_attn.restype = C.c_int
