@@ -49,7 +49,7 @@ extern "C" int ggb_peer_free(void* ptr) {
 
 __global__ void __launch_bounds__(256) peer_reduce_residual_kernel(float* __restrict__ x, uint64_t own_base, int n, int64_t d, int64_t d_cap) {
     pdl_wait();
-    pdl_launch_dependents();   /* after the wait, like the GEMV: at most the next launch is resident meanwhile */
+    pdl_launch_dependents();   /* after the wait, like the GEMV: at most the next launch is resident meanwhile (70B tp2: 139.5 tok/s; without: 134.6) */
     uint8_t* base = reinterpret_cast<uint8_t*>(own_base);
     int* state = reinterpret_cast<int*>(base + ggb_peer_state_off(n, d_cap));
     const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int*>(state + 1) + 1);   /* the exchange this rank just fed */
