@@ -201,6 +201,32 @@ def test_gemv_q5k_mixed_segments(oracle, mix):
         assert np.array_equal(_bits(got), _bits(canon))
 
 
+def test_gemv_min_smem_and_smem_query(oracle):
+    """min_smem only changes the shared-memory request (placement), never the result; ggb_gemv_smem_bytes reports it"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    k, rows = 4096, 1000
+    rng = np.random.default_rng(23)
+    raw = rand_blocks(12, rows * k // 256, rng)
+    x = rng.standard_normal(k).astype(np.float32)
+    w, xd = U.gpu_repack(12, raw, rows, k), U.to_dev(x)
+    y = torch.zeros(rows, dtype=torch.float32, device=U.DEV)
+    a = cabi.make_gemv_args([(w.data_ptr(), 12, rows, y.data_ptr())], k, xd.data_ptr())
+    base = L.ggb_gemv_smem_bytes(C.byref(a))
+    assert 60 * 1024 < base < 114 * 1024
+    a.min_smem = 118 * 1024
+    assert L.ggb_gemv_smem_bytes(C.byref(a)) == 118 * 1024
+    cabi.check(L.ggb_gemv(C.byref(a), U.stream_ptr()))
+    U.sync()
+    assert np.array_equal(_bits(y.cpu().numpy()), _bits(oracle.matmul(12, raw, rows, k, x, mode="canon")))
+    a.min_smem = 16            # smaller than needed: ignored
+    assert L.ggb_gemv_smem_bytes(C.byref(a)) == base
+    a.k = 100                  # invalid args: the query reports the error code
+    assert L.ggb_gemv_smem_bytes(C.byref(a)) == -1
+
+
 def test_gemv_residual_and_swiglu_epilogues(oracle):
     import torch
     import gpu_util as U
