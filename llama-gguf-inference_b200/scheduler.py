@@ -28,10 +28,24 @@ class SamplingParams:
     top_k: int = 40
     top_p: float = 0.95
     seed: int | None = None
+    min_p: float = 0.0                 # keep tokens with p >= min_p * p_max (0 = off)
+    repeat_penalty: float = 1.0        # llama.cpp: logits of recent tokens divided (if > 0) or multiplied (if < 0) by this
+    presence_penalty: float = 0.0      # OpenAI: subtracted once for every token seen in the window
+    frequency_penalty: float = 0.0     # OpenAI: subtracted per occurrence in the window
+    repeat_last_n: int = 64            # window of the three penalties (prompt tail + generated tokens)
+
+    @property
+    def penalised(self) -> bool:
+        return self.repeat_penalty != 1.0 or self.presence_penalty != 0.0 or self.frequency_penalty != 0.0
+
+    @property
+    def arg_max(self) -> bool:
+        return self.temperature <= 0.0 or self.top_k == 1
 
     @property
     def greedy(self) -> bool:
-        return self.temperature <= 0.0 or self.top_k == 1
+        """decided on the device: arg-max of the raw logits"""
+        return self.arg_max and not self.penalised
 
 
 @dataclass
@@ -46,9 +60,28 @@ class Request:
     t_submit: float = field(default_factory=time.time)
 
 
-def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator) -> int:
-    """temperature -> top-k -> top-p -> multinomial, the default order of upstream's sampler chain [UPSTREAM-MEM]."""
-    if sp.greedy:
+def apply_penalties(logits: np.ndarray, sp: SamplingParams, history) -> np.ndarray:
+    """repeat / presence / frequency penalties over the last repeat_last_n tokens (llama.cpp's `penalties` sampler
+    [UPSTREAM-MEM: llama-sampling.cpp]): x = x / r if x > 0 else x * r, then x -= count * frequency + presence."""
+    if not sp.penalised or not history:
+        return logits
+    win = list(history)[-sp.repeat_last_n:] if sp.repeat_last_n > 0 else list(history)
+    ids, counts = np.unique(np.asarray(win, dtype=np.int64), return_counts=True)
+    keep = (ids >= 0) & (ids < logits.size)
+    ids, counts = ids[keep], counts[keep]
+    x = logits.astype(np.float32).copy()
+    if sp.repeat_penalty != 1.0:
+        v = x[ids]
+        x[ids] = np.where(v > 0, v / sp.repeat_penalty, v * sp.repeat_penalty)
+    x[ids] -= counts.astype(np.float32) * np.float32(sp.frequency_penalty) + np.float32(sp.presence_penalty)
+    return x
+
+
+def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator, history=None) -> int:
+    """penalties -> temperature -> top-k -> top-p -> min-p -> multinomial (the samplers of upstream's default chain
+    that the reference's API documents, docs/API_REFERENCE.md:369-379 [UPSTREAM-MEM for the arithmetic])."""
+    logits = apply_penalties(logits, sp, history)
+    if sp.arg_max:
         return int(np.argmax(logits))
     x = logits.astype(np.float64) / max(sp.temperature, 1e-6)
     k = sp.top_k if 0 < sp.top_k < x.size else x.size
@@ -58,6 +91,9 @@ def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generato
     p /= p.sum()
     if 0.0 < sp.top_p < 1.0:
         keep = int(np.searchsorted(np.cumsum(p), sp.top_p) + 1)
+        idx, p = idx[:keep], p[:keep] / p[:keep].sum()
+    if 0.0 < sp.min_p < 1.0:
+        keep = max(1, int((p >= sp.min_p * p[0]).sum()))          # p is sorted, p[0] is the maximum
         idx, p = idx[:keep], p[:keep] / p[:keep].sum()
     return int(idx[rng.choice(len(idx), p=p)])
 
@@ -71,6 +107,8 @@ class _Active:
         self.text = ""
         self.sent = 0          # characters of self.text already emitted
         self.rng = np.random.default_rng(req.sampling.seed)
+        n = max(0, req.sampling.repeat_last_n)
+        self.history = deque(req.prompt_ids[-n:] if n else req.prompt_ids, maxlen=n or None)   # penalty window
         self.t_first = None
         self.t_start = time.time()
 
@@ -196,7 +234,7 @@ class Scheduler(threading.Thread):
         """token produced by the step that just ran"""
         if a.req.sampling.greedy:
             return a.slot.read_last_token()
-        return sample_token(a.slot.read_logits(), a.req.sampling, a.rng)
+        return sample_token(a.slot.read_logits(), a.req.sampling, a.rng, a.history)
 
     def _step(self, i: int):
         a = self.active.get(i)
@@ -227,13 +265,14 @@ class Scheduler(threading.Thread):
         self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
         self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
         for b, (i, a) in enumerate(zip(live, acts)):
-            tok = toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng)
+            tok = toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng, a.history)
             self._emit(i, tok)
 
     def _emit(self, i: int, tok: int):
         a = self.active[i]
         req = a.req
         a.last_tok = tok
+        a.history.append(tok)
         if a.t_first is None:
             a.t_first = time.time()
         if tok in self.tok.eog and not (req.ignore_eos or self.ignore_eos):

@@ -179,7 +179,12 @@ class Handler(BaseHTTPRequestHandler):
         d = st.defaults
         sp = SamplingParams(temperature=float(body.get("temperature", d.temperature)),
                             top_k=int(body.get("top_k", d.top_k)), top_p=float(body.get("top_p", d.top_p)),
-                            seed=(int(body["seed"]) if body.get("seed") not in (None, -1) else d.seed))
+                            seed=(int(body["seed"]) if body.get("seed") not in (None, -1) else d.seed),
+                            min_p=float(body.get("min_p", d.min_p)),
+                            repeat_penalty=float(body.get("repeat_penalty", d.repeat_penalty)),
+                            presence_penalty=float(body.get("presence_penalty", d.presence_penalty)),
+                            frequency_penalty=float(body.get("frequency_penalty", d.frequency_penalty)),
+                            repeat_last_n=int(body.get("repeat_last_n", d.repeat_last_n)))
         stop = body.get("stop") or []
         if isinstance(stop, str):
             stop = [stop]

@@ -290,3 +290,24 @@ def test_header_scale_regrouping_roundtrip(layout_lib):
             a, b = C.c_int(), C.c_int()
             layout_lib.dec(hdr.ctypes.data_as(C.POINTER(C.c_uint8)), j, C.byref(a), C.byref(b))
             assert (a.value, b.value) == (int(sc), int(mn))
+
+
+def test_sampler_min_p_and_penalties():
+    """the samplers the reference's API documents beyond temperature/top-k/top-p (docs/API_REFERENCE.md:369-379)"""
+    from ggufb200.scheduler import SamplingParams, apply_penalties, sample_token
+    rng = np.random.default_rng(0)
+    logits = np.array([2.0, 1.9, -1.0, 0.5, -3.0], dtype=np.float32)
+    # min_p keeps only tokens with p >= min_p * p_max: at 0.5 only tokens 0 and 1 survive
+    sp = SamplingParams(temperature=1.0, top_k=0, top_p=1.0, min_p=0.5, seed=1)
+    assert {sample_token(logits, sp, rng) for _ in range(200)} == {0, 1}
+    # repeat penalty: positive logits divided, negative multiplied; frequency counts occurrences; presence once
+    sp = SamplingParams(temperature=0.0, repeat_penalty=2.0, presence_penalty=0.25, frequency_penalty=0.5, repeat_last_n=4)
+    hist = [4, 0, 0, 2, 0]           # window = last 4 -> token 0 three times, token 2 once; the leading 4 is outside
+    x = apply_penalties(logits, sp, hist)
+    assert np.allclose(x, [2.0 / 2 - 3 * 0.5 - 0.25, 1.9, -1.0 * 2 - 0.5 - 0.25, 0.5, -3.0])
+    assert not sp.greedy and sp.arg_max                    # decided on the host: the device arg-max sees raw logits
+    assert sample_token(logits, sp, rng, hist) == 1        # token 0 was the raw arg-max
+    assert sample_token(logits, SamplingParams(temperature=0.0), rng, hist) == 0
+    assert SamplingParams(temperature=0.0).greedy
+    # ids outside the vocabulary in the history are ignored
+    assert np.array_equal(apply_penalties(logits, sp, [99, -1]), logits)
