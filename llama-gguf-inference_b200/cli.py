@@ -80,6 +80,25 @@ def main(argv=None) -> int:
         print(VERSION_LINE)
         return 0
     log = Log()
+    # one process per GPU under torchrun: tensor parallelism; rank 0 serves, the others follow (tp_serve.py)
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        args.device = local_rank
+        if rank != 0:
+            from .model import Engine
+            from .tp_serve import follower_loop
+            eng = Engine(args.model, n_ctx=args.ctx_size, device=local_rank, use_graph=not args.no_graph, use_pdl=not args.no_pdl,
+                         n_slots=max(1, args.parallel), tp_rank=rank, tp_size=world)
+            eng.warmup()
+            follower_loop(eng, dist)
+            eng.close()
+            dist.destroy_process_group()
+            return 0
     if unknown:
         log(f"warn: ignoring unsupported arguments: {' '.join(unknown)}")
     if not args.model:
@@ -137,7 +156,8 @@ def main(argv=None) -> int:
         t0 = time.time()
         log(f"main: loading model {args.model}")
         eng = Engine(args.model, n_ctx=args.ctx_size, device=args.device, use_graph=not args.no_graph,
-                     use_pdl=not args.no_pdl, n_slots=max(1, args.parallel), verbose=args.verbose)
+                     use_pdl=not args.no_pdl, n_slots=max(1, args.parallel), verbose=args.verbose,
+                     tp_rank=rank if world > 1 else 0, tp_size=world)
         eng.warmup()
         info.update({"n_layer": eng.hp.n_layer, "n_embd": eng.hp.d, "weights_gb": round(eng.weight_bytes / 1e9, 3)})
         log(f"main: model loaded in {time.time() - t0:.2f} s ({eng.weight_bytes / 1e9:.2f} GB of weights in HBM, "
@@ -146,7 +166,11 @@ def main(argv=None) -> int:
         print(f"error: failed to load model: {e!r}", file=sys.stderr)
         httpd.shutdown()
         return 1
-    sched = Scheduler(eng, tok, ignore_eos=args.ignore_eos, log=log)
+    leader = None
+    if world > 1:
+        from .tp_serve import TPLeader
+        leader = TPLeader(eng, dist)
+    sched = Scheduler(leader or eng, tok, ignore_eos=args.ignore_eos, log=log)
     sched.start()
     state.sched = sched
     state.ready.set()
@@ -160,6 +184,10 @@ def main(argv=None) -> int:
         stop.wait(0.5)
     sched.shutdown()
     httpd.shutdown()
+    if leader is not None:
+        sched.join(timeout=30)
+        leader.shutdown()
+        dist.destroy_process_group()
     log("main: clean exit")
     return 0
 

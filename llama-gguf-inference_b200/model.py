@@ -377,6 +377,11 @@ class Slot:
         self.stream.synchronize()
         return self.host_logits.numpy()
 
+    def logits_tensor(self):
+        """this rank's (vocabulary-sharded under tensor parallelism) logits, on the device, after the stream has drained"""
+        self.stream.synchronize()
+        return self.logits
+
     def tokens(self, n: int) -> list[int]:
         self.stream.synchronize()
         return self.out_tokens[:n].cpu().tolist()

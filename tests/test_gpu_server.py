@@ -77,3 +77,56 @@ def test_llama_server_process_contract_and_parity(oracle, model_dir, tmp_path):
     finally:
         if proc.poll() is None:
             proc.kill()
+
+
+def test_tensor_parallel_llama_server_under_torchrun(oracle, model_dir, tmp_path):
+    """`torchrun --nproc-per-node 2 --no-python bin/llama-server ...`: rank 0 serves HTTP, rank 1 mirrors its engine calls
+    (tp_serve.py); greedy text equals the single-process oracle, a sampled request (which gathers the vocabulary-sharded
+    logits from both ranks) is served too."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from dataclasses import replace
+    from ggufb200 import synth
+    from ggufb200.gguf_reader import GGUFFile
+    from ggufb200.tokenizer import Tokenizer
+    cfg = replace(synth.PRESETS["medium"], n_layer=4, ff=3072)
+    path = os.path.join(model_dir, "tp-serve-medium.gguf")
+    synth.write_gguf(path, cfg, "Q4_K_M", seed=0xB200)
+    keyfile = tmp_path / "backend.key"
+    keyfile.write_text(KEY + "\n")
+    port = free_port()
+    argv = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+            "--master-port", str(free_port()), "--no-python", os.path.join(ROOT, "bin", "llama-server"), "-m", path, "--host", "127.0.0.1",
+            "--port", str(port), "-c", "256", "--api-key-file", str(keyfile), "--parallel", "2", "--temp", "0", "--ignore-eos"]
+    env = dict(os.environ, GGUFB200_PYTHON=sys.executable)
+    proc = subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, start_new_session=True)
+    try:
+        ok = False
+        for _ in range(480):
+            try:
+                st, body = call(port, "GET", "/health", key=None)
+                if st == 200 and body["status"] == "ok":
+                    ok = True
+                    break
+            except OSError:
+                pass
+            assert proc.poll() is None, proc.stdout.read()
+            time.sleep(0.25)
+        assert ok
+        st, body = call(port, "POST", "/v1/chat/completions", {"model": "default", "messages": MSG, "max_tokens": 24})
+        assert st == 200
+        tok = Tokenizer(GGUFFile(path).meta)
+        ids = tok.encode_chat(MSG)
+        ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")
+        assert body["choices"][0]["message"]["content"] == tok.decode(ref.greedy(ids, 24))
+        st, body = call(port, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 8, "temperature": 1.0, "seed": 5})
+        assert st == 200 and body["usage"]["completion_tokens"] == 8
+    finally:
+        if proc.poll() is None:
+            os.killpg(proc.pid, signal.SIGTERM)     # the process group WE started (torchrun + both ranks)
+            try:
+                proc.wait(timeout=60)
+            except subprocess.TimeoutExpired:
+                os.killpg(proc.pid, signal.SIGKILL)

@@ -184,3 +184,39 @@ def test_tensor_parallel_engine_bit_exact_vs_oracle(oracle, model_dir, tmp_path,
     assert list(parts[0]["toks"]) == list(parts[1]["toks"]) == ref_toks
     got = np.concatenate([p["logits"] for p in parts], axis=1)
     assert np.array_equal(got.view(np.uint32), np.stack(ref_logits).view(np.uint32))
+
+
+def _tp_serve_worker(rank, world, port, path, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from fake_engine import OracleEngine
+    from ggufb200.tp_serve import TPLeader, follower_loop
+    eng = OracleEngine(path, n_ctx=64, n_slots=2)
+    if rank == 0:
+        lead = TPLeader(eng, dist)
+        s1, s0 = lead.slots[1], lead.slots[0]
+        s1.reset(); s1.prefill([1, 300, 301, 302]); s1.decode(3)
+        s0.reset(); s0.prefill([1, 400]); s0.feed(305)
+        full = s1.read_logits()
+        assert full.shape[0] == world * eng.slots[1].read_logits().shape[0]      # one shard per rank, concatenated
+        assert np.array_equal(full[: full.shape[0] // world], eng.slots[1].read_logits())
+        lead.shutdown()
+    else:
+        follower_loop(eng, dist)
+    np.savez(os.path.join(out_dir, f"serve{rank}.npz"), past=[s.n_past for s in eng.slots], last=[s.read_last_token() for s in eng.slots])
+    dist.destroy_process_group()
+
+
+def test_tp_serving_followers_mirror_the_leader(model_dir, tmp_path):
+    """rank 0's scheduler calls reach every rank in the same order (tp_serve.py); gloo, 2 processes, stand-in engines"""
+    import torch.multiprocessing as mp
+    from ggufb200 import synth
+    path = os.path.join(model_dir, "tpserve-tiny.gguf")
+    if not os.path.exists(path):
+        synth.write_gguf(path, "tiny", "Q4_K_M", seed=0xB200)
+    mp.spawn(_tp_serve_worker, args=(2, _free_port(), path, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "serve0.npz"), np.load(tmp_path / "serve1.npz")
+    assert list(a["past"]) == list(b["past"]) == [3, 7]
+    assert list(a["last"]) == list(b["last"])
