@@ -55,6 +55,7 @@ class Request:
     sampling: SamplingParams = field(default_factory=SamplingParams)
     stop: list = field(default_factory=list)
     ignore_eos: bool = False
+    cache_prompt: bool = True       # reuse the slot's KV cache for the longest common prefix with its previous sequence
     events: "queue.Queue" = field(default_factory=queue.Queue)   # ("piece", text, token_id) | ("done", reason, usage) | ("error", msg)
     cancelled: threading.Event = field(default_factory=threading.Event)
     t_submit: float = field(default_factory=time.time)
@@ -75,6 +76,15 @@ def apply_penalties(logits: np.ndarray, sp: SamplingParams, history) -> np.ndarr
         x[ids] = np.where(v > 0, v / sp.repeat_penalty, v * sp.repeat_penalty)
     x[ids] -= counts.astype(np.float32) * np.float32(sp.frequency_penalty) + np.float32(sp.presence_penalty)
     return x
+
+
+def _lcp(a, b) -> int:
+    n = 0
+    for x, y in zip(a, b):
+        if x != y:
+            break
+        n += 1
+    return n
 
 
 def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator, history=None) -> int:
@@ -122,6 +132,7 @@ class Scheduler(threading.Thread):
         self.cv = threading.Condition()
         self.active: dict[int, _Active] = {}
         self.stop_flag = False
+        self.slot_tokens: dict[int, list] = {}      # tokens whose K/V a free slot still holds at positions 0..len-1 (prompt cache)
         self.log = log or (lambda *a: None)
         self.stats = {"requests": 0, "prompt_tokens": 0, "completion_tokens": 0, "decode_seconds": 0.0}
         self.fatal: str | None = None
@@ -156,7 +167,9 @@ class Scheduler(threading.Thread):
                     fresh = []
                     while self.pending and len(self.active) < len(self.engine.slots):
                         req = self.pending.popleft()
-                        free = next(i for i in range(len(self.engine.slots)) if i not in self.active)
+                        # the free slot whose cache shares the longest prefix with this prompt (llama-server's slot similarity)
+                        free = max((i for i in range(len(self.engine.slots)) if i not in self.active),
+                                   key=lambda i: (_lcp(self.slot_tokens.get(i, ()), req.prompt_ids) if req.cache_prompt else 0, -i))
                         self.active[free] = _Active(req, self.engine.slots[free], self.tok)
                         fresh.append(free)
                 self._start_many(fresh)
@@ -201,7 +214,7 @@ class Scheduler(threading.Thread):
         for i in fresh:
             a = self.active[i]
             n = len(a.req.prompt_ids)
-            if many is None or n < floor or n + 1 >= a.slot.n_ctx or n > limit:
+            if many is None or n < floor or n + 1 >= a.slot.n_ctx or n > limit or self._reusable_prefix(i):
                 self._start(i)
                 continue
             if group_tokens + n > limit:
@@ -220,8 +233,15 @@ class Scheduler(threading.Thread):
             return
         req.max_tokens = max(0, min(req.max_tokens, n_ctx - len(req.prompt_ids) - 1))
         if not prefilled:
-            slot.reset()
-            slot.prefill(req.prompt_ids)
+            common = self._reusable_prefix(i)
+            slot.reset()                                   # counters only: the K/V of positions < common stay valid
+            if common:
+                slot.prefill(req.prompt_ids[common:], start_pos=common)
+                self.stats["prompt_tokens_cached"] = self.stats.get("prompt_tokens_cached", 0) + common
+            else:
+                slot.prefill(req.prompt_ids)
+        a.fed = list(req.prompt_ids)                       # tokens whose K/V the slot holds
+        self.slot_tokens.pop(i, None)
         self.stats["requests"] += 1
         self.stats["prompt_tokens"] += len(req.prompt_ids)
         a.t_decode0 = time.time()
@@ -229,6 +249,15 @@ class Scheduler(threading.Thread):
             self._finish(i, "length")
             return
         self._emit(i, self._pick(a))
+
+    def _reusable_prefix(self, i: int) -> int:
+        """length of the prompt prefix whose K/V is already in slot i (at least one token is always processed, and short
+        overlaps are not worth a different code path)"""
+        a = self.active[i]
+        if not a.req.cache_prompt:
+            return 0
+        n = min(_lcp(self.slot_tokens.get(i, ()), a.req.prompt_ids), len(a.req.prompt_ids) - 1)
+        return n if n >= 16 else 0
 
     def _pick(self, a: _Active) -> int:
         """token produced by the step that just ran"""
@@ -247,6 +276,7 @@ class Scheduler(threading.Thread):
             a.slot.decode(1)            # the device already holds the next token, its position and embedding
         else:
             a.slot.feed(a.last_tok)     # sampled on the host, or the slot last advanced inside a batch
+        a.fed.append(a.last_tok)
         self._emit(i, self._pick(a))
 
     def _step_batch(self, live: list[int]):
@@ -262,6 +292,8 @@ class Scheduler(threading.Thread):
         bd = self.engine.batch
         acts = [self.active[i] for i in live]
         toks = bd.step([(a.slot.index, a.last_tok, a.slot.n_past) for a in acts])
+        for a in acts:
+            a.fed.append(a.last_tok)
         self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
         self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
         for b, (i, a) in enumerate(zip(live, acts)):
@@ -309,6 +341,8 @@ class Scheduler(threading.Thread):
 
     def _finish(self, i: int, reason: str):
         a = self.active.pop(i)
+        if getattr(a, "fed", None):
+            self.slot_tokens[i] = a.fed                    # what the next request on this slot may reuse
         dt = time.time() - getattr(a, "t_decode0", a.t_start)
         self.stats["completion_tokens"] += a.n_gen
         self.stats["decode_seconds"] += dt

@@ -189,7 +189,8 @@ class Handler(BaseHTTPRequestHandler):
         if isinstance(stop, str):
             stop = [stop]
         stop = [s for s in stop if isinstance(s, str) and s]
-        return Request(prompt_ids=ids, max_tokens=max_tokens, sampling=sp, stop=stop, ignore_eos=bool(body.get("ignore_eos", False)))
+        return Request(prompt_ids=ids, max_tokens=max_tokens, sampling=sp, stop=stop, ignore_eos=bool(body.get("ignore_eos", False)),
+                       cache_prompt=bool(body.get("cache_prompt", True)))
 
     def _completion(self, body: dict, chat: bool):
         st = self.state

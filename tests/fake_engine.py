@@ -15,10 +15,11 @@ class OracleSlot:
         self.chain_valid = True
 
     def reset(self):
-        self.m.reset()
-        self.n_past = 0
+        self.n_past = 0          # like the GPU slot: counters only, the K/V of earlier positions stays (prompt cache)
 
     def prefill(self, tokens, start_pos=None):
+        if start_pos is not None:
+            self.n_past = start_pos
         if self.n_past + len(tokens) >= self.n_ctx:
             raise ValueError("context")
         for t in tokens:

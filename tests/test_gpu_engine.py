@@ -321,3 +321,23 @@ def test_chunked_long_prompt_prefill_matches_single_chunk(oracle, model_dir):
     assert out["exact"][1] == want[0][0]
     assert np.array_equal(_bits(ref), _bits(want[1][0]))
     eng.close()
+
+
+def test_prefix_reuse_equals_cold_prefill(oracle, model_dir):
+    """the scheduler's prompt cache: reset() keeps the K/V, prefill(suffix, start_pos=n) continues behind a prefix that
+    an earlier sequence left in the slot -- bit-identical to processing the whole prompt"""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "small", "Q4_K_M")
+    eng = Engine(path, n_ctx=128)
+    eng.warmup()
+    eng.gemm_prefill_min = 10 ** 9                 # exact path
+    prefix = [1] + list(range(300, 330))
+    a, b = prefix + [400, 401, 402], prefix + [500, 501, 502, 503, 504]
+    sl = eng.slots[0]
+    sl.reset(); sl.prefill(b); sl.decode(5)
+    cold = (sl.tokens(6), sl.last_logits().copy())
+    sl.reset(); sl.prefill(a); sl.decode(9)         # another sequence with the same prefix (and a longer tail in the cache)
+    sl.reset(); sl.prefill(b[len(prefix):], start_pos=len(prefix)); sl.decode(5)
+    assert sl.tokens(6) == cold[0]
+    assert np.array_equal(_bits(sl.last_logits()), _bits(cold[1]))
+    eng.close()

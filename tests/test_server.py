@@ -251,3 +251,24 @@ def test_unchanged_reference_gateway_and_benchmark_in_front(oracle, backend):
     finally:
         gw.terminate()
         gw.wait(timeout=10)
+
+
+def test_prompt_cache_reuses_the_common_prefix(oracle, backend):
+    """a follow-up request whose prompt starts like the previous one only processes the new tokens (llama-server's
+    cache_prompt); the text must be what a cold run of the full prompt gives"""
+    p = backend["port"]
+    sched = backend["state"].sched
+    first = [{"role": "user", "content": "Hi"}]            # the test backend has a 160-token context
+    st, r1 = call(p, "POST", "/v1/chat/completions", {"messages": first, "max_tokens": 4, "temperature": 0})
+    assert st == 200
+    follow = first + [{"role": "assistant", "content": r1["choices"][0]["message"]["content"]}, {"role": "user", "content": "Go"}]
+    before = sched.stats.get("prompt_tokens_cached", 0)
+    st, r2 = call(p, "POST", "/v1/chat/completions", {"messages": follow, "max_tokens": 10, "temperature": 0})
+    assert st == 200, r2
+    assert sched.stats.get("prompt_tokens_cached", 0) - before >= 16
+    want, n_prompt = expected_text(oracle, backend, follow, 10)
+    assert r2["choices"][0]["message"]["content"] == want and r2["usage"]["prompt_tokens"] == n_prompt
+    before = sched.stats.get("prompt_tokens_cached", 0)
+    r3 = call(p, "POST", "/v1/chat/completions", {"messages": follow, "max_tokens": 10, "temperature": 0, "cache_prompt": False})[1]
+    assert sched.stats.get("prompt_tokens_cached", 0) == before
+    assert r3["choices"][0]["message"]["content"] == want
