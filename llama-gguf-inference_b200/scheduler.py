@@ -201,9 +201,15 @@ class Scheduler(threading.Thread):
         def flush():
             nonlocal group, group_tokens
             if len(group) > 1:
+                jobs = []
                 for i in group:
-                    self.active[i].slot.reset()
-                many([(self.active[i].slot.index, self.active[i].req.prompt_ids, 0) for i in group])
+                    a = self.active[i]
+                    common = self._reusable_prefix(i)
+                    a.slot.reset()                         # counters only: cached K/V below `common` stays
+                    jobs.append((a.slot.index, a.req.prompt_ids[common:], common))
+                    if common:
+                        self.stats["prompt_tokens_cached"] = self.stats.get("prompt_tokens_cached", 0) + common
+                many(jobs)
                 for i in group:
                     self._start(i, prefilled=True)
             else:
@@ -213,8 +219,8 @@ class Scheduler(threading.Thread):
 
         for i in fresh:
             a = self.active[i]
-            n = len(a.req.prompt_ids)
-            if many is None or n < floor or n + 1 >= a.slot.n_ctx or n > limit or self._reusable_prefix(i):
+            n = len(a.req.prompt_ids) - self._reusable_prefix(i)      # tokens that actually have to be processed
+            if many is None or n < floor or len(a.req.prompt_ids) + 1 >= a.slot.n_ctx or n > limit:
                 self._start(i)
                 continue
             if group_tokens + n > limit:

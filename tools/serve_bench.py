@@ -29,9 +29,10 @@ def free_port():
     return p
 
 
-def stream_one(port, idx, max_tokens, out):
+def stream_one(port, idx, max_tokens, out, rep=0):
+    # the round number comes first: no two requests share a prefix long enough for the server's prompt cache
     body = {"model": "default", "stream": True, "max_tokens": max_tokens, "temperature": 0,
-            "messages": [{"role": "user", "content": f"Request {idx}: write a short story about the number {idx}."}]}
+            "messages": [{"role": "user", "content": f"{rep}/{idx}: write a short story about the number {idx}, round {rep}."}]}
     c = http.client.HTTPConnection("127.0.0.1", port, timeout=600)
     t0 = time.perf_counter()
     c.request("POST", "/v1/chat/completions", json.dumps(body), {"Content-Type": "application/json", "Authorization": f"Bearer {KEY}"})
@@ -89,7 +90,7 @@ def main():
         for n in levels:
             for rep in range(2):      # first round warms up (graph capture for this batch size); the second is reported
                 out = {}
-                ts = [threading.Thread(target=stream_one, args=(port, i, args.max_tokens, out)) for i in range(n)]
+                ts = [threading.Thread(target=stream_one, args=(port, i, args.max_tokens, out, rep)) for i in range(n)]
                 t0 = time.perf_counter()
                 [t.start() for t in ts]
                 [t.join() for t in ts]
