@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libggufb200.so")
+LIB = os.environ.get("GGB_LIB_OUT") or os.path.join(HERE, "libggufb200.so")   # GGB_LIB_OUT: experiment builds (tools/)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -47,7 +47,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not os.environ.get("GGB_LIB_OUT") else "build_" + os.path.basename(LIB).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)

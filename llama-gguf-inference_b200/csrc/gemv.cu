@@ -31,6 +31,7 @@
 #include "layout.cuh"
 #include "gemv_common.cuh"
 #include "peer.cuh"
+#include "prefetch.cuh"
 
 #ifndef GEMV_NW
 #define GEMV_NW 8                          /* warps per CTA */
@@ -79,6 +80,7 @@ struct GemvK {
     int peer_n, peer_rank;
     int64_t peer_d_cap;
     uint64_t peer_base[GGB_PEER_MAX];
+    PfSet pf;                  /* L2 prefetch of later launches' weights (prefetch.cuh) */
 };
 
 // ------------------------------------------------------------------ optional in-kernel timeline (debug builds only)
@@ -101,7 +103,7 @@ __device__ __forceinline__ void argmax_comb(float& v, int& i, float ov, int oi) 
 
 // MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0, bit3 Q5_K segments present (dead-code elimination per launch shape)
 template <int MASK, int R, int STEPS>
-__global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const __grid_constant__ GemvK P) {
+__global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kernel(const __grid_constant__ GemvK P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ double red[GEMV_NW];
     __shared__ float s_val[GEMV_NW];
@@ -198,6 +200,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
         for (int i = 0; i < STEPS; i++) if (ip < npairs) issue_step();
     }
 
+    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AT_START, c, warp, GEMV_NW);
+
     // the RMSNorm gains are weights too: fetch this lane's eight for the warp's first 256-block now
     float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
     if (P.pro == GGB_PRO_RMSNORM && warp < K / 256) {
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
     // prologues of the running launch: 505 vs 543 tok/s.  Triggering after the prologue instead: no difference.
     pdl_launch_dependents();
     TL_STAMP(2);
+    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AFTER_WAIT, c, warp, GEMV_NW);
 
     // epilogue operands that only depend on the previous phase: request them now, use them at the end
     float res_pre = 0.f;
@@ -304,6 +309,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
             if (lane < U) A = load_act<MASK>(type, t * 32 + lane, qs_s, bs_s, dsc_s);
             const uint32_t slot0 = ring0 + cstage * R * SLOT;
             mbar_wait(bar0 + 8 * cstage, cphase);
+#ifndef GGB_NO_INTERLEAVE
+            if (full && nv == R) {   /* common case, branch-free: the R rows' dependency chains can be interleaved */
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] += consume<MASK, true>(type, slot0 + r * SLOT, lane, 32, GGB_TILE_SB, A, L);
+            } else
+#endif
             if (full) {
 #pragma unroll
                 for (int r = 0; r < R; r++)
@@ -346,6 +357,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) gemv_kernel(const
             }
         }
     }
+    // this warp has no demand loads left: pull the next launch's weights towards L2 while the slower CTAs finish, the
+    // dependency is handed over and the next prologue runs (HBM would idle through all three)
+    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AT_TAIL, c, warp, GEMV_NW);
     __syncthreads();
     TL_STAMP(4);
 
@@ -458,11 +472,11 @@ template <int MASK, int R, int STEPS>
 static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK, R, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMV_MAX_SMEM));
+        GGB_CUDA(cudaFuncSetAttribute(ggb_dq_gemv_kernel<MASK, R, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMV_MAX_SMEM));
         // every decode kernel asks for the SAME (maximal) shared-memory carveout: an SM whose L1/shared split differs from
         // what the next launch prefers must drain before it is reconfigured, which silently defeats the PDL co-residency
         // (in-situ timeline: only launches with equal footprints overlapped)
-        GGB_CUDA(cudaFuncSetAttribute(gemv_kernel<MASK, R, STEPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        GGB_CUDA(cudaFuncSetAttribute(ggb_dq_gemv_kernel<MASK, R, STEPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -475,11 +489,12 @@ static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_kernel<MASK, R, STEPS>, P));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, ggb_dq_gemv_kernel<MASK, R, STEPS>, P));
     return GGB_OK;
 }
 
 static thread_local int64_t* g_smem_query = nullptr;   /* ggb_gemv_smem_bytes: plan only, report the shared memory, do not launch */
+static thread_local int64_t* g_ring_query = nullptr;   /* ggb_gemv_ring_bytes: likewise, the bytes of one CTA's weight rings */
 
 extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     if (!a) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: null args");
@@ -552,6 +567,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     P.kcache = a->kcache; P.vcache = a->vcache; P.part_val = a->part_val; P.part_idx = a->part_idx;
     P.peer_n = a->peer_n; P.peer_rank = a->peer_rank; P.peer_d_cap = a->peer_d_cap;
     for (int p = 0; p < GGB_PEER_MAX; p++) P.peer_base[p] = a->peer_base[p];
+    P.pf = make_pfset(a->pf);
     // ring geometry: RING_SLOTS slots sized for the largest tile of the launch
     P.slot_bytes = (max_tile + 15) & ~15;
     const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;   /* any mix with Q5_K: generic R=2, STEPS=2 */
@@ -573,6 +589,7 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     // is otherwise placed unevenly -- two CTAs here, none there -- and so is everything launched behind it.
     if (a->min_smem > 0 && smem < (size_t)a->min_smem && (size_t)a->min_smem <= GEMV_MAX_SMEM) smem = (size_t)a->min_smem;
     if (smem > GEMV_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
+    if (g_ring_query) { *g_ring_query = (P.T <= STEPS) ? (int64_t)GEMV_NW * P.ring_bytes : 0; return GGB_OK; }
     if (g_smem_query) { *g_smem_query = (int64_t)smem; return GGB_OK; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (mask) {
@@ -594,3 +611,14 @@ extern "C" int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* a) {
     return rc == GGB_OK ? v : (int64_t)rc;
 }
 
+
+// Bytes at the START of every CTA's weight slice that the per-warp rings request before the dependency wait (0 when the
+// rows have more K-tiles than ring stages, i.e. the ring holds scattered tiles rather than a prefix of the slice): what
+// an L2 prefetch on behalf of this launch may skip (ggb_prefetch.skip).
+extern "C" int64_t ggb_gemv_ring_bytes(const ggb_gemv_args* a) {
+    int64_t v = 0;
+    g_ring_query = &v;
+    const int rc = ggb_gemv(a, nullptr);
+    g_ring_query = nullptr;
+    return rc == GGB_OK ? v : (int64_t)rc;
+}

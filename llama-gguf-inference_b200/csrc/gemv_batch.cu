@@ -141,7 +141,7 @@ __device__ __forceinline__ void warp_reduce_many(double (&v)[N], int lane) {
 // MASK: bit0 Q4_K, bit1 Q6_K, bit2 Q8_0, bit3 Q5_K segments present; NBT = tokens per launch (compile-time upper bound, the
 // images of tokens >= nb are zero-filled by the prologue)
 template <int MASK, int NBT, int R>
-__global__ void __launch_bounds__(GB_THREADS, 1) gemv_batch_kernel(const __grid_constant__ GemvBK P) {
+__global__ void __launch_bounds__(GB_THREADS, 1) ggb_dq_gemv_batch_kernel(const __grid_constant__ GemvBK P) {
     constexpr int STEPS = GB_STEPS;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[GB_NW][STEPS];
@@ -461,13 +461,13 @@ template <int MASK, int NBT, int R>
 static int launch_b(const GemvBK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        GGB_CUDA(cudaFuncSetAttribute(gemv_batch_kernel<MASK, NBT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_MAX_SMEM));
+        GGB_CUDA(cudaFuncSetAttribute(ggb_dq_gemv_batch_kernel<MASK, NBT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_MAX_SMEM));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     launch_cfg(cfg, at, dim3(grid), dim3(GB_THREADS), smem, use_pdl, st);
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_batch_kernel<MASK, NBT, R>, P));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, ggb_dq_gemv_batch_kernel<MASK, NBT, R>, P));
     return GGB_OK;
 }
 

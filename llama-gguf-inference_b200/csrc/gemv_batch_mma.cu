@@ -62,7 +62,7 @@ struct GbmCtx { int r0[GGB_MAX_SEG], cnt[GGB_MAX_SEG], ng[GGB_MAX_SEG], ngroups;
 
 // NT = 8-token n-tiles per launch (1: <= 8 tokens, 2: <= 16)
 template <int NT>
-__global__ void __launch_bounds__(GBM_THREADS, 1) gemv_batch_mma_kernel(const __grid_constant__ GbmK P) {
+__global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(const __grid_constant__ GbmK P) {
     constexpr int NBT = 8 * NT;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[GBM_MAX_STAGES], s_empty[GBM_MAX_STAGES], s_abar;
@@ -294,7 +294,7 @@ template <int NT>
 static int gbm_launch_nt(const GbmK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        GGB_CUDA(cudaFuncSetAttribute(gemv_batch_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBM_MAX_SMEM));
+        GGB_CUDA(cudaFuncSetAttribute(ggb_dq_gemv_batch_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBM_MAX_SMEM));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -303,7 +303,7 @@ static int gbm_launch_nt(const GbmK& P, int grid, size_t smem, int use_pdl, cuda
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, gemv_batch_mma_kernel<NT>, P));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, ggb_dq_gemv_batch_mma_kernel<NT>, P));
     return GGB_OK;
 }
 

@@ -173,36 +173,31 @@ class Slot:
             self._attn_pdl.append(self.use_pdl | trig)
             self._layer_args.append((qkv, o, gu, dn))
         self._head = self._head_args()
-        self._mega = None
-        if e.use_mega:
-            self._build_mega()
+        self._plan_prefetch()
 
-    def _build_mega(self):
-        """One persistent cooperative launch per token (csrc/mega.cu) instead of ~160: the same phase descriptions,
-        handed over as a table."""
-        torch, lib, hp, e = self.torch, self.lib, self.hp, self.eng
-        phases, attn = [], []
-        for qkv, o, gu, dn in self._layer_args:
-            phases += [qkv, o, gu, dn]
-            attn += [self.attn.data_ptr(), 0, 0, 0]
-        phases.append(self._head)
-        attn.append(0)
-        n = len(phases)
-        self._mega_plan = torch.zeros(lib.ggb_mega_plan_bytes(n), dtype=torch.uint8, device=e.dev)
-        self._mega_bar = torch.zeros(4, dtype=torch.int32, device=e.dev)
-        arr = (cabi.GemvArgs * n)(*phases)
-        att = (C.c_void_p * n)(*attn)
-        mask = C.c_int32()
-        torch.cuda.synchronize()
-        cabi.check(lib.ggb_mega_plan(arr, att, n, self._mega_plan.data_ptr(), C.byref(mask)), "mega_plan")
-        m = cabi.MegaArgs()
-        m.plan, m.n_phases, m.type_mask = self._mega_plan.data_ptr(), n, mask.value
-        m.barrier, m.pos_dev, m.rope_tab = self._mega_bar.data_ptr(), self.pos_dev.data_ptr(), e.rope_tab.data_ptr()
-        m.n_rot, m.head_dim, m.n_head, m.n_kv, m.n_ctx = hp.n_rot, hp.head_dim, self.nh, self.nkv, self.n_ctx
-        m.k_max = max(a.k for a in phases)
-        m.rows_max = max(sum(a.seg[i].rows for i in range(a.n_seg)) for a in phases)
-        m.part_val, m.part_idx = self.part_val.data_ptr(), self.part_idx.data_ptr()
-        self._mega = m
+    def _plan_prefetch(self):
+        """L2 prefetch plan of the decode chain (include/ggufb200.h: ggb_prefetch).  Every GEMV launch pulls, when its
+        warps run out of rows, the next GGB_PF_TAIL_KB (per CTA) of the NEXT launch's weight stream into L2 -- HBM would
+        otherwise idle through the exit spread, the dependency hand-over and the next prologue; the attention, which
+        reads a few hundred KB, does the same for the gate/up projection (GGB_PF_ATTN_KB).  0 disables either."""
+        lib = self.lib
+        tail = int(os.environ.get("GGB_PF_TAIL_KB", "0")) * 1024
+        attn = int(os.environ.get("GGB_PF_ATTN_KB", "0")) * 1024
+        when = int(os.environ.get("GGB_PF_WHEN", str(cabi.PF_AT_TAIL)))
+        self._attn_pf = [None] * len(self._layer_args)
+        if not (tail or attn):
+            return
+        chain = [a for quad in self._layer_args for a in quad] + [self._head]
+        skip = [max(0, lib.ggb_gemv_ring_bytes(C.byref(a))) for a in chain]
+        for i, a in enumerate(chain[:-1]):
+            extra = attn if (i % 4 == 1) else 0     # the output projection: the attention took the first part of gate/up
+            if tail:
+                cabi.fill_prefetch(a.pf[0], chain[i + 1], skip[i + 1] + extra, tail, when)
+        if attn:
+            for l in range(len(self._layer_args)):
+                pf = (cabi.Prefetch * cabi.PF_MAX)()
+                cabi.fill_prefetch(pf[0], chain[4 * l + 2], skip[4 * l + 2], attn, cabi.PF_AFTER_WAIT)
+                self._attn_pf[l] = pf
 
     # ------------------------------------------------------------------ enqueue
     def _enqueue_embed(self, s: int):
@@ -225,9 +220,10 @@ class Slot:
         tp = self.eng.tp_size > 1
         for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
             cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
-            cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
-                                           self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
-                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i], s), "attn_decode")
+            cabi.check(lib.ggb_attn_decode_pf(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                                              self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
+                                              self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i],
+                                              self._attn_pf[i], s), "attn_decode")
             cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
             if tp:
                 self._allreduce_residual(s)
@@ -252,14 +248,6 @@ class Slot:
                                        self.out_tokens.data_ptr(), self.max_new, e.emb_type,
                                        e.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
 
-    def _enqueue_mega(self, s: int):
-        lib, e = self.lib, self.eng
-        cabi.check(lib.ggb_mega_run(C.byref(self._mega), s), "mega_run")
-        cabi.check(lib.ggb_argmax_next(self.part_val.data_ptr(), self.part_idx.data_ptr(), self.n_part,
-                                       self.tok_dev.data_ptr(), self.pos_dev.data_ptr(), self.step_dev.data_ptr(),
-                                       self.out_tokens.data_ptr(), self.max_new, e.emb_type,
-                                       e.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
-
     def _run(self, kind: str):
         """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head)."""
         torch = self.torch
@@ -267,9 +255,6 @@ class Slot:
         def body(s):
             if kind != "decode":
                 self._enqueue_embed(s)
-            if self._mega is not None and kind != "prompt":
-                self._enqueue_mega(s)
-                return
             self._enqueue_layers(s)
             if kind != "prompt":
                 self._enqueue_head(s)
@@ -435,8 +420,6 @@ class Engine:
             self.dist = dist
         self.n_ctx = int(n_ctx)
         self.max_new = max_new
-        # one persistent launch per token (csrc/mega.cu); needs the single-CTA attention's context limit
-        self.use_mega = (os.environ.get("GGB_MEGA", "0") == "1" and self.tp_size == 1 and self.n_ctx <= 4096)
         self.peer = None
         if self.tp_size > 1 and os.environ.get("GGB_TP_EXCHANGE", "peer") != "nccl":
             self._setup_peer_exchange()

@@ -249,21 +249,6 @@ def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("preset,ftype", [("small", "Q4_K_M"), ("medium", "Q8_0"), ("medium", "Q6_K"), ("small", "Q5_K_M")])
-def test_persistent_per_token_kernel_is_bit_identical(oracle, model_dir, preset, ftype, monkeypatch):
-    """csrc/mega.cu (GGB_MEGA=1): all phases of a token in one cooperative launch, grid barriers instead of kernel
-    boundaries, rings prefetching across phases -- same tokens, same logits as the oracle / the multi-kernel graph."""
-    path = _model(model_dir, preset, ftype)
-    n_new = 24
-    monkeypatch.setenv("GGB_MEGA", "1")
-    toks, logits = _gpu_run(path, n_new)
-    ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")
-    ref_toks, ref_logits = ref.greedy(PROMPT, n_new, return_logits=True)
-    assert toks == ref_toks
-    for got, want in zip(logits, ref_logits):
-        assert np.array_equal(_bits(got), _bits(want))
-
-
 def test_multi_sequence_gemm_prefill_equals_per_sequence_prefill(oracle, model_dir):
     """Engine.prefill_many: the prompts of several requests in ONE pass of tensor-core GEMMs (per-token slot/position for
     RoPE and the KV write, attention per sequence) must leave every slot where its own prefill would."""
