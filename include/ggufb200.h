@@ -105,25 +105,6 @@ typedef struct ggb_gemv_seg {
     float* y;        /* output vector of this segment (f32) or NULL when the epilogue consumes it */
 } ggb_gemv_seg;
 
-/* L2 prefetch of weights a LATER launch will stream (csrc/prefetch.cuh).  The decode chain is a sequence of
- * dependent launches; between two of them (exit spread, dependency hand-over, activation prologue, the attention) HBM
- * would idle.  A launch can therefore be told to pull the next bytes of a following launch's weight stream into the
- * 126 MB L2 with cp.async.bulk.prefetch.L2 (SASS UBLKPF): CTA c prefetches the window [skip, skip + bytes) of the
- * byte range consumer CTA c will stream (its row slice of segment 0, then 1, then 2).  A hint: results never change. */
-#define GGB_PF_MAX 2
-#define GGB_PF_AT_START 1   /* issue before the dependency wait (right after the own ring fill) */
-#define GGB_PF_AFTER_WAIT 2 /* issue right after the dependency wait */
-#define GGB_PF_AT_TAIL 4    /* each warp issues its share when it has finished its own rows */
-typedef struct ggb_prefetch {
-    int32_t n_seg;             /* 0 = nothing */
-    int32_t grid;              /* CTAs of the consumer launch (ggb_gemv_grid) */
-    const void* w[GGB_MAX_SEG];
-    int64_t row_bytes[GGB_MAX_SEG];
-    int32_t rows[GGB_MAX_SEG];
-    int32_t when;              /* GGB_PF_* */
-    int64_t skip, bytes;       /* window per consumer CTA, multiples of 16 */
-} ggb_prefetch;
-
 typedef struct ggb_gemv_args {
     int32_t n_seg;
     int32_t k;                 /* shared inner dimension, multiple of 256 */
@@ -153,16 +134,12 @@ typedef struct ggb_gemv_args {
      * memory two CTAs of the launch can never share an SM, which keeps the placement even when it becomes resident while
      * another kernel's small CTAs are still running (the output projection behind the attention) */
     int32_t min_smem;
-    ggb_prefetch pf[GGB_PF_MAX];   /* optional L2 prefetch of later launches' weights */
 } ggb_gemv_args;
 
 int ggb_gemv(const ggb_gemv_args* args, void* stream);
 /* dynamic shared memory ggb_gemv would request for these args (the host uses it to decide which adjacent launches can
  * be co-resident); negative = error code */
 int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* args);
-/* bytes at the start of every CTA's weight slice that the launch's own rings request before its dependency wait
- * (what a ggb_prefetch on its behalf may skip); 0 when the ring does not hold a prefix of the slice */
-int64_t ggb_gemv_ring_bytes(const ggb_gemv_args* args);
 /* number of CTAs ggb_gemv will launch for these args (size of part_val/part_idx) */
 int ggb_gemv_grid(const ggb_gemv_args* args);
 
@@ -224,11 +201,6 @@ int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_de
 size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim);
 int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
                     int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream);
-/* the same launch, additionally prefetching later launches' weights into L2 once its dependency wait has returned
- * (HBM is otherwise idle while the attention runs); pf = GGB_PF_MAX entries or NULL */
-int ggb_attn_decode_pf(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
-                       int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl,
-                       const ggb_prefetch* pf, void* stream);
 
 /* ---- small-batch decode: several sequences ("slots"), ONE new token each, in one pass over the weights.
  * Stands in for llama-server's continuous batching (ggml mul_mat with a few activation columns); the arithmetic

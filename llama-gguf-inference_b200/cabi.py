@@ -22,9 +22,9 @@ EXPORTS = [
     "ggb_abi_version", "ggb_last_error", "ggb_device_info",
     "ggb_dequant", "ggb_repacked_row_stride", "ggb_repack", "ggb_dequant_repacked",
     "ggb_quantize_q8_K", "ggb_quantize_q8_0",
-    "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemv_ring_bytes", "ggb_gemm", "ggb_f32_to_bf16",
+    "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemm", "ggb_f32_to_bf16",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
-    "ggb_attn_decode_ws_bytes", "ggb_attn_decode", "ggb_attn_decode_pf",
+    "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
     "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
@@ -38,18 +38,6 @@ class GGBError(RuntimeError):
 
 class GemvSeg(C.Structure):
     _fields_ = [("w", C.c_void_p), ("type", C.c_int32), ("rows", C.c_int32), ("y", C.c_void_p)]
-
-
-PF_MAX = 2
-PF_AT_START, PF_AFTER_WAIT, PF_AT_TAIL = 1, 2, 4
-
-
-class Prefetch(C.Structure):
-    _fields_ = [
-        ("n_seg", C.c_int32), ("grid", C.c_int32),
-        ("w", C.c_void_p * MAX_SEG), ("row_bytes", C.c_int64 * MAX_SEG), ("rows", C.c_int32 * MAX_SEG),
-        ("when", C.c_int32), ("skip", C.c_int64), ("bytes", C.c_int64),
-    ]
 
 
 class GemvArgs(C.Structure):
@@ -67,7 +55,6 @@ class GemvArgs(C.Structure):
         ("grid", C.c_int32),
         ("peer_n", C.c_int32), ("peer_rank", C.c_int32), ("peer_d_cap", C.c_int64), ("peer_base", C.c_uint64 * PEER_MAX),
         ("min_smem", C.c_int32),
-        ("pf", Prefetch * PF_MAX),
     ]
 
 
@@ -106,7 +93,6 @@ def lib() -> C.CDLL:
         "ggb_gemv": ([C.POINTER(GemvArgs), vp], i32),
         "ggb_gemv_grid": ([C.POINTER(GemvArgs)], i32),
         "ggb_gemv_smem_bytes": ([C.POINTER(GemvArgs)], i64),
-        "ggb_gemv_ring_bytes": ([C.POINTER(GemvArgs)], i64),
         "ggb_gemm": ([i32, vp, i32, i32, vp, i32, vp, i64, vp], i32),
         "ggb_f32_to_bf16": ([vp, vp, i64, vp], i32),
         "ggb_embed_row": ([i32, vp, i64, vp, vp, vp], i32),
@@ -116,7 +102,6 @@ def lib() -> C.CDLL:
         "ggb_argmax": ([vp, i64, vp, vp], i32),
         "ggb_attn_decode_ws_bytes": ([i32, i32], sz),
         "ggb_attn_decode": ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp], i32),
-        "ggb_attn_decode_pf": ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, C.POINTER(Prefetch), vp], i32),
         "ggb_residual_add_f64": ([vp, vp, i64, i32, vp], i32),
         "ggb_embed_rows": ([i32, vp, i64, vp, i32, vp, vp], i32),
         "ggb_rope_kv_prefill": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
@@ -191,14 +176,3 @@ def make_gemv_batch_args(segs, k, act, nb, *, epilogue=EPI_STORE, residual=0, us
         a.seg[i].w, a.seg[i].type, a.seg[i].rows, a.seg[i].y = w, t, rows, y
     a.epilogue, a.nb, a.act, a.residual, a.use_pdl, a.grid = epilogue, nb, act, residual, use_pdl, grid
     return a
-
-
-def fill_prefetch(pf: Prefetch, consumer: GemvArgs, skip: int, nbytes: int, when: int) -> None:
-    """Describe the window [skip, skip + nbytes) of every consumer CTA's weight stream (ggb_prefetch)."""
-    L = lib()
-    pf.n_seg, pf.grid, pf.when = consumer.n_seg, L.ggb_gemv_grid(C.byref(consumer)), when
-    for i in range(consumer.n_seg):
-        pf.w[i] = consumer.seg[i].w
-        pf.row_bytes[i] = L.ggb_repacked_row_stride(consumer.seg[i].type, consumer.k)
-        pf.rows[i] = consumer.seg[i].rows
-    pf.skip, pf.bytes = int(skip) & ~15, int(nbytes) & ~15

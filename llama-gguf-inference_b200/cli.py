@@ -165,6 +165,8 @@ def main(argv=None) -> int:
     except Exception as e:
         print(f"error: failed to load model: {e!r}", file=sys.stderr)
         httpd.shutdown()
+        if world > 1:   # followers that did load are blocked in their command broadcast: release them
+            _tp_release(dist)
         return 1
     leader = None
     if world > 1:
@@ -180,6 +182,8 @@ def main(argv=None) -> int:
         if not sched.is_alive():
             log("main: the scheduler thread died (engine failure), exiting")
             httpd.shutdown()
+            if leader is not None:
+                _tp_release(dist, leader)
             return 1
         stop.wait(0.5)
     sched.shutdown()
@@ -190,6 +194,19 @@ def main(argv=None) -> int:
         dist.destroy_process_group()
     log("main: clean exit")
     return 0
+
+
+def _tp_release(dist, leader=None):
+    """rank 0 is leaving on an error path: tell the follower ranks to stop (they wait in broadcast_object_list and would
+    otherwise hold their GPUs until the NCCL timeout) and tear the process group down; best effort, never raises"""
+    try:
+        if leader is not None:
+            leader.shutdown()
+        else:
+            dist.broadcast_object_list([("stop",)], src=0)
+        dist.destroy_process_group()
+    except Exception as e:  # the collective itself may be what failed
+        print(f"warn: could not release the tensor-parallel followers: {e!r}", file=sys.stderr)
 
 
 if __name__ == "__main__":

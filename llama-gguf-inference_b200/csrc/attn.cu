@@ -18,7 +18,6 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "prefetch.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -41,7 +40,7 @@ template <int HD, int CL, int NW>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NW * 32)
 attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                    const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
-                   const int32_t* __restrict__ slot_dev, int64_t slot_stride, int trigger, const __grid_constant__ PfSet pf) {
+                   const int32_t* __restrict__ slot_dev, int64_t slot_stride, int trigger) {
     constexpr int LPG = HD / 8;        // lanes per position (each lane owns 8 consecutive dims = one 16-byte load)
     constexpr int PPW = 32 / LPG;      // positions per warp step
     constexpr int SLOTS = NW * PPW;
@@ -97,8 +96,6 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     // them inherits the imbalance, and the step gets 10 % slower (485 tok/s; tools/step_timeline.py shows entry times
     // spread over 20 us).  Hence a flag, set by the host when it has padded the projection.
     if (trigger) pdl_launch_dependents();
-    // HBM idles while the attention runs (it reads a few hundred KB of cache): pull later launches' weights into L2
-    if (lane == 0 && blockIdx.y == 0) l2_prefetch_set(pf, GGB_PF_AFTER_WAIT | GGB_PF_AT_START | GGB_PF_AT_TAIL, blockIdx.x, warp, NW);
 
     float qr[8];
     {
@@ -229,7 +226,7 @@ extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
 template <int HD, int CL, int NW = ATTN_WARPS_BATCH>
 static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
                        int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev = nullptr, int64_t slot_stride = 0,
-                       int nb = 1, const ggb_prefetch* pfh = nullptr) {
+                       int nb = 1) {
     const int trigger = (use_pdl & 2) ? 1 : 0;
     int chunk_max = (n_ctx + CL - 1) / CL;
     chunk_max = (chunk_max + 7) & ~7;
@@ -251,28 +248,22 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = (use_pdl & 1) ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL, NW>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride, trigger, make_pfset(pfh)));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<HD, CL, NW>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride, trigger));
     return GGB_OK;
 }
 
 extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
                                int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream) {
-    return ggb_attn_decode_pf(q, kcache, vcache, pos_dev, n_head, n_kv, head_dim, n_ctx, ws, out, use_pdl, nullptr, stream);
-}
-
-extern "C" int ggb_attn_decode_pf(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
-                                  int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl,
-                                  const ggb_prefetch* pf, void* stream) {
     (void)ws;
     if (!q || !kcache || !vcache || !pos_dev || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: null pointer");
     if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
     if (n_ctx <= 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_ctx must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     static const int cl1 = []() { const char* v = getenv("GGB_ATTN_CL"); return v && *v ? atoi(v) : 0; }();
-    if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, nullptr, 0, 1, pf);
-    if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, nullptr, 0, 1, pf);
-    if (head_dim == 128) return launch_attn<128, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, nullptr, 0, 1, pf);
-    if (head_dim == 64) return launch_attn<64, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, nullptr, 0, 1, pf);
+    if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 128) return launch_attn<128, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    if (head_dim == 64) return launch_attn<64, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_decode: head_dim=%d (supported: 64, 128)", head_dim);
 }
 

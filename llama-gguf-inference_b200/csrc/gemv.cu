@@ -26,12 +26,13 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "actquant.cuh"
 #include "common.cuh"
 #include "layout.cuh"
 #include "gemv_common.cuh"
 #include "peer.cuh"
-#include "prefetch.cuh"
 
 #ifndef GEMV_NW
 #define GEMV_NW 8                          /* warps per CTA */
@@ -61,8 +62,11 @@ struct GemvK {
     int n_seg, k, T;
     int pro, epi;
     int act_q8_0;
-    int slot_bytes, n_slots;   /* ring geometry (host-computed from the largest tile of the launch) */
-    int ring_bytes;            /* per warp = n_slots * slot_bytes: 4.5 KB (Q4_K) .. 8.5 KB (Q8_0) -> 72..136 KB per CTA */
+    /* ring geometry (host-computed).  A stage holds K-tile t of the rows of ONE group; a group has 1 << lg[s] rows of
+     * segment s (<= R, the kernel's template maximum), each in a slot of slot_b[s] bytes (the segment's tile size). */
+    int slot_b[GGB_MAX_SEG], lg[GGB_MAX_SEG];
+    int stage_bytes;           /* max over segments of (rows per group * slot) */
+    int ring_bytes;            /* per warp = STEPS * stage_bytes: 9 KB (Q4_K) .. 13 KB (Q6_K) -> 72..105 KB per CTA */
     int rowv_off;              /* byte offset of the per-row results in dynamic shared memory */
     unsigned tl_slot;
     int rq[GGB_MAX_SEG], rr[GGB_MAX_SEG];   /* rows = rq*grid + rr: CTA c starts at c*rq + min(c, rr) (no division on the device) */
@@ -80,7 +84,6 @@ struct GemvK {
     int peer_n, peer_rank;
     int64_t peer_d_cap;
     uint64_t peer_base[GGB_PEER_MAX];
-    PfSet pf;                  /* L2 prefetch of later launches' weights (prefetch.cuh) */
 };
 
 // ------------------------------------------------------------------ optional in-kernel timeline (debug builds only)
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
     int16_t* bsums = reinterpret_cast<int16_t*>(qs + K);          // K/16 int16
     float* dsc = reinterpret_cast<float*>(qs + K + K / 8);        // K/32 floats
     double* rowv = reinterpret_cast<double*>(smem + P.rowv_off);  // one f64 row sum per local row (rounded once, in the epilogue)
-    const uint32_t SLOT = P.slot_bytes;                           // one tile; a step holds two (rows A and B)
+    const uint32_t STAGE = P.stage_bytes;
 
     // ---- this CTA's row range in every segment (even-aligned: row pairs and RoPE pairs stay together)
     const int G = gridDim.x, c = blockIdx.x;
@@ -129,10 +132,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
     {
         const bool last = (c + 1 == G);
         auto range = [&](int sg, int& r0, int& cnt) {
-            const int q = P.rq[sg], r = P.rr[sg];
-            const int a = (c * q + min(c, r)) & ~(R - 1);
+            const int q = P.rq[sg], r = P.rr[sg], m = ~((1 << P.lg[sg]) - 1);
+            const int a = (c * q + min(c, r)) & m;
             int b = (c + 1) * q + min(c + 1, r);
-            if (!last) b &= ~(R - 1);
+            if (!last) b &= m;
             r0 = a; cnt = b - a;
         };
         range(0, r0_0, cnt0);
@@ -140,16 +143,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         if (P.n_seg > 2) range(2, r0_2, cnt2);
     }
     const int nloc = cnt0 + cnt1 + cnt2;
-    // local rows are laid out [seg0 | seg1 | seg2]; a group of R rows never straddles a segment; a count that is
-    // not a multiple of R (possible only in the last CTA) leaves a short last group.
-    const int np0 = (cnt0 + R - 1) / R, np1 = (cnt1 + R - 1) / R, np2 = (cnt2 + R - 1) / R;
+    // local rows are laid out [seg0 | seg1 | seg2]; a group (2 or 4 rows, per segment) never straddles a segment; a count
+    // that is not a multiple of the group size (possible only in the last CTA) leaves a short last group.
+    const int lg0 = P.lg[0], lg1 = P.lg[1], lg2 = P.lg[2];
+    const int np0 = (cnt0 + (1 << lg0) - 1) >> lg0, np1 = (cnt1 + (1 << lg1) - 1) >> lg1, np2 = (cnt2 + (1 << lg2) - 1) >> lg2;
     const int npairs = np0 + np1 + np2;   /* number of row groups of this CTA */
 
-    // group index -> segment, first row, number of rows present (1..R), first local row index
+    // group index -> segment, first row, number of rows present (1..rows per group), first local row index
     auto pair_info = [&](int p, int& s, int& row, int& nv, int& lr) {
-        if (p < np0) { s = 0; row = r0_0 + R * p; nv = min(R, cnt0 - R * p); lr = R * p; }
-        else if (p < np0 + np1) { p -= np0; s = 1; row = r0_1 + R * p; nv = min(R, cnt1 - R * p); lr = cnt0 + R * p; }
-        else { p -= np0 + np1; s = 2; row = r0_2 + R * p; nv = min(R, cnt2 - R * p); lr = cnt0 + cnt1 + R * p; }
+        if (p < np0) { s = 0; const int o = p << lg0; row = r0_0 + o; nv = min(1 << lg0, cnt0 - o); lr = o; }
+        else if (p < np0 + np1) { p -= np0; s = 1; const int o = p << lg1; row = r0_1 + o; nv = min(1 << lg1, cnt1 - o); lr = cnt0 + o; }
+        else { p -= np0 + np1; s = 2; const int o = p << lg2; row = r0_2 + o; nv = min(1 << lg2, cnt2 - o); lr = cnt0 + cnt1 + o; }
     };
 
     // ---- producer (lane 0 of each warp).  One "step" = K-tile t of the R rows of a group = one ring stage
@@ -164,10 +168,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
     }
     __syncwarp();
     const int nsb_last = ggb_tile_nsb(K, T - 1);
+    const uint64_t wpolicy = l2_policy_evict_first();   /* streamed weights must not flush code / activations out of L2 */
     int ip = warp, it = 0, istage = 0;
     const uint8_t* isrc = nullptr;   // tile `it` of the first row of group `ip`
     int istride = 0, itile = 0, ilast = 0;   // row stride, full-tile bytes, last-tile bytes (16-byte rounded)
-    int inv = 0;
+    int inv = 0, islot = 0;
     auto issue_pair_setup = [&]() {
         int s, row, lr;
         pair_info(ip, s, row, inv, lr);
@@ -176,16 +181,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         itile = sbb * GGB_TILE_SB;
         ilast = (nsb_last * sbb + 15) & ~15;
         isrc = P.seg[s].w + (int64_t)row * istride;
+        islot = P.slot_b[s];
     };
     if (ip < npairs) issue_pair_setup();
     auto issue_step = [&]() {  // lane 0 only: tile `it` of every row of the group into stage `istage`, then advance
         const uint32_t bytes = (it == T - 1) ? (uint32_t)ilast : (uint32_t)itile;
         const uint32_t bar = bar0 + 8 * istage;
-        const uint32_t dst = ring0 + istage * R * SLOT;
+        const uint32_t dst = ring0 + istage * STAGE;
         mbar_expect_tx(bar, (uint32_t)inv * bytes);
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (r < inv) bulk_g2s(dst + r * SLOT, isrc + (int64_t)r * istride, bytes, bar);
+            if (r < inv) bulk_g2s_hint(dst + r * islot, isrc + (int64_t)r * istride, bytes, bar, wpolicy);
         istage = (istage + 1 == STEPS) ? 0 : istage + 1;
         isrc += itile;
         if (++it == T) {
@@ -200,34 +206,38 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         for (int i = 0; i < STEPS; i++) if (ip < npairs) issue_step();
     }
 
-    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AT_START, c, warp, GEMV_NW);
-
-    // the RMSNorm gains are weights too: fetch this lane's eight for the warp's first 256-block now
-    float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
-    if (P.pro == GGB_PRO_RMSNORM && warp < K / 256) {
-        g0 = *reinterpret_cast<const float4*>(P.norm_w + warp * 256 + lane * 8);
-        g1 = *reinterpret_cast<const float4*>(P.norm_w + warp * 256 + lane * 8 + 4);
-    }
-
-    TL_STAMP(1);
-    pdl_wait();
-    // Trigger the dependent launch only NOW (not before the wait): at most the next launch is then resident while this
-    // one works, filling its ring.  Triggering before the wait lets launches pile up three deep once co-residency really
-    // works (equal shared-memory carveouts, see the host side), and their ring fills then slow the latency-bound
-    // prologues of the running launch: 505 vs 543 tok/s.  Triggering after the prologue instead: no difference.
-    pdl_launch_dependents();
-    TL_STAMP(2);
-    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AFTER_WAIT, c, warp, GEMV_NW);
-
-    // epilogue operands that only depend on the previous phase: request them now, use them at the end
+    // ---- activation prologue, part 1 (before the dependency wait).  Three shapes, by the number of 256-blocks:
+    //   PBR = 2 / 4   every warp keeps its (up to PBR) blocks in registers: ONE trip to L2 for x serves both the RMSNorm
+    //                 sum of squares and the quantisation; the RMSNorm gains are weights and are fetched here already
+    //   PBR = 0       more than 4 blocks per warp (ffn_down): batches of 4 (2 with RMSNorm), the next batch's loads
+    //                 issued before the current batch is quantised
+    constexpr bool Q80 = (MASK == 4);
+    const int nblk = K / 256;
+    const int PBR = nblk <= 2 * GEMV_NW ? 2 : (nblk <= 4 * GEMV_NW ? 4 : 0);
+    const bool norm = (P.pro == GGB_PRO_RMSNORM);
+    // The dependency wait sits INSIDE the prologue shapes below (the resident ones fetch their gains first).
+    // The dependent launch is triggered right after the wait, not before it: at most the next launch is then resident
+    // while this one works, filling its ring.  Triggering before the wait lets launches pile up three deep once
+    // co-residency really works (equal shared-memory carveouts, see the host side), and their ring fills then slow the
+    // latency-bound prologues of the running launch: 505 vs 543 tok/s.  Triggering after the prologue: no difference.
     float res_pre = 0.f;
-    if (P.epi == GGB_EPI_RESIDUAL && tid < cnt0) res_pre = P.residual[r0_0 + tid];
+    auto wait_dep = [&]() {
+        TL_STAMP(1);
+        pdl_wait();
+#if !defined(GGB_TRIGGER_LATE) && !defined(GGB_TRIGGER_NEVER)
+        pdl_launch_dependents();
+#endif
+        TL_STAMP(2);
+        // epilogue operands that only depend on the previous phase: request them now, use them at the end
+        if (P.epi == GGB_EPI_RESIDUAL && tid < cnt0) res_pre = P.residual[r0_0 + tid];
+    };
 
-    // ---- prologue: (rms_norm * gain) and activation quantisation into shared memory
-    float scale = 1.f;
-    if (P.pro == GGB_PRO_RMSNORM) {
-        double s = 0.0;
-        for (int i = tid; i < K; i += GEMV_THREADS) { const float v = P.x[i]; s += (double)__fmul_rn(v, v); }
+    // ---- activation prologue, part 2: (rms_norm * gain) and quantisation into shared memory
+    auto load_block = [&](const float* src, int b, float (&v)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(src + b * 256 + lane * 8), c4 = *reinterpret_cast<const float4*>(src + b * 256 + lane * 8 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+    };
+    auto rms_scale = [&](double s) {   /* s = this lane's share of the sum of squares */
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) red[warp] = s;
@@ -236,56 +246,113 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
 #pragma unroll
         for (int i = 0; i < GEMV_NW; i++) tot += red[i];
         const float mean = (float)(tot / (double)K);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(mean + P.eps));
-    }
-    // two 256-blocks per warp iteration, loads of both issued before either is quantised
-    auto quant_block = [&](int b, float v[8], const float4& ga, const float4& gb) {
-        if (P.pro == GGB_PRO_RMSNORM) {
-            const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), g[i]);
-        }
-        const int chunk = (b * 256 + lane * 8) >> 4;
-        uint2* dst = reinterpret_cast<uint2*>(qs + 16 * swz(chunk) + 8 * (lane & 1));
-        if (P.act_q8_0) {
-            float df; uint16_t db;
-            const Q8Codes cq = warp_quantize_q8_0(v, df, db);
-            *dst = cq.q;
-            if (!(lane & 3)) dsc[b * 8 + (lane >> 2)] = df;
-        } else {
-            float dd;
-            const Q8Codes cq = warp_quantize_q8_K(v, lane, dd);
-            *dst = cq.q;
-            const int s16 = cq.sum8 + __shfl_xor_sync(0xffffffffu, cq.sum8, 1);
-            if (!(lane & 1)) bsums[chunk] = (int16_t)s16;
-            if (lane == 0) dsc[b] = dd;
-        }
+        return __fdiv_rn(1.0f, __fsqrt_rn(mean + P.eps));
     };
-    const int nblk = K / 256;
-    constexpr int PB = 4;   /* 256-blocks per warp iteration: all their loads are in flight before the first is quantised */
-    for (int b = warp; b < nblk; b += PB * GEMV_NW) {
-        float4 xa[PB], xb[PB], ga[PB], gb[PB];
+    // PB blocks (b0, b0 + NW, ...) in registers -> codes, sums, scales in shared memory.  Straight-line: blocks past the end
+    // are computed on whatever the clamped load returned and only their stores are predicated, so the PB chains interleave.
+    auto quant_store = [&](auto pbc, int b0, float (&v)[decltype(pbc)::value][8], const float (&g)[decltype(pbc)::value][8], float scale) {
+        constexpr int PB = decltype(pbc)::value;
+        Q8Codes cq[PB];
+        float dd[PB];
+        bool all_ok = true;
 #pragma unroll
         for (int j = 0; j < PB; j++) {
-            const int bj = b + j * GEMV_NW;
-            const int e = (bj < nblk ? bj : b) * 256 + lane * 8;
-            xa[j] = *reinterpret_cast<const float4*>(P.x + e);
-            xb[j] = *reinterpret_cast<const float4*>(P.x + e + 4);
-            if (P.pro == GGB_PRO_RMSNORM) {
-                if (j == 0 && b == warp) { ga[j] = g0; gb[j] = g1; }
-                else { ga[j] = *reinterpret_cast<const float4*>(P.norm_w + e); gb[j] = *reinterpret_cast<const float4*>(P.norm_w + e + 4); }
-            } else { ga[j] = g0; gb[j] = g1; }
+            if (norm) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[j][i] = __fmul_rn(__fmul_rn(v[j][i], scale), g[j][i]);
+            }
+            if (Q80) { uint16_t db; cq[j] = warp_quantize_q8_0(v[j], dd[j], db); }
+            else { bool ok; cq[j] = warp_quantize_q8_K_sl(v[j], lane, dd[j], ok); all_ok = all_ok && (ok || b0 + j * GEMV_NW >= nblk); }
         }
+        if (!Q80 && !all_ok) {   /* a scale outside the exact range of the inline division (never in practice): the reference
+                                    form, on re-fetched inputs so that the straight-line path need not keep its own alive */
 #pragma unroll
-        for (int j = 0; j < PB; j++) {
-            const int bj = b + j * GEMV_NW;
-            if (bj < nblk) {
-                float v[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
-                quant_block(bj, v, ga[j], gb[j]);
+            for (int j = 0; j < PB; j++) {
+                const int b = b0 + j * GEMV_NW < nblk ? b0 + j * GEMV_NW : b0;
+                float w[8], gw[8];
+                load_block(P.x, b, w);
+                if (norm) {
+                    load_block(P.norm_w, b, gw);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = __fmul_rn(__fmul_rn(w[i], scale), gw[i]);
+                }
+                cq[j] = warp_quantize_q8_K(w, lane, dd[j]);
             }
         }
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+            const int b = b0 + j * GEMV_NW;
+            const bool valid = b < nblk;
+            const int chunk = (b * 256 + lane * 8) >> 4;
+            uint2* dst = reinterpret_cast<uint2*>(qs + 16 * swz(chunk) + 8 * (lane & 1));
+            if (valid) *dst = cq[j].q;
+            if (Q80) {
+                if (valid && !(lane & 3)) dsc[b * 8 + (lane >> 2)] = dd[j];
+            } else {
+                const int s16 = cq[j].sum8 + __shfl_xor_sync(0xffffffffu, cq[j].sum8, 1);
+                if (valid && !(lane & 1)) bsums[chunk] = (int16_t)s16;
+                if (valid && lane == 0) dsc[b] = dd[j];
+            }
+        }
+    };
+    auto resident = [&](auto pbc) {
+        constexpr int PB = decltype(pbc)::value;
+        float v[PB][8], g[PB][8];
+        if (norm) {   /* the gains are weights: on their way before the dependency wait */
+#pragma unroll
+            for (int j = 0; j < PB; j++) { const int bj = warp + j * GEMV_NW; load_block(P.norm_w, bj < nblk ? bj : 0, g[j]); }
+        }
+        wait_dep();
+#pragma unroll
+        for (int j = 0; j < PB; j++) { const int bj = warp + j * GEMV_NW; load_block(P.x, bj < nblk ? bj : 0, v[j]); }
+        float scale = 1.f;
+        if (norm) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const bool valid = warp + j * GEMV_NW < nblk;
+#pragma unroll
+                for (int i = 0; i < 8; i++) s += valid ? (double)__fmul_rn(v[j][i], v[j][i]) : 0.0;
+            }
+            scale = rms_scale(s);
+        }
+        quant_store(pbc, warp, v, g, scale);
+    };
+    auto pipelined = [&](auto pbc, float scale) {
+        constexpr int PB = decltype(pbc)::value;
+        float cur[PB][8], nxt[PB][8], gc[PB][8], gn[PB][8];
+        auto fetch = [&](int b0, float (&xv)[PB][8], float (&gg)[PB][8]) {
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const int bj = b0 + j * GEMV_NW;
+                load_block(P.x, bj < nblk ? bj : b0, xv[j]);
+                if (norm) load_block(P.norm_w, bj < nblk ? bj : b0, gg[j]);
+            }
+        };
+        if (warp < nblk) fetch(warp, cur, gc);
+        for (int b = warp; b < nblk; b += PB * GEMV_NW) {
+            const int bn = b + PB * GEMV_NW;
+            if (bn < nblk) fetch(bn, nxt, gn);
+            quant_store(pbc, b, cur, gc, scale);
+#pragma unroll
+            for (int j = 0; j < PB; j++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) { cur[j][i] = nxt[j][i]; if (norm) gc[j][i] = gn[j][i]; }
+        }
+    };
+    if (PBR == 2) resident(std::integral_constant<int, 2>());
+    else if (PBR == 4) resident(std::integral_constant<int, 4>());
+    else if (!norm) { wait_dep(); pipelined(std::integral_constant<int, 4>(), 1.f); }
+    else {
+        wait_dep();
+        double s = 0.0;
+        for (int i = tid; i < K; i += GEMV_THREADS) { const float v = P.x[i]; s += (double)__fmul_rn(v, v); }
+        pipelined(std::integral_constant<int, 2>(), rms_scale(s));
     }
     __syncthreads();
+#if defined(GGB_TRIGGER_LATE)
+    pdl_launch_dependents();
+#endif
     TL_STAMP(3);
 
     // ---- main loop over this warp's row groups
@@ -299,6 +366,13 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         int s, row, lr, nv;
         pair_info(p, s, row, nv, lr);
         const int type = P.seg[s].type;
+        const int rg = 1 << (s == 0 ? lg0 : (s == 1 ? lg1 : lg2));   /* rows per group of this segment */
+        // Rows beyond nv (the short last group of the last CTA) read a duplicate of the last present row's slot and their
+        // sums are discarded below: no separate code path for short groups, and the common path stays branch-free so the
+        // rows' dependency chains interleave.
+        uint32_t ro[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) ro[r] = (uint32_t)min(r, nv - 1) * (uint32_t)P.slot_b[s];
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = 0.0;
@@ -307,22 +381,25 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
             const int U = full ? 32 : U_last;
             Act A;
             if (lane < U) A = load_act<MASK>(type, t * 32 + lane, qs_s, bs_s, dsc_s);
-            const uint32_t slot0 = ring0 + cstage * R * SLOT;
+            const uint32_t slot0 = ring0 + cstage * STAGE;
             mbar_wait(bar0 + 8 * cstage, cphase);
-#ifndef GGB_NO_INTERLEAVE
-            if (full && nv == R) {   /* common case, branch-free: the R rows' dependency chains can be interleaved */
+            // TM = the weight format(s) the unrolled rows may hold (one format = no branch between the rows), NR = rows
+            auto rows = [&](auto tm_c, auto nr_c) {
+                constexpr int TM = decltype(tm_c)::value, NR = decltype(nr_c)::value;
+                if (full) {
 #pragma unroll
-                for (int r = 0; r < R; r++) acc[r] += consume<MASK, true>(type, slot0 + r * SLOT, lane, 32, GGB_TILE_SB, A, L);
-            } else
-#endif
-            if (full) {
+                    for (int r = 0; r < NR; r++) acc[r] += consume<TM, true>(type, slot0 + ro[r], lane, 32, GGB_TILE_SB, A, L);
+                } else {
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (r < nv) acc[r] += consume<MASK, true>(type, slot0 + r * SLOT, lane, 32, GGB_TILE_SB, A, L);
+                    for (int r = 0; r < NR; r++) acc[r] += consume<TM, false>(type, slot0 + ro[r], lane, U, nsb_last, A, L);
+                }
+            };
+            if constexpr (MASK == 3) {   /* the unified K-quant instance: Q4_K groups have R rows, Q6_K groups R or R / 2 */
+                if (type == GGB_TYPE_Q4_K) rows(std::integral_constant<int, 1>(), std::integral_constant<int, R>());
+                else if (rg == R) rows(std::integral_constant<int, 2>(), std::integral_constant<int, R>());
+                else rows(std::integral_constant<int, 2>(), std::integral_constant<int, R / 2>());
             } else {
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (r < nv) acc[r] += consume<MASK, false>(type, slot0 + r * SLOT, lane, U, nsb_last, A, L);
+                rows(std::integral_constant<int, MASK>(), std::integral_constant<int, R>());
             }
             if (++cstage == STEPS) { cstage = 0; cphase ^= 1; }
             // the stage is free again: refill it (lane 0) once every lane's reads have been issued
@@ -332,10 +409,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         // butterfly reduction of the group: after log2(R) exchange levels each lane holds ONE row's partial,
         // then the remaining levels finish all R rows at once.  Row r ends up in lane r * (32 / R).
         {
-            if constexpr (R == 4) {
+            if (R == 4 && rg == 4) {
             const bool up16 = lane & 16, up8 = lane & 8;
-            double k0 = up16 ? acc[2] : acc[0], k1 = up16 ? acc[3] : acc[1];
-            const double s0 = up16 ? acc[0] : acc[2], s1 = up16 ? acc[1] : acc[3];
+            double k0 = up16 ? acc[R - 2] : acc[0], k1 = up16 ? acc[R - 1] : acc[1];
+            const double s0 = up16 ? acc[0] : acc[R - 2], s1 = up16 ? acc[1] : acc[R - 1];
             k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
             k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
             double keep = up8 ? k1 : k0;
@@ -357,9 +434,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
             }
         }
     }
-    // this warp has no demand loads left: pull the next launch's weights towards L2 while the slower CTAs finish, the
-    // dependency is handed over and the next prologue runs (HBM would idle through all three)
-    if (lane == 0) l2_prefetch_set(P.pf, GGB_PF_AT_TAIL, c, warp, GEMV_NW);
     __syncthreads();
     TL_STAMP(4);
 
@@ -494,7 +568,6 @@ static int launch(const GemvK& P, int grid, size_t smem, int use_pdl, cudaStream
 }
 
 static thread_local int64_t* g_smem_query = nullptr;   /* ggb_gemv_smem_bytes: plan only, report the shared memory, do not launch */
-static thread_local int64_t* g_ring_query = nullptr;   /* ggb_gemv_ring_bytes: likewise, the bytes of one CTA's weight rings */
 
 extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     if (!a) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv: null args");
@@ -567,12 +640,30 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     P.kcache = a->kcache; P.vcache = a->vcache; P.part_val = a->part_val; P.part_idx = a->part_idx;
     P.peer_n = a->peer_n; P.peer_rank = a->peer_rank; P.peer_d_cap = a->peer_d_cap;
     for (int p = 0; p < GGB_PEER_MAX; p++) P.peer_base[p] = a->peer_base[p];
-    P.pf = make_pfset(a->pf);
-    // ring geometry: RING_SLOTS slots sized for the largest tile of the launch
-    P.slot_bytes = (max_tile + 15) & ~15;
-    const int R = (mask == 1 || mask == 2) ? 4 : 2, STEPS = (mask == 3) ? 3 : 2;   /* any mix with Q5_K: generic R=2, STEPS=2 */
-    P.n_slots = R * STEPS;
-    P.ring_bytes = P.n_slots * P.slot_bytes;
+    // Kernel instance and ring geometry.  ONE instance serves every launch of a Q4_K / Q6_K model (mask 1, 2 and 3 all map
+    // to <3, 4, 2>): switching between instances costs 2.5-4.5 us per switch -- the instruction caches of the SMs hold one
+    // instance's hot code, not two (tools/gemv_bench.py, sequences of shapes) -- and a layer would switch four times.
+    //   rows per group  4, except the Q6_K segments of a launch that also has Q4_K segments (q, k, v): 2, so that a stage
+    //                   stays 4 x 1152 B and two CTAs (this launch and the next, resident early through PDL) fit one SM
+    //   STEPS           2 stages per warp
+    // Q5_K mixes use the generic instance <11, 2, 2>, Q8_0 models <4, 2, 2> (one instance per model as well).
+    static const int force_generic = env_int("GGB_GEMV_GENERIC", 0);   /* experiment: the generic instance for everything */
+    if (force_generic && !(mask & 4)) mask = 11;
+    const bool unified = (mask == 1 || mask == 2 || mask == 3);
+    const int R = unified ? 4 : 2, STEPS = 2;
+    (void)max_tile;
+    P.stage_bytes = 0;
+    for (int s = 0; s < GGB_MAX_SEG; s++) {
+        P.lg[s] = unified ? 2 : 1;
+        P.slot_b[s] = 0;
+        if (s >= a->n_seg) continue;
+        if (mask == 3 && a->seg[s].type == GGB_TYPE_Q6_K) P.lg[s] = 1;
+        const int tile = ggb_sb_bytes(a->seg[s].type) * (a->k >= GGB_TILE_ELEMS ? GGB_TILE_SB : a->k / 256);
+        P.slot_b[s] = (tile + 15) & ~15;
+        const int st = (1 << P.lg[s]) * P.slot_b[s];
+        if (st > P.stage_bytes) P.stage_bytes = st;
+    }
+    P.ring_bytes = STEPS * P.stage_bytes;
 #ifdef GGB_TIMELINE
     P.tl_slot = g_tl_counter++;
 #endif
@@ -589,13 +680,10 @@ extern "C" int ggb_gemv(const ggb_gemv_args* a, void* stream) {
     // is otherwise placed unevenly -- two CTAs here, none there -- and so is everything launched behind it.
     if (a->min_smem > 0 && smem < (size_t)a->min_smem && (size_t)a->min_smem <= GEMV_MAX_SMEM) smem = (size_t)a->min_smem;
     if (smem > GEMV_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv: k=%d rows=%lld needs %zu bytes of shared memory", a->k, (long long)total_rows, smem);
-    if (g_ring_query) { *g_ring_query = (P.T <= STEPS) ? (int64_t)GEMV_NW * P.ring_bytes : 0; return GGB_OK; }
     if (g_smem_query) { *g_smem_query = (int64_t)smem; return GGB_OK; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (mask) {
-        case 1: return launch<1, 4, 2>(P, grid, smem, a->use_pdl, st);
-        case 2: return launch<2, 4, 2>(P, grid, smem, a->use_pdl, st);
-        case 3: return launch<3, 2, 3>(P, grid, smem, a->use_pdl, st);
+        case 1: case 2: case 3: return launch<3, 4, 2>(P, grid, smem, a->use_pdl, st);
         case 4: return launch<4, 2, 2>(P, grid, smem, a->use_pdl, st);
         default:
             if ((mask & 8) && !(mask & 4)) return launch<11, 2, 2>(P, grid, smem, a->use_pdl, st);   /* Q5_K alone or mixed with Q4_K / Q6_K */
@@ -608,17 +696,5 @@ extern "C" int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* a) {
     g_smem_query = &v;
     const int rc = ggb_gemv(a, nullptr);
     g_smem_query = nullptr;
-    return rc == GGB_OK ? v : (int64_t)rc;
-}
-
-
-// Bytes at the START of every CTA's weight slice that the per-warp rings request before the dependency wait (0 when the
-// rows have more K-tiles than ring stages, i.e. the ring holds scattered tiles rather than a prefix of the slice): what
-// an L2 prefetch on behalf of this launch may skip (ggb_prefetch.skip).
-extern "C" int64_t ggb_gemv_ring_bytes(const ggb_gemv_args* a) {
-    int64_t v = 0;
-    g_ring_query = &v;
-    const int rc = ggb_gemv(a, nullptr);
-    g_ring_query = nullptr;
     return rc == GGB_OK ? v : (int64_t)rc;
 }

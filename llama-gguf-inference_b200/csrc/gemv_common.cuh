@@ -30,6 +30,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// The same copy with an L2 eviction-priority hint.  Weights are read exactly once per token and 4.6 GB of them stream
+// through the 126 MB L2 per token; with the default policy they flush everything else out of it -- including the
+// INSTRUCTIONS of the kernels that are not running at the moment, so that every switch between kernel instances re-fetched
+// its code from HBM (measured: +2.5..4.5 us per switch, tools/gemv_bench.py sequences).  evict_first makes the streamed
+// lines the first victims and leaves code, activations and the KV cache resident.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
 // bank swizzle of 16-byte activation chunks: conflict-free LDS.128 for both the Q4_K/Q8_0 unit pattern
 // (chunks 4u+i) and the Q6_K pattern (chunks 16sb+8n+2r+t) -- see DESIGN.md "activation staging".
 __device__ __forceinline__ int swz(int c) { return c ^ ((c >> 2) & 7); }

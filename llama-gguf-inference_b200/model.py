@@ -173,31 +173,6 @@ class Slot:
             self._attn_pdl.append(self.use_pdl | trig)
             self._layer_args.append((qkv, o, gu, dn))
         self._head = self._head_args()
-        self._plan_prefetch()
-
-    def _plan_prefetch(self):
-        """L2 prefetch plan of the decode chain (include/ggufb200.h: ggb_prefetch).  Every GEMV launch pulls, when its
-        warps run out of rows, the next GGB_PF_TAIL_KB (per CTA) of the NEXT launch's weight stream into L2 -- HBM would
-        otherwise idle through the exit spread, the dependency hand-over and the next prologue; the attention, which
-        reads a few hundred KB, does the same for the gate/up projection (GGB_PF_ATTN_KB).  0 disables either."""
-        lib = self.lib
-        tail = int(os.environ.get("GGB_PF_TAIL_KB", "0")) * 1024
-        attn = int(os.environ.get("GGB_PF_ATTN_KB", "0")) * 1024
-        when = int(os.environ.get("GGB_PF_WHEN", str(cabi.PF_AT_TAIL)))
-        self._attn_pf = [None] * len(self._layer_args)
-        if not (tail or attn):
-            return
-        chain = [a for quad in self._layer_args for a in quad] + [self._head]
-        skip = [max(0, lib.ggb_gemv_ring_bytes(C.byref(a))) for a in chain]
-        for i, a in enumerate(chain[:-1]):
-            extra = attn if (i % 4 == 1) else 0     # the output projection: the attention took the first part of gate/up
-            if tail:
-                cabi.fill_prefetch(a.pf[0], chain[i + 1], skip[i + 1] + extra, tail, when)
-        if attn:
-            for l in range(len(self._layer_args)):
-                pf = (cabi.Prefetch * cabi.PF_MAX)()
-                cabi.fill_prefetch(pf[0], chain[4 * l + 2], skip[4 * l + 2], attn, cabi.PF_AFTER_WAIT)
-                self._attn_pf[l] = pf
 
     # ------------------------------------------------------------------ enqueue
     def _enqueue_embed(self, s: int):
@@ -220,10 +195,9 @@ class Slot:
         tp = self.eng.tp_size > 1
         for i, (qkv, o, gu, dn) in enumerate(self._layer_args):
             cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
-            cabi.check(lib.ggb_attn_decode_pf(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
-                                              self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
-                                              self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i],
-                                              self._attn_pf[i], s), "attn_decode")
+            cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                                           self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
+                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i], s), "attn_decode")
             cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
             if tp:
                 self._allreduce_residual(s)
@@ -300,10 +274,6 @@ class Slot:
                 self.stream.synchronize()
         self.reset()
 
-    def _prefill_gemm(self, tokens: list[int], start: int):
-        """Many tokens at once: tcgen05 dequant-GEMMs + tensor-core attention (Engine.prefill_many with one job)."""
-        self.eng.prefill_many([(self.index, tokens, start)])
-
     def prefill(self, tokens: list[int], start_pos: int | None = None):
         """Feed tokens at positions start_pos.. (default: append).  Long prompts go through the tcgen05 GEMM path
         (tolerance-level numerics, like upstream's batched CUDA path); short ones run token by token through the
@@ -311,13 +281,15 @@ class Slot:
         generated token (greedy) and the logits."""
         if not tokens:
             raise ValueError("empty prompt")
+        self.eng.check_tokens(tokens)
         start = self.n_past if start_pos is None else start_pos
         if start + len(tokens) >= self.n_ctx:
             raise ValueError(f"prompt of {len(tokens)} tokens does not fit the context ({self.n_ctx})")
         e = self.eng
         if e.tp_size == 1 and len(tokens) >= e.gemm_prefill_min:
             for c0 in range(0, len(tokens), e.prefill_chunk):
-                self._prefill_gemm(tokens[c0:c0 + e.prefill_chunk], start + c0)
+                # only the final chunk runs the head: it emits the first generated token and advances the step counter
+                e.prefill_many([(self.index, tokens[c0:c0 + e.prefill_chunk], start + c0)], head=c0 + e.prefill_chunk >= len(tokens))
             return
         first = 0
         if e.tp_size == 1 and len(tokens) >= 4:
@@ -474,7 +446,7 @@ class Engine:
         raw = np.array(self.file.data(name))  # copy: torch refuses read-only mmap views
         return torch.from_numpy(raw).to(self.dev, non_blocking=False)
 
-    def _load_matrix(self, name: str) -> Weight:
+    def _load_matrix(self, name: str, shard_as: str | None = None) -> Weight:
         torch = self.torch
         ti = self.file.tensors[name]
         if ti.ggml_type not in QUANT_TYPES:
@@ -482,7 +454,7 @@ class Engine:
         k, rows = ti.ne[0], ti.ne[1]
         if k % 256:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
-        sh = parallel.shard_of(name, self.hp, self.tp_size, self.tp_rank)
+        sh = parallel.shard_of(shard_as or name, self.hp, self.tp_size, self.tp_rank)
         if sh.kind == parallel.FULL:
             canon = self._upload(name)
         else:
@@ -527,14 +499,24 @@ class Engine:
                 "wd": self._load_matrix(p + "ffn_down.weight"),
             })
         self.out_norm = self._load_f32("output_norm.weight")
-        out_name = "output.weight" if "output.weight" in f.tensors else "token_embd.weight"
-        self.w_out = self._load_matrix(out_name)
+        # tied embeddings (no output.weight, e.g. Llama-3.2 1B/3B): the head reads token_embd -- under tensor parallelism
+        # vocabulary-sharded like output.weight, while the embedding gather keeps its replicated canonical copy
+        tied = "output.weight" not in f.tensors
+        self.w_out = self._load_matrix("token_embd.weight" if tied else "output.weight", shard_as="output.weight")
         ff = None
         if "rope_freqs.weight" in f.tensors:
             ff = self._load_f32("rope_freqs.weight").cpu().numpy()
         self.rope_tab = self.torch.from_numpy(rope_table(self.n_ctx, hp.n_rot, hp.rope_base, ff)).to(self.dev)
 
-    def prefill_many(self, jobs):
+    def check_tokens(self, tokens) -> None:
+        """token ids index the embedding table on the device without a bound check there: refuse anything outside the
+        vocabulary here (ValueError = the caller's input is wrong, not an engine failure)"""
+        v = self.hp.vocab
+        for t in tokens:
+            if isinstance(t, bool) or not isinstance(t, (int, np.integer)) or not 0 <= int(t) < v:
+                raise ValueError(f"token id {t!r} is outside the vocabulary (0..{v - 1})")
+
+    def prefill_many(self, jobs, head: bool = True):
         """jobs = [(slot index, tokens, start position)]: the prompt chunks of SEVERAL sequences in one pass through the
         tcgen05 dequant-GEMMs (csrc/gemm.cu) -- the GEMMs, norms and element-wise ops run on the concatenated tokens, RoPE
         and the KV write take per-token (slot, position), attention runs per sequence (csrc/prefill.cu).  Each sequence's
@@ -548,6 +530,7 @@ class Engine:
         for sl, toks, start in jobs:
             if start + len(toks) >= self.n_ctx or not toks:
                 raise ValueError("prompt does not fit the context")
+            self.check_tokens(toks)
         B = self.prefill_buffers(T)
         s = self.stream.cuda_stream
         qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
@@ -594,9 +577,10 @@ class Engine:
             for sl, toks, start in jobs:
                 slot = self.slots[sl]
                 off += len(toks)
-                slot.x.copy_(X[(off - 1) * hp.d:off * hp.d], non_blocking=True)
-                slot._set_tok_pos(int(toks[-1]), start + len(toks) - 1)
-                slot._enqueue_head(s)
+                if head:    # (an intermediate chunk of a long prompt only fills the cache)
+                    slot.x.copy_(X[(off - 1) * hp.d:off * hp.d], non_blocking=True)
+                    slot._set_tok_pos(int(toks[-1]), start + len(toks) - 1)
+                    slot._enqueue_head(s)
             self.stream.synchronize()
         for sl, toks, start in jobs:
             self.slots[sl].n_past = start + len(toks)

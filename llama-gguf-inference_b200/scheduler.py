@@ -88,12 +88,14 @@ def _lcp(a, b) -> int:
 
 
 def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator, history=None) -> int:
-    """penalties -> temperature -> top-k -> top-p -> min-p -> multinomial (the samplers of upstream's default chain
-    that the reference's API documents, docs/API_REFERENCE.md:369-379 [UPSTREAM-MEM for the arithmetic])."""
+    """penalties -> top-k -> top-p -> min-p -> temperature -> multinomial: the order of upstream's default sampler chain
+    [UPSTREAM-MEM: common/sampling.cpp; the reference documents the parameters in docs/API_REFERENCE.md:369-379].
+    The nucleus and min-p cut-offs are therefore taken on the UNtempered distribution; the temperature only reshapes the
+    probabilities of the survivors."""
     logits = apply_penalties(logits, sp, history)
     if sp.arg_max:
         return int(np.argmax(logits))
-    x = logits.astype(np.float64) / max(sp.temperature, 1e-6)
+    x = logits.astype(np.float64)
     k = sp.top_k if 0 < sp.top_k < x.size else x.size
     idx = np.argpartition(x, -k)[-k:]
     idx = idx[np.argsort(-x[idx], kind="stable")]
@@ -104,7 +106,10 @@ def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generato
         idx, p = idx[:keep], p[:keep] / p[:keep].sum()
     if 0.0 < sp.min_p < 1.0:
         keep = max(1, int((p >= sp.min_p * p[0]).sum()))          # p is sorted, p[0] is the maximum
-        idx, p = idx[:keep], p[:keep] / p[:keep].sum()
+        idx = idx[:keep]
+    xt = x[idx] / max(sp.temperature, 1e-6)
+    p = np.exp(xt - xt[0])
+    p /= p.sum()
     return int(idx[rng.choice(len(idx), p=p)])
 
 
@@ -209,7 +214,15 @@ class Scheduler(threading.Thread):
                     jobs.append((a.slot.index, a.req.prompt_ids[common:], common))
                     if common:
                         self.stats["prompt_tokens_cached"] = self.stats.get("prompt_tokens_cached", 0) + common
-                many(jobs)
+                try:
+                    many(jobs)
+                except ValueError as e:                    # a malformed prompt in the group: each request answers for itself
+                    self.log(f"grouped prefill rejected ({e}); retrying the requests one by one")
+                    for i in group:
+                        self.slot_tokens.pop(i, None)
+                        self._start(i)
+                    group, group_tokens = [], 0
+                    return
                 for i in group:
                     self._start(i, prefilled=True)
             else:
@@ -241,11 +254,17 @@ class Scheduler(threading.Thread):
         if not prefilled:
             common = self._reusable_prefix(i)
             slot.reset()                                   # counters only: the K/V of positions < common stay valid
-            if common:
-                slot.prefill(req.prompt_ids[common:], start_pos=common)
-                self.stats["prompt_tokens_cached"] = self.stats.get("prompt_tokens_cached", 0) + common
-            else:
-                slot.prefill(req.prompt_ids)
+            try:
+                if common:
+                    slot.prefill(req.prompt_ids[common:], start_pos=common)
+                    self.stats["prompt_tokens_cached"] = self.stats.get("prompt_tokens_cached", 0) + common
+                else:
+                    slot.prefill(req.prompt_ids)
+            except ValueError as e:                        # this request's input is unusable: it alone fails (HTTP 400)
+                req.events.put(("error", f"invalid request: {e}"))
+                del self.active[i]
+                self.slot_tokens.pop(i, None)
+                return
         a.fed = list(req.prompt_ids)                       # tokens whose K/V the slot holds
         self.slot_tokens.pop(i, None)
         self.stats["requests"] += 1

@@ -125,6 +125,8 @@ class Handler(BaseHTTPRequestHandler):
             n = int(self.headers.get("Content-Length", "0") or 0)
         except ValueError:
             return self._send(*_err(400, "invalid Content-Length", "invalid_request_error"))
+        if n < 0:
+            return self._send(*_err(400, "invalid Content-Length", "invalid_request_error"))
         if n > MAX_BODY:
             return self._send(*_err(413, "request body too large", "invalid_request_error"))
         raw = self.rfile.read(n) if n else b""
@@ -150,7 +152,7 @@ class Handler(BaseHTTPRequestHandler):
                 return self._send(*_err(501, "embeddings are not served by this engine (decode path only)", "not_supported_error"))
         except (BrokenPipeError, ConnectionResetError):
             return
-        except ValueError as e:
+        except (ValueError, TypeError) as e:   # malformed field (wrong type, out-of-range token id, ...): this request only
             return self._send(*_err(400, str(e), "invalid_request_error"))
         self._send(*_err(404, f"File Not Found: {p}", "not_found_error"))
 
@@ -166,25 +168,44 @@ class Handler(BaseHTTPRequestHandler):
             ids = st.tok.encode_chat(msgs)
         else:
             prompt = body.get("prompt")
-            if isinstance(prompt, list) and prompt and all(isinstance(t, int) for t in prompt):
-                ids = [int(t) for t in prompt]
+            if isinstance(prompt, list) and prompt and all(isinstance(t, int) and not isinstance(t, bool) for t in prompt):
+                # raw token ids go straight to the embedding gather on the device: range-check them here
+                n_vocab = st.tok.n_vocab
+                bad = [t for t in prompt if not 0 <= t < n_vocab]
+                if bad:
+                    raise ValueError(f"prompt token id {bad[0]} is outside the vocabulary (0..{n_vocab - 1})")
+                ids = list(prompt)
             elif isinstance(prompt, (str, list)):
                 ids = st.tok.encode(prompt if isinstance(prompt, str) else "".join(map(str, prompt)))
             else:
                 raise ValueError("'prompt' is required")
         if not ids:
             raise ValueError("the prompt is empty after tokenisation")
-        mt = body.get("max_tokens", body.get("max_completion_tokens", body.get("n_predict")))
-        max_tokens = st.n_ctx if mt is None or int(mt) < 0 else int(mt)
+        def num(key, default, cast):
+            """a JSON null means "use the default"; anything that is not a plain number is the client's error (400)"""
+            v = body.get(key)
+            if v is None:
+                return default
+            if isinstance(v, bool) or not isinstance(v, (int, float)):
+                raise ValueError(f"'{key}' must be a number")
+            return cast(v)
+
+        mt = None
+        for key in ("max_tokens", "max_completion_tokens", "n_predict"):
+            if body.get(key) is not None:
+                mt = num(key, None, int)
+                break
+        max_tokens = st.n_ctx if mt is None or mt < 0 else mt
         d = st.defaults
-        sp = SamplingParams(temperature=float(body.get("temperature", d.temperature)),
-                            top_k=int(body.get("top_k", d.top_k)), top_p=float(body.get("top_p", d.top_p)),
-                            seed=(int(body["seed"]) if body.get("seed") not in (None, -1) else d.seed),
-                            min_p=float(body.get("min_p", d.min_p)),
-                            repeat_penalty=float(body.get("repeat_penalty", d.repeat_penalty)),
-                            presence_penalty=float(body.get("presence_penalty", d.presence_penalty)),
-                            frequency_penalty=float(body.get("frequency_penalty", d.frequency_penalty)),
-                            repeat_last_n=int(body.get("repeat_last_n", d.repeat_last_n)))
+        seed = num("seed", None, int)
+        sp = SamplingParams(temperature=num("temperature", d.temperature, float),
+                            top_k=num("top_k", d.top_k, int), top_p=num("top_p", d.top_p, float),
+                            seed=(seed if seed not in (None, -1) else d.seed),
+                            min_p=num("min_p", d.min_p, float),
+                            repeat_penalty=num("repeat_penalty", d.repeat_penalty, float),
+                            presence_penalty=num("presence_penalty", d.presence_penalty, float),
+                            frequency_penalty=num("frequency_penalty", d.frequency_penalty, float),
+                            repeat_last_n=num("repeat_last_n", d.repeat_last_n, int))
         stop = body.get("stop") or []
         if isinstance(stop, str):
             stop = [stop]
@@ -259,7 +280,7 @@ class Handler(BaseHTTPRequestHandler):
                     out["content"] = content   # llama-server's native /completion field
                 return self._send(200, json.dumps(out, ensure_ascii=False).encode())
             else:
-                code = 400 if "context size" in ev[1] else 500
+                code = 400 if ("context size" in ev[1] or ev[1].startswith("invalid request")) else 500
                 return self._send(*_err(code, ev[1], "invalid_request_error" if code == 400 else "server_error"))
 
 

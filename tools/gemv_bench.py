@@ -63,6 +63,58 @@ def bench(name, segs, k, pro, epi, n_buf=32, reps=20, use_pdl=1):
     return us
 
 
+SHAPES = {
+    "QKV": ([(12, 4096), (12, 1024), (14, 1024)], 4096, cabi.PRO_RMSNORM, cabi.EPI_ROPE_KV),
+    "O": ([(12, 4096)], 4096, cabi.PRO_PLAIN, cabi.EPI_RESIDUAL),
+    "GU": ([(12, 14336), (12, 14336)], 4096, cabi.PRO_RMSNORM, cabi.EPI_SWIGLU),
+    "DOWN": ([(14, 4096)], 14336, cabi.PRO_PLAIN, cabi.EPI_RESIDUAL),
+    "DOWN4": ([(12, 4096)], 14336, cabi.PRO_PLAIN, cabi.EPI_RESIDUAL),
+}
+
+
+def bench_seq(names, n_rep=8, reps=20, use_pdl=1):
+    """An arbitrary sequence of launch shapes, repeated n_rep times over distinct buffers: consecutive launches may be
+    DIFFERENT kernel instances with different shared-memory footprints -- what the decode step really does (minus the
+    attention).  Prints us per repetition of the sequence."""
+    x = {4096: torch.randn(4096, device=DEV) * 0.01, 14336: torch.randn(14336, device=DEV) * 0.01}
+    nw = torch.ones(14336, device=DEV)
+    y = [torch.zeros(14336, device=DEV) for _ in range(3)]
+    res = torch.zeros(4096, device=DEV)
+    pos = torch.tensor([7], dtype=torch.int32, device=DEV)
+    tab = torch.zeros(64 * 128, device=DEV)
+    kc = torch.zeros(64 * 2048, dtype=torch.int16, device=DEV)
+    keep, args = [], []
+    for _ in range(n_rep):
+        for nm in names:
+            segs, k, pro, epi = SHAPES[nm]
+            ws = [rand_weight(qt, r, k) for qt, r in segs]
+            keep.append(ws)
+            args.append(cabi.make_gemv_args([(w.data_ptr(), qt, r, yy.data_ptr()) for w, (qt, r), yy in zip(ws, segs, y)], k, x[k].data_ptr(),
+                                            prologue=pro, epilogue=epi, norm_w=nw.data_ptr(), eps=1e-5, use_pdl=use_pdl, residual=res.data_ptr(),
+                                            pos_dev=pos.data_ptr(), rope_tab=tab.data_ptr(), n_rot=128, head_dim=128, kcache=kc.data_ptr(),
+                                            vcache=kc.data_ptr()))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for a in args[:len(names)]:
+            cabi.check(L.ggb_gemv(C.byref(a), s.cuda_stream))
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for a in args:
+                cabi.check(L.ggb_gemv(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            g.replay()
+        e1.record(s)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * n_rep)
+    print(f"sequence {'+'.join(names):24s} pdl={use_pdl}: {us:7.2f} us per repetition", flush=True)
+    return us
+
+
 if __name__ == "__main__":
     pdl = int(os.environ.get("PDL", "1"))
     t = 0
@@ -73,3 +125,6 @@ if __name__ == "__main__":
     d4 = bench("DOWN_q4", [(12, 4096)], 14336, cabi.PRO_PLAIN, cabi.EPI_RESIDUAL, use_pdl=pdl)
     bench("HEAD", [(14, 128256)], 4096, cabi.PRO_RMSNORM, cabi.EPI_ARGMAX, n_buf=4, use_pdl=pdl)
     print(f"layer GEMV sum (q6 down) {t:.1f} us -> 32 layers {t*32/1e3:.2f} ms")
+    for seq in (["QKV"], ["O"], ["GU"], ["DOWN"], ["O", "GU"], ["GU", "DOWN"], ["DOWN", "QKV"], ["QKV", "O"], ["GU", "DOWN4"], ["QKV", "O", "GU", "DOWN"]):
+        for p in (1, 0):
+            bench_seq(seq, use_pdl=p)

@@ -1,6 +1,6 @@
 """Sweep decode-chain knobs (environment variables read when an Engine is built) on the headline workload:
 Llama-3-8B Q4_K_M, bs=1 greedy decode after a 256-token prompt, device-timed graph replays.
-    python tools/pf_sweep.py "GGB_PF_TAIL_KB=0" "GGB_PF_TAIL_KB=128" "GGB_PF_TAIL_KB=128 GGB_PF_ATTN_KB=256" ...
+    python tools/knob_sweep.py "" "GGB_ATTN_CL=4" ...
 Every configuration must produce the same tokens as the first one (the knobs are hints, never arithmetic)."""
 import os
 import sys
@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from ggufb200.model import Engine  # noqa: E402
 
-KNOBS = ("GGB_PF_TAIL_KB", "GGB_PF_ATTN_KB", "GGB_PF_WHEN", "GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM")
+KNOBS = ("GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM", "GGB_LIB_PATH")
 
 
 def run(path, steps, warm):
