@@ -176,3 +176,12 @@ def make_gemv_batch_args(segs, k, act, nb, *, epilogue=EPI_STORE, residual=0, us
         a.seg[i].w, a.seg[i].type, a.seg[i].rows, a.seg[i].y = w, t, rows, y
     a.epilogue, a.nb, a.act, a.residual, a.use_pdl, a.grid = epilogue, nb, act, residual, use_pdl, grid
     return a
+
+
+def copy_args(a: GemvArgs, **override) -> GemvArgs:
+    """a field-by-field copy of a launch description with some fields replaced"""
+    b = GemvArgs()
+    C.memmove(C.byref(b), C.byref(a), C.sizeof(GemvArgs))
+    for k, v in override.items():
+        setattr(b, k, v)
+    return b

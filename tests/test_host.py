@@ -187,6 +187,20 @@ def test_sampler_is_seeded_and_respects_top_k_top_p():
     assert a == b
 
 
+def test_sampler_cuts_on_the_untempered_distribution_then_applies_temperature():
+    """upstream's default chain: top-k, top-p and min-p act on softmax(logits); temperature comes last.  Hand-computed:
+    logits (2, 1, 0): p = (0.665, 0.245, 0.090).  top_p = 0.7 keeps two tokens whatever the temperature (tempering first
+    at T = 4 would flatten p to (0.39, 0.33, 0.28) and keep all three); min_p = 0.2 drops only the last (0.090 < 0.133)."""
+    from ggufb200.scheduler import SamplingParams, sample_token
+    logits = np.array([2.0, 1.0, 0.0], dtype=np.float32)
+    draws = [sample_token(logits, SamplingParams(temperature=4.0, top_k=0, top_p=0.7), np.random.default_rng(s)) for s in range(300)]
+    assert set(draws) == {0, 1}
+    # the survivors are then drawn at temperature 4: p0 = 1 / (1 + exp(-1/4)) = 0.562
+    assert abs(draws.count(0) / 300 - 0.562) < 0.09
+    draws = {sample_token(logits, SamplingParams(temperature=4.0, top_k=0, top_p=1.0, min_p=0.2), np.random.default_rng(s)) for s in range(200)}
+    assert draws == {0, 1}
+
+
 # ----------------------------------------------------------------------------- C-ABI library
 def test_library_loads_and_exports_every_declared_symbol():
     from ggufb200 import cabi

@@ -156,6 +156,26 @@ def test_completions_endpoint_stop_and_errors(oracle, backend):
     assert c.getresponse().status == 400
 
 
+def test_malformed_requests_get_400_and_leave_the_backend_healthy(backend):
+    """raw token ids outside the vocabulary, non-numeric fields, null fields, a negative Content-Length: each is the
+    client's error (400) -- none may reach the engine or kill the scheduler"""
+    p = backend["port"]
+    nv = backend["tok"].n_vocab
+    for bad in ([1, nv], [1, -5], [1, 10 ** 12]):
+        st, body = call(p, "POST", "/v1/completions", {"prompt": bad, "max_tokens": 2})
+        assert st == 400 and "vocabulary" in body["error"]["message"]
+    assert call(p, "POST", "/v1/completions", {"prompt": [1, 300], "max_tokens": [1]})[0] == 400
+    assert call(p, "POST", "/v1/completions", {"prompt": [1, 300], "max_tokens": 2, "temperature": "hot"})[0] == 400
+    st, body = call(p, "POST", "/v1/completions", {"prompt": [1, 300], "max_tokens": 2, "temperature": None, "top_p": None, "seed": None})
+    assert st == 200 and body["usage"]["completion_tokens"] == 2          # JSON null = default
+    s = socket.create_connection(("127.0.0.1", p), timeout=10)
+    s.sendall(b"POST /v1/completions HTTP/1.1\r\nHost: x\r\nAuthorization: Bearer " + KEY.encode() + b"\r\nContent-Length: -5\r\n\r\n")
+    assert b" 400 " in s.recv(4096).split(b"\r\n")[0]
+    s.close()
+    assert backend["state"].sched.is_alive() and backend["state"].sched.fatal is None
+    assert call(p, "POST", "/v1/completions", {"prompt": [1, 300], "max_tokens": 2})[0] == 200
+
+
 def test_sampling_is_seeded_and_differs_from_greedy(backend):
     p = backend["port"]
     req = {"messages": MSG, "max_tokens": 12, "temperature": 1.5, "top_k": 50, "seed": 7}
