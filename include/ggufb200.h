@@ -134,6 +134,9 @@ typedef struct ggb_gemv_args {
      * memory two CTAs of the launch can never share an SM, which keeps the placement even when it becomes resident while
      * another kernel's small CTAs are still running (the output projection behind the attention) */
     int32_t min_smem;
+    /* 1 = every ggb_gemv launch of this model has k % 2048 == 0: Q4_K / Q6_K launches then use the kernel instance that
+     * carries no partial-tile code (the kernel is instruction-fetch bound: leaner code is faster code).  0 = generic. */
+    int32_t full_k_model;
 } ggb_gemv_args;
 
 int ggb_gemv(const ggb_gemv_args* args, void* stream);

@@ -54,7 +54,7 @@ class GemvArgs(C.Structure):
         ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
         ("grid", C.c_int32),
         ("peer_n", C.c_int32), ("peer_rank", C.c_int32), ("peer_d_cap", C.c_int64), ("peer_base", C.c_uint64 * PEER_MAX),
-        ("min_smem", C.c_int32),
+        ("min_smem", C.c_int32), ("full_k_model", C.c_int32),
     ]
 
 
@@ -145,7 +145,7 @@ def device_info() -> dict:
 
 def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w=0, eps=0.0, use_pdl=0, residual=0,
                    pos_dev=0, rope_tab=0, n_rot=0, head_dim=0, kcache=0, vcache=0, part_val=0, part_idx=0, grid=0,
-                   peer=None, min_smem=0) -> GemvArgs:
+                   peer=None, min_smem=0, full_k_model=0) -> GemvArgs:
     """segs: list of (w_ptr, type, rows, y_ptr)."""
     a = GemvArgs()
     a.n_seg = len(segs)
@@ -160,6 +160,7 @@ def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w
     a.pos_dev, a.rope_tab, a.n_rot, a.head_dim = pos_dev, rope_tab, n_rot, head_dim
     a.kcache, a.vcache, a.part_val, a.part_idx, a.grid = kcache, vcache, part_val, part_idx, grid
     a.min_smem = min_smem
+    a.full_k_model = full_k_model
     if peer is not None:    # (bases of every rank's exchange region in this process, own rank, capacity in rows)
         bases, rank, d_cap = peer
         a.peer_n, a.peer_rank, a.peer_d_cap = len(bases), rank, d_cap

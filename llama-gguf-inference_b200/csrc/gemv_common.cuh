@@ -19,9 +19,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
+        "@!p bra WAIT_LOOP;\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // TMA bulk copy global -> shared::cta, completion signalled on an mbarrier (SASS: UBLKCP)

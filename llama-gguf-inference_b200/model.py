@@ -118,6 +118,8 @@ class Slot:
         self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.host_logits = None
         self._graphs = {}
+        # every GEMV of this model has k % 2048 == 0: all launches share the kernel instance without partial-tile code
+        self.full_k = int(all(k % 2048 == 0 for k in (hp.d, self.nh * hp.head_dim, self.ffl)))
         self._build_args()
         self.n_past = 0   # host mirror of the number of positions held in the KV cache
 
@@ -127,7 +129,8 @@ class Slot:
         return cabi.make_gemv_args(
             [(e.w_out.ptr, e.w_out.type, e.w_out.rows, self.logits.data_ptr())], hp.d, self.x.data_ptr(),
             prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ARGMAX, norm_w=e.out_norm.data_ptr(), eps=hp.eps,
-            use_pdl=self.use_pdl, part_val=self.part_val.data_ptr(), part_idx=self.part_idx.data_ptr())
+            use_pdl=self.use_pdl, part_val=self.part_val.data_ptr(), part_idx=self.part_idx.data_ptr(),
+            full_k_model=getattr(self, "full_k", 0))
 
     def _build_args(self):
         hp, e = self.hp, self.eng
@@ -141,7 +144,7 @@ class Slot:
                 hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_ROPE_KV,
                 norm_w=L["attn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, pos_dev=self.pos_dev.data_ptr(),
                 rope_tab=e.rope_tab.data_ptr(), n_rot=hp.n_rot, head_dim=hp.head_dim,
-                kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr())
+                kcache=self.kc[i].data_ptr(), vcache=self.vc[i].data_ptr(), full_k_model=self.full_k)
             tp = e.tp_size > 1
             # row-split projections: partial sums leave through the fused peer exchange, or as a local f64 vector (NCCL)
             epi_rs = (cabi.EPI_PEER_F64 if e.peer else cabi.EPI_STORE_F64) if tp else cabi.EPI_RESIDUAL
@@ -149,16 +152,16 @@ class Slot:
             o = cabi.make_gemv_args(
                 [(L["wo"].ptr, L["wo"].type, L["wo"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wo"].k,
                 self.attn.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=epi_rs,
-                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer)
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer, full_k_model=self.full_k)
             gu = cabi.make_gemv_args(
                 [(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
                  (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)],
                 hp.d, self.x.data_ptr(), prologue=cabi.PRO_RMSNORM, epilogue=cabi.EPI_SWIGLU,
-                norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl)
+                norm_w=L["ffn_norm"].data_ptr(), eps=hp.eps, use_pdl=self.use_pdl, full_k_model=self.full_k)
             dn = cabi.make_gemv_args(
                 [(L["wd"].ptr, L["wd"].type, L["wd"].rows, self.y64.data_ptr() if tp else self.x.data_ptr())], L["wd"].k,
                 self.h.data_ptr(), prologue=cabi.PRO_PLAIN, epilogue=epi_rs,
-                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer)
+                residual=self.x.data_ptr(), use_pdl=self.use_pdl, peer=peer, full_k_model=self.full_k)
             # The attention releases the output projection early (it then fills its weight ring while the attention runs)
             # only if two CTAs of the projection cannot land on one SM: pad its shared memory past half an SM's when the
             # gate/up launch behind it still fits next to it (csrc/attn.cu, csrc/gemv.cu: min_smem).
