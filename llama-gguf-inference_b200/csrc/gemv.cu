@@ -249,8 +249,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
     };
     // PB blocks (b0, b0 + NW, ...) in registers -> codes, sums, scales in shared memory.  Straight-line: blocks past the end
     // are computed on whatever the clamped load returned and only their stores are predicated, so the PB chains interleave.
+    bool redo = false;      /* some block's scale fell outside the exact range of the inline division (never in practice) */
+    float rms_used = 1.f;   /* the RMSNorm factor the prologue applied */
     auto quant_store = [&](auto pbc, int b0, float (&v)[decltype(pbc)::value][8], const float (&g)[decltype(pbc)::value][8], float scale) {
         constexpr int PB = decltype(pbc)::value;
+        rms_used = scale;
         Q8Codes cq[PB];
         float dd[PB];
         bool all_ok = true;
@@ -262,25 +265,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
             }
             if (Q80) { uint16_t db; cq[j] = warp_quantize_q8_0(v[j], dd[j], db); }
             else { bool ok; cq[j] = warp_quantize_q8_K_sl(v[j], lane, dd[j], ok); all_ok = all_ok && (ok || b0 + j * GEMV_NW >= nblk); }
-        }
-#ifdef V_NOFB
-        if (false) {
-#else
-        if (!Q80 && !all_ok) {
-#endif   /* a scale outside the exact range of the inline division (never in practice): the reference
-                                    form, on re-fetched inputs so that the straight-line path need not keep its own alive */
-#pragma unroll
-            for (int j = 0; j < PB; j++) {
-                const int b = b0 + j * GEMV_NW < nblk ? b0 + j * GEMV_NW : b0;
-                float w[8], gw[8];
-                load_block(P.x, b, w);
-                if (norm) {
-                    load_block(P.norm_w, b, gw);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] = __fmul_rn(__fmul_rn(w[i], scale), gw[i]);
-                }
-                cq[j] = warp_quantize_q8_K(w, lane, dd[j]);
-            }
         }
 #pragma unroll
         for (int j = 0; j < PB; j++) {
@@ -297,6 +281,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
                 if (valid && lane == 0) dsc[b] = dd[j];
             }
         }
+        if (!Q80 && !all_ok) redo = true;   /* see below: one out-of-range scale redoes the warp's blocks in the reference form */
     };
     auto resident = [&](auto pbc) {
         constexpr int PB = decltype(pbc)::value;
@@ -351,6 +336,28 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_MIN_CTAS) ggb_dq_gemv_kerne
         double s = 0.0;
         for (int i = tid; i < K; i += GEMV_THREADS) { const float v = P.x[i]; s += (double)__fmul_rn(v, v); }
         pipelined(std::integral_constant<int, 2>(), rms_scale(s));
+    }
+    // The reference form of the quantiser (__fdiv_rn) for a warp that met an out-of-range scale: ONE rolled copy behind
+    // all prologue shapes.  (Inlined into the straight-line quantiser it was 12 unrolled copies that never ran and still
+    // cost 3.6 % tokens/s in instruction fetch; as a __noinline__ routine its call cost 15 registers kernel-wide.)
+    if (redo) {
+#pragma unroll 1
+        for (int b = warp; b < nblk; b += GEMV_NW) {
+            float w[8], gw[8];
+            load_block(P.x, b, w);
+            if (norm) {
+                load_block(P.norm_w, b, gw);
+#pragma unroll
+                for (int i = 0; i < 8; i++) w[i] = __fmul_rn(__fmul_rn(w[i], rms_used), gw[i]);
+            }
+            float d;
+            const Q8Codes cq = warp_quantize_q8_K(w, lane, d);
+            const int chunk = (b * 256 + lane * 8) >> 4;
+            *reinterpret_cast<uint2*>(qs + 16 * swz(chunk) + 8 * (lane & 1)) = cq.q;
+            const int s16 = cq.sum8 + __shfl_xor_sync(0xffffffffu, cq.sum8, 1);
+            if (!(lane & 1)) bsums[chunk] = (int16_t)s16;
+            if (lane == 0) dsc[b] = d;
+        }
     }
     __syncthreads();
 #if defined(GGB_TRIGGER_LATE)

@@ -144,6 +144,25 @@ def test_gemv_store_matches_oracle(oracle, name, rows, k):
     assert np.abs(got - ref).max() <= tol, (np.abs(got - ref).max(), tol)
 
 
+@pytest.mark.parametrize("full_k_model", [0, 1])
+@pytest.mark.parametrize("name,rows,k", [("q4_k", 300, 4096), ("q6_k", 200, 14336), ("q4_k", 64, 8192), ("q5_k", 40, 4096)])
+def test_gemv_activation_scales_outside_the_inline_division_range(oracle, name, rows, k, full_k_model):
+    """Blocks whose largest magnitude is below 2^-90 or above 2^90 leave the prologue's inline-division quantiser and are
+    redone in the reference form (gemv.cu: `redo`); every prologue shape (2, 4 and > 4 blocks per warp), both kernel
+    instances.  ggml: quantize_row_q8_K [UPSTREAM-MEM ggml-quants.c]."""
+    import gpu_util as U
+    qt = GEMV_TYPES[name]
+    raw, x = _gemv_case(oracle, qt, rows, k, rows + k)
+    x[:256] *= np.float32(1e-33)
+    x[256:512] *= np.float32(1e30)
+    x[512:768] = 0
+    x[k - 256:] *= np.float32(3e-30)
+    canon = oracle.matmul(qt, raw, rows, k, x, mode="canon")
+    w = U.gpu_repack(qt, raw, rows, k)
+    (got,) = U.gpu_gemv([(w, qt, rows)], k, x, full_k_model=full_k_model)
+    assert np.array_equal(_bits(got), _bits(canon)), f"{(got != canon).sum()} of {rows} outputs differ from the canon oracle"
+
+
 def test_gemv_zero_rows_and_bad_args(oracle):
     import torch
     import gpu_util as U
