@@ -218,10 +218,13 @@ def time_decode(eng, steps, warmup, prompt, barrier, sampler=None, rank=0):
         sampler.start()          # the fork happens BEFORE the barriers: no rank waits for it inside the timed region
     barrier()
     barrier()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()   # no-op unless a profiler attached with --profile-from-start off: then exactly the timed region
     ev0.record(eng.stream)
     eng.decode(steps)
     ev1.record(eng.stream)
     barrier()
+    torch.cuda.profiler.stop()
     return ev0.elapsed_time(ev1)
 
 

@@ -40,3 +40,23 @@ if "--source" in sys.argv:
     top = sorted(body, key=lambda r: -int(r[ci["# Samples"]] or 0))[:25]
     for r in top:
         print(r[ci["# Samples"]].rjust(6), r[ci["Instructions Executed"]].rjust(8), r[ci["Source"]][:110])
+
+if "--table" in sys.argv:   # one line per launch: the columns the round's notes quote
+    cols = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+            ("smsp__inst_executed.sum", "warp_inst"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+            ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn_smem"),
+            ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "st_noinst"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_longsb"),
+            ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
+            ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_barrier"),
+            ("sm__icc_request_hit_rate.pct", "icc_hit%")]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    ix = [(n, hdr.index(m)) for m, n in cols if m in hdr]
+    print("units: " + ", ".join(f"{n}={rows[1][i]}" for n, i in ix if rows[1][i]))
+    print(" ".join(f"{n:>10s}" for n, _ in ix) + "  kernel")
+    kn = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        print(" ".join(f"{float(r[i] or 0):10.2f}" for _, i in ix) + "  " + r[kn].split("(")[0].replace("void ", ""))
