@@ -73,7 +73,9 @@ def read_key(args) -> str | None:
     return None
 
 
-def main(argv=None) -> int:
+def main(argv=None, engine_factory=None) -> int:
+    """engine_factory(args) -> engine: dependency injection for the CPU tests of the process contract (tests/fake_llama_server.py
+    puts the oracle behind this very main loop); the product entry point never passes it -- the engine is the GPU one or nothing."""
     argv = sys.argv[1:] if argv is None else argv
     args, unknown = build_parser().parse_known_args(argv)
     if args.version:
@@ -155,9 +157,12 @@ def main(argv=None) -> int:
         from .model import Engine
         t0 = time.time()
         log(f"main: loading model {args.model}")
-        eng = Engine(args.model, n_ctx=args.ctx_size, device=args.device, use_graph=not args.no_graph,
-                     use_pdl=not args.no_pdl, n_slots=max(1, args.parallel), verbose=args.verbose,
-                     tp_rank=rank if world > 1 else 0, tp_size=world)
+        if engine_factory is not None:
+            eng = engine_factory(args)
+        else:
+            eng = Engine(args.model, n_ctx=args.ctx_size, device=args.device, use_graph=not args.no_graph,
+                         use_pdl=not args.no_pdl, n_slots=max(1, args.parallel), verbose=args.verbose,
+                         tp_rank=rank if world > 1 else 0, tp_size=world)
         eng.warmup()
         info.update({"n_layer": eng.hp.n_layer, "n_embd": eng.hp.d, "weights_gb": round(eng.weight_bytes / 1e9, 3)})
         log(f"main: model loaded in {time.time() - t0:.2f} s ({eng.weight_bytes / 1e9:.2f} GB of weights in HBM, "

@@ -49,6 +49,15 @@ class OracleEngine:
         self.slots = [OracleSlot(O.OracleLlama(path, n_ctx=n_ctx, mode="canon"), n_ctx, i) for i in range(n_slots)]
         self.batch_capable = n_slots > 1
         self.batch = OracleBatch(self)
+        m = self.slots[0].m
+        self.hp = type("HP", (), {"n_layer": getattr(m, "n_layer", 0), "d": getattr(m, "d", 0)})()   # what cli.main reports
+        self.weight_bytes = 0
+
+    def warmup(self):
+        pass
+
+    def close(self):
+        pass
 
 
 class OracleBatch:

@@ -273,6 +273,78 @@ def test_unchanged_reference_gateway_and_benchmark_in_front(oracle, backend):
         gw.wait(timeout=10)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "scripts", "start.sh")), reason="reference checkout not mounted (set REF_DIR)")
+def test_reference_start_sh_runs_the_whole_stack(oracle, tiny_path, tmp_path):
+    """The reference's launcher, scripts/start.sh, run by bash from where it is mounted.  Only its two container paths are
+    redirected while it is piped to bash (/app/llama-server -> a stand-in that runs the product's cli.main with the oracle
+    engine; /opt/app/scripts -> the mounted scripts directory): version probe (start.sh:359-365), argv (473-494), the
+    `| tee` log pipe (516-517), the authenticated /health poll and the no-key probe (600-646), health server, gateway,
+    a chat completion through the gateway with a key from AUTH_KEYS_FILE, and the SIGTERM shutdown (402-430)."""
+    import shutil
+    import signal
+    if not shutil.which("bash") or not shutil.which("curl"):
+        pytest.skip("needs bash and curl")
+    app = tmp_path / "app"
+    app.mkdir()
+    fake = app / "llama-server"
+    fake.write_text(f"#!/bin/sh\nexec {sys.executable} {os.path.join(ROOT, 'tests', 'fake_llama_server.py')} \"$@\"\n")
+    fake.chmod(0o755)
+    data = tmp_path / "data"
+    (data / "models").mkdir(parents=True)
+    os.symlink(tiny_path, data / "models" / "tiny.gguf")
+    user_key = "sk-test-" + "k" * 40
+    (data / "api_keys.txt").write_text(f"tester:{user_key}\n")
+    script = open(os.path.join(REF, "scripts", "start.sh")).read()
+    assert "/app/llama-server" in script and "/opt/app/scripts" in script
+    script = script.replace("/app/llama-server", str(fake)).replace("/opt/app/scripts", os.path.join(REF, "scripts"))
+    gport, bport, hport = free_port(), free_port(), free_port()
+    env = {**os.environ, "DATA_DIR": str(data), "MODEL_NAME": "tiny.gguf", "PORT": str(gport), "PORT_BACKEND": str(bport),
+           "PORT_HEALTH": str(hport), "NGL": "0", "CTX": "160", "THREADS": "2", "EXTRA_ARGS": "--parallel 2 --temp 0 --ignore-eos",
+           "AUTH_ENABLED": "true", "INSTANCE_ID": f"pytest-{os.getpid()}", "MAX_CONCURRENT_REQUESTS": "2"}
+    proc = subprocess.Popen(["bash", "-s"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            env=env, start_new_session=True)
+    proc.stdin.write(script)
+    proc.stdin.close()
+    lines = []
+    threading.Thread(target=lambda: lines.extend(proc.stdout), daemon=True).start()
+    try:
+        ok = False
+        for _ in range(600):
+            assert proc.poll() is None, "".join(lines)[-4000:]
+            try:
+                if call(gport, "GET", "/ping", key=None, raw=True)[0] == 200 and any("Services running" in ln for ln in lines):
+                    ok = True
+                    break
+            except OSError:
+                pass
+            time.sleep(0.1)
+        assert ok, "".join(lines)[-4000:]
+        log = "".join(lines)
+        assert "llama-server: version:" in log                                   # start.sh:364-365 printed OUR --version line
+        assert "Backend responds correctly" in log                               # start.sh:600-635, authenticated /health poll
+        # start.sh:637-646 then probes /health WITHOUT a key: upstream's llama-server keeps /health public (and gateway.py:336-344
+        # relies on that), so the launcher prints its warning -- for the real binary and for this one alike -- and carries on
+        assert "Backend responded without authentication" in log
+        st, h = call(gport, "GET", "/health", key=None)
+        assert st == 200 and h["backend"]["status"] == "ok"
+        body = {"model": "default", "messages": MSG, "max_tokens": 10, "temperature": 0}
+        assert call(gport, "POST", "/v1/chat/completions", body, key=None)[0] == 401           # the gateway's own auth
+        st, r = call(gport, "POST", "/v1/chat/completions", body, key=user_key)
+        tok_path = {"tok": __import__("ggufb200.tokenizer", fromlist=["Tokenizer"]).Tokenizer(
+            __import__("ggufb200.gguf_reader", fromlist=["GGUFFile"]).GGUFFile(tiny_path).meta), "path": tiny_path}
+        assert st == 200 and r["choices"][0]["message"]["content"] == expected_text(oracle, tok_path, MSG, 10)[0]
+        logs = list((data / "logs" / "llama").glob("*_server_*.log"))           # the tee'd backend log (start.sh:505-517)
+        assert logs and "server is listening" in logs[0].read_text()
+        os.killpg(proc.pid, signal.SIGTERM)
+        assert proc.wait(timeout=60) is not None
+        time.sleep(0.5)
+        with pytest.raises(OSError):                                             # the backend is gone with its launcher
+            call(bport, "GET", "/health", key=None)
+    finally:
+        if proc.poll() is None:
+            os.killpg(proc.pid, signal.SIGKILL)
+
+
 def test_prompt_cache_reuses_the_common_prefix(oracle, backend):
     """a follow-up request whose prompt starts like the previous one only processes the new tokens (llama-server's
     cache_prompt); the text must be what a cold run of the full prompt gives"""
