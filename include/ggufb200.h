@@ -147,10 +147,14 @@ int64_t ggb_gemv_smem_bytes(const ggb_gemv_args* args);
 int ggb_gemv_grid(const ggb_gemv_args* args);
 
 /* ---- K2: dequant-GEMM on tcgen05 / TMEM (ggml mul_mat with many activation columns: prefill, large batches)
- *   Y[tokens][y_stride >= rows] (f32) = X[tokens][k] (bf16) . W[rows][k]^T,  W in tile-SoA layout, k % 128 == 0.
- * Weights are dequantised exactly (f32) and rounded to bf16 inside the kernel; accumulation is f32 in TMEM. */
-int ggb_gemm(int type, const void* w, int rows, int k, const void* x_bf16, int tokens, float* y, int64_t y_stride, void* stream);
-int ggb_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+ *   Y[tokens][y_stride >= rows] (f32) = X[tokens][k] (f16) . W[rows][k]^T,  W in tile-SoA layout, k % 128 == 0.
+ * Weights are dequantised exactly (f32) and rounded to f16 inside the kernel (kind::f16 with fp16 operands: 11 significand bits); accumulation is f32 in TMEM. */
+int ggb_gemm(int type, const void* w, int rows, int k, const void* x_f16, int tokens, float* y, int64_t y_stride, void* stream);
+int ggb_f32_to_f16(const float* x, void* y_f16, int64_t n, void* stream);
+/* y = f16(d * q): x [m][k] quantised as the CPU path quantises the activation operand (Q8_K per 256 elements; Q8_0 per 32
+ * when q8_0 != 0) and dequantised again -- the activation operand of ggb_gemm that keeps it within f16 rounding of ggml's
+ * integer dot (quantize_row_q8_K / q8_0 + vec_dot) */
+int ggb_act_fakequant_f16(const float* x, void* y_f16, int64_t k, int m, int q8_0, void* stream);
 
 /* ---- batched glue of the prefill path (ggml get_rows / rope / cpy / flash_attn_ext / add on T tokens) */
 int ggb_embed_rows(int type, const void* token_embd, int64_t k, const int32_t* ids_dev, int tokens, float* out, void* stream);

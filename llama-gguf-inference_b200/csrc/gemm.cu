@@ -1,11 +1,11 @@
 // gemm.cu -- K2: dequant-GEMM for prefill / large batches on the 5th-generation tensor cores.
-//   Y[tokens][rows] = X[tokens][K] . W[rows][K]^T      W quantised (tile-SoA Q4_K / Q6_K / Q8_0), X bf16
+//   Y[tokens][rows] = X[tokens][K] . W[rows][K]^T      W quantised (tile-SoA Q4_K / Q6_K / Q8_0), X f16
 // Stands in for ggml-cuda's mul_mat_q / dequantise+cuBLAS path of the reference's backend [UPSTREAM-MEM].
 //
 // One CTA computes a 128 (weight rows) x 256 (tokens) output tile:
 //   * 8 producer warps unpack the packed weights of the current 128-wide K block straight into shared memory as
-//     bf16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
-//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5); the matching bf16
+//     f16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
+//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5); the matching f16
 //     activation block arrives next to it by cp.async, issued one K block ahead; weight tiles are prefetched into
 //     L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
 //   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) eight
@@ -14,10 +14,10 @@
 //     signals the epilogue;
 //   * epilogue: the 8 producer warps read the accumulator with tcgen05.ld (32x32b.x32) and store Y.
 // Two shared-memory stages (2 x 96 KB); TMEM allocation = 256 columns.
-// Numerics: weights are dequantised exactly as ggml does (f32) and rounded to bf16, activations are bf16, products
+// Numerics: weights are dequantised exactly as ggml does (f32) and rounded to f16, activations are f16, products
 // are accumulated in f32 by the tensor core -- the tolerance-level path (like upstream's CUDA backend for batches),
 // not the bit-exact integer path of the decode GEMV.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "layout.cuh"
@@ -61,17 +61,18 @@ __device__ __forceinline__ uint64_t gm_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                    /* SWIZZLE_128B */
     return d;
 }
-// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A and B,
-// N>>3 at [17,23), M>>4 at [24,29)
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29).  fp16 operands, not f16: the same UTCHMMA rate with 11 significand bits instead of
+// 8 -- the prefill's end-to-end error against the integer path drops 8x (tests/test_gpu_engine.py).
 __device__ __forceinline__ uint32_t gm_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
 }
 
-// byte offset of the 16-byte chunk `c` (0..7 inside a 128-byte swizzle row) of row `r` in a [rows][64 bf16] atom
+// byte offset of the 16-byte chunk `c` (0..7 inside a 128-byte swizzle row) of row `r` in a [rows][64 f16] atom
 __device__ __forceinline__ uint32_t gm_sw(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {   /* two dequantised weights -> f16x2 (|w| << 65504) */
+    const __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
@@ -79,11 +80,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float u2f(uint32_t n) { return __fsub_rn(__uint_as_float(0x4B000000u | n), 8388608.0f); }
 __device__ __forceinline__ float u2f_bias(uint32_t n, float bias) { return __fsub_rn(__uint_as_float(0x4B000000u | n), bias); }   /* n - (bias - 2^23) */
 
-// dequantise 64 consecutive elements (one "unit") of a weight row into 8 chunks of 8 bf16
+// dequantise 64 consecutive elements (one "unit") of a weight row into 8 chunks of 8 f16
 struct Chunk8 { uint4 c[8]; };
 
 // The dequantiser is split into "fetch the packed bytes of my 64 elements" (issued one K block ahead, so the L2 /
-// HBM latency hides behind the conversion of the current block) and "convert them to 8 chunks of 8 bf16".
+// HBM latency hides behind the conversion of the current block) and "convert them to 8 chunks of 8 f16".
 template <int TYPE> struct Raw;
 template <> struct Raw<GGB_TYPE_Q4_K> { uint4 q0, q1, h; int g; };
 template <> struct Raw<GGB_TYPE_Q5_K> { uint4 q0, q1, h; uint2 qhu; int g; };
@@ -123,7 +124,7 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q4_K>& R, Chunk8& 
                 const uint32_t word = w[2 * c + (j >> 1)];
                 const uint32_t b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
                 const uint32_t b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
-                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
+                r[j] = pack_f16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
             }
             o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
         }
@@ -165,7 +166,7 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q5_K>& R, Chunk8& 
                 const int e0 = 8 * c + 2 * j;
                 const uint32_t b0 = ((word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF) | (((bits >> e0) & 1) << 4);
                 const uint32_t b1 = ((word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF) | (((bits >> (e0 + 1)) & 1) << 4);
-                r[j] = pack_bf16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
+                r[j] = pack_f16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
             }
             o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
         }
@@ -211,7 +212,7 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q6_K>& R, Chunk8& 
                         const uint32_t q6 = lo | (((hb >> (2 * r)) & 3) << 4);
                         v[e] = __fmul_rn(ds, u2f_bias(q6, 8388640.0f));      /* (float)(q6 - 32), exactly */
                     }
-                    pk[jj] = pack_bf16(v[0], v[1]);
+                    pk[jj] = pack_f16(v[0], v[1]);
                 }
                 o.c[4 * rr + 2 * t + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -239,7 +240,7 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q8_0>& R, Chunk8& 
                 /* int8 -> float: flip the sign bit (value + 128 as unsigned), then subtract 2^23 + 128 (exact) */
                 const float a = __fmul_rn(u2f_bias(((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
                 const float b = __fmul_rn(u2f_bias(((w[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
-                pk[j] = pack_bf16(a, b);
+                pk[j] = pack_f16(a, b);
             }
             o.c[2 * i + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -248,7 +249,7 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q8_0>& R, Chunk8& 
 
 template <int TYPE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, const __nv_bfloat16* __restrict__ X, int tokens,
+gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, const __half* __restrict__ X, int tokens,
             float* __restrict__ Y, int64_t y_stride) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], bar_acc;
@@ -285,9 +286,9 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
 #pragma unroll 4
             for (int i = 0; i < 16; i++) {
                 const int id = i * 256 + pt;
-                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 bf16 = 128 K */
+                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 f16 = 128 K */
                 const bool live = tok0 + tk < tokens;
-                const __nv_bfloat16* src = X + (int64_t)(live ? tok0 + tk : 0) * K + kb * GM_BK + kc * 8;
+                const __half* src = X + (int64_t)(live ? tok0 + tk : 0) * K + kb * GM_BK + kc * 8;
                 const uint32_t dst = gm_smem_u32(sB + (kc >> 3) * (GM_BN * 128) + gm_sw(tk, kc & 7));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(live ? 16 : 0) : "memory");   /* src-size 0: zero fill */
             }
@@ -415,21 +416,22 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
     }
 }
 
-// ------------------------------------------------------------------ f32 -> bf16 activations
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+// ------------------------------------------------------------------ f32 -> f16 activations (saturating: no Inf from an outlier)
+__device__ __forceinline__ __half f2h_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t n) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i + 1 < n) {
-        *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(x[i], x[i + 1]);
+        *reinterpret_cast<__half2*>(y + i) = __halves2half2(f2h_sat(x[i]), f2h_sat(x[i + 1]));
     } else if (i < n) {
-        y[i] = __float2bfloat16_rn(x[i]);
+        y[i] = f2h_sat(x[i]);
     }
 }
 
-extern "C" int ggb_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
-    if (n < 0 || (n && (!x || !y_bf16))) GGB_FAIL(GGB_ERR_ARG, "ggb_f32_to_bf16: bad argument");
+extern "C" int ggb_f32_to_f16(const float* x, void* y_f16, int64_t n, void* stream) {
+    if (n < 0 || (n && (!x || !y_f16))) GGB_FAIL(GGB_ERR_ARG, "ggb_f32_to_f16: bad argument");
     if (n == 0) return GGB_OK;
-    f32_to_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, n);
-    GGB_CHECK_LAUNCH("ggb_f32_to_bf16");
+    f32_to_f16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y_f16, n);
+    GGB_CHECK_LAUNCH("ggb_f32_to_f16");
     return GGB_OK;
 }
 
@@ -442,23 +444,23 @@ static int launch_gemm(const void* w, int rows, int k, const void* x, int tokens
         attr = true;
     }
     dim3 grid((rows + GM_BM - 1) / GM_BM, (tokens + GM_BN - 1) / GM_BN);
-    gemm_kernel<TYPE><<<grid, GM_THREADS, smem, st>>>((const uint8_t*)w, ggb_row_stride(TYPE, k), rows, k, (const __nv_bfloat16*)x, tokens, y, y_stride);
+    gemm_kernel<TYPE><<<grid, GM_THREADS, smem, st>>>((const uint8_t*)w, ggb_row_stride(TYPE, k), rows, k, (const __half*)x, tokens, y, y_stride);
     GGB_CHECK_LAUNCH("ggb_gemm");
     return GGB_OK;
 }
 
-extern "C" int ggb_gemm(int type, const void* w, int rows, int k, const void* x_bf16, int tokens, float* y, int64_t y_stride, void* stream) {
+extern "C" int ggb_gemm(int type, const void* w, int rows, int k, const void* x_f16, int tokens, float* y, int64_t y_stride, void* stream) {
     if (rows < 0 || tokens < 0 || k <= 0 || (k % GM_BK)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: k=%d must be a positive multiple of %d", k, GM_BK);
     if (rows == 0 || tokens == 0) return GGB_OK;
-    if (!w || !x_bf16 || !y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: null pointer");
-    if (((uintptr_t)w & 15) || ((uintptr_t)x_bf16 & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: operands must be 16-byte aligned");
+    if (!w || !x_f16 || !y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: null pointer");
+    if (((uintptr_t)w & 15) || ((uintptr_t)x_f16 & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: operands must be 16-byte aligned");
     if (y_stride < rows) GGB_FAIL(GGB_ERR_ARG, "ggb_gemm: y_stride smaller than rows");
     cudaStream_t st = (cudaStream_t)stream;
     switch (type) {
-        case GGB_TYPE_Q4_K: return launch_gemm<GGB_TYPE_Q4_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
-        case GGB_TYPE_Q5_K: return launch_gemm<GGB_TYPE_Q5_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
-        case GGB_TYPE_Q6_K: return launch_gemm<GGB_TYPE_Q6_K>(w, rows, k, x_bf16, tokens, y, y_stride, st);
-        case GGB_TYPE_Q8_0: return launch_gemm<GGB_TYPE_Q8_0>(w, rows, k, x_bf16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q4_K: return launch_gemm<GGB_TYPE_Q4_K>(w, rows, k, x_f16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q5_K: return launch_gemm<GGB_TYPE_Q5_K>(w, rows, k, x_f16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q6_K: return launch_gemm<GGB_TYPE_Q6_K>(w, rows, k, x_f16, tokens, y, y_stride, st);
+        case GGB_TYPE_Q8_0: return launch_gemm<GGB_TYPE_Q8_0>(w, rows, k, x_f16, tokens, y, y_stride, st);
         default: GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemm: unsupported weight type %d", type);
     }
 }

@@ -39,6 +39,43 @@ __global__ void quantize_q8_0_kernel(const float* __restrict__ x, int8_t* __rest
     if (!(i & 3)) d[i >> 2] = db;
 }
 
+// Activation operand of the prefill GEMM: x quantised EXACTLY as the CPU path quantises it (Q8_K per 256, or Q8_0 per 32)
+// and dequantised again, d * q, as f16.  The tensor-core product then differs from ggml's integer dot only by the f16
+// rounding of the two operands (2^-11 each) -- feeding the GEMM the unquantised activations instead makes it a DIFFERENT
+// (more precise) computation than the reference's, 1-4e-2 away from it in the logits of the synthetic models.
+__global__ void act_fakequant_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t nblocks, int q8_0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   /* one warp per 256 elements */
+    if (b >= nblocks) return;
+    const float4* p = reinterpret_cast<const float4*>(x + b * 256 + lane * 8);
+    const float4 v0 = p[0], v1 = p[1];
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float dd;
+    Q8Codes c;
+    if (q8_0) { uint16_t db; c = warp_quantize_q8_0(v, dd, db); }
+    else c = warp_quantize_q8_K(v, lane, dd);
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t w = i < 2 ? c.q.x : c.q.y;
+        const int q0 = (int)(int8_t)((w >> (16 * (i & 1))) & 0xFF), q1 = (int)(int8_t)((w >> (16 * (i & 1) + 8)) & 0xFF);
+        const float a = fminf(fmaxf(__fmul_rn(dd, (float)q0), -65504.0f), 65504.0f), bb = fminf(fmaxf(__fmul_rn(dd, (float)q1), -65504.0f), 65504.0f);
+        const __half2 h = __floats2half2_rn(a, bb);
+        out[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(y + b * 256 + lane * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+extern "C" int ggb_act_fakequant_f16(const float* x, void* y_f16, int64_t k, int m, int q8_0, void* stream) {
+    if (k < 0 || (k % 256) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_act_fakequant_f16: k=%lld must be a multiple of 256", (long long)k);
+    const int64_t nb = k / 256 * m;
+    if (nb == 0) return GGB_OK;
+    if (!x || !y_f16 || ((uintptr_t)x & 15) || ((uintptr_t)y_f16 & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_act_fakequant_f16: null or unaligned pointer");
+    act_fakequant_f16_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y_f16, nb, q8_0);
+    GGB_CHECK_LAUNCH("ggb_act_fakequant_f16");
+    return GGB_OK;
+}
+
 extern "C" int ggb_quantize_q8_K(const float* x, int8_t* qs, float* d, int16_t* bsums, int64_t k, int m, void* stream) {
     if (k < 0 || (k % 256) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_quantize_q8_K: k=%lld must be a multiple of 256", (long long)k);
     const int64_t nb = k / 256 * m;

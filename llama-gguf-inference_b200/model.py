@@ -404,6 +404,8 @@ class Engine:
         self.load_seconds = time.time() - t0
         self.gemm_prefill_min = int(os.environ.get("GGB_GEMM_PREFILL_MIN", "64"))   # prompts at least this long use the GEMM path
         self.prefill_chunk = 2048
+        self.prefill_raw_act = os.environ.get("GGB_PREFILL_RAW_ACT", "0") == "1"
+        self.prefill_exact_attn = os.environ.get("GGB_PREFILL_EXACT_ATTN", "0") == "1"
         self._pf = None
         n_slots = max(1, n_slots)
         kvd = (self.hp.n_kv // self.tp_size) * self.hp.head_dim
@@ -542,8 +544,14 @@ class Engine:
         def gemm(w, xb, y):
             cabi.check(lib.ggb_gemm(w.type, w.ptr, w.rows, w.k, xb.data_ptr(), T, y.data_ptr(), w.rows, s), "gemm")
 
-        def to_bf16(x, n):
-            cabi.check(lib.ggb_f32_to_bf16(x.data_ptr(), B["xb"].data_ptr(), n, s), "f32_to_bf16")
+        def to_f16(x, k, w):
+            """the GEMM's activation operand: x [T][k] quantised like the CPU path quantises it for a weight of w's format
+            (Q8_K, or Q8_0 for Q8_0 weights) and dequantised to f16 -- the product then matches ggml's integer dot to f16
+            rounding.  GGB_PREFILL_RAW_ACT=1: plain f16 conversion (no activation quantisation), for comparison."""
+            if self.prefill_raw_act:
+                cabi.check(lib.ggb_f32_to_f16(x.data_ptr(), B["xb"].data_ptr(), T * k, s), "f32_to_f16")
+            else:
+                cabi.check(lib.ggb_act_fakequant_f16(x.data_ptr(), B["xb"].data_ptr(), k, T, 1 if w.type == G.GGML_Q8_0 else 0, s), "act_fakequant_f16")
 
         ids, pos, slots = [], [], []
         for sl, toks, start in jobs:
@@ -556,24 +564,28 @@ class Engine:
             cabi.check(lib.ggb_embed_rows(self.emb_type, self.emb_canon.data_ptr(), hp.d, meta[0].data_ptr(), T, X.data_ptr(), s), "embed_rows")
             for i, L in enumerate(self.layers):
                 cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["attn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_bf16(XN, T * hp.d)
+                to_f16(XN, hp.d, L["wq"])
                 gemm(L["wq"], B["xb"], B["q"]); gemm(L["wk"], B["xb"], B["k"]); gemm(L["wv"], B["xb"], B["v"])
                 cabi.check(lib.ggb_rope_kv_batch(B["q"].data_ptr(), B["k"].data_ptr(), B["v"].data_ptr(), T, meta[1].data_ptr(), meta[2].data_ptr(),
                                                  slot_stride, hp.n_head, hp.n_kv, hp.head_dim, hp.n_rot, self.rope_tab.data_ptr(),
                                                  self.k_all[0, i].data_ptr(), self.v_all[0, i].data_ptr(), s), "rope_kv_batch")
                 off = 0
-                for sl, toks, start in jobs:
+                if self.prefill_exact_attn:   # diagnosis: the decode attention (f64 sums), one batch entry per prompt token
+                    cabi.check(lib.ggb_attn_decode_batch(B["q"].data_ptr(), self.k_all[0, i].data_ptr(), self.v_all[0, i].data_ptr(),
+                                                         meta[1].data_ptr(), meta[2].data_ptr(), slot_stride, T, hp.n_head, hp.n_kv, hp.head_dim,
+                                                         self.n_ctx, B["att"].data_ptr(), 0, s), "attn_decode_batch")
+                for sl, toks, start in ([] if self.prefill_exact_attn else jobs):
                     cabi.check(lib.ggb_attn_prefill(B["q"].data_ptr() + off * qd * 4, self.k_all[sl, i].data_ptr(), self.v_all[sl, i].data_ptr(),
                                                     len(toks), start, hp.n_head, hp.n_kv, hp.head_dim, B["att"].data_ptr() + off * qd * 4, s), "attn_prefill")
                     off += len(toks)
-                to_bf16(B["att"], T * qd)
+                to_f16(B["att"], qd, L["wo"])
                 gemm(L["wo"], B["xb"], Y)
                 cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
                 cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["ffn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_bf16(XN, T * hp.d)
+                to_f16(XN, hp.d, L["wg"])
                 gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
                 cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
-                to_bf16(B["gate"], T * hp.ff)
+                to_f16(B["gate"], hp.ff, L["wd"])
                 gemm(L["wd"], B["xb"], Y)
                 cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
             off = 0
@@ -598,7 +610,7 @@ class Engine:
             qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
             self._pf = {"cap": cap, "x": f32(hp.d), "xn": f32(hp.d), "y": f32(hp.d), "q": f32(qd), "k": f32(kvd), "v": f32(kvd),
                         "att": f32(qd), "gate": f32(hp.ff), "up": f32(hp.ff),
-                        "xb": torch.empty(cap * max(hp.d, hp.ff, qd), dtype=torch.bfloat16, device=dev)}
+                        "xb": torch.empty(cap * max(hp.d, hp.ff, qd), dtype=torch.float16, device=dev)}
         return self._pf
 
     @property

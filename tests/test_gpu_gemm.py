@@ -1,8 +1,8 @@
 """-m gpu: the tcgen05/TMEM dequant-GEMM (csrc/gemm.cu) against the oracle.
 
-The GEMM is the tolerance-level path (bf16 operands, f32 accumulation in TMEM) -- the same trade upstream's CUDA
+The GEMM is the tolerance-level path (fp16 operands, f32 accumulation in TMEM) -- the same trade upstream's CUDA
 backend makes for batches.  Two checks: (1) against an exact emulation of its own arithmetic (oracle-dequantised
-weights rounded to bf16, bf16 activations, float64 accumulation) the error must be f32-accumulation noise; (2)
+weights rounded to f16, f16 activations, float64 accumulation) the error must be f32-accumulation noise; (2)
 against the reference integer path (oracle mul_mat, Q8_K activations) it must sit inside the stated 1e-2."""
 import numpy as np
 import pytest
@@ -13,10 +13,8 @@ pytestmark = pytest.mark.gpu
 TYPES = {"q4_k": 12, "q5_k": 13, "q6_k": 14, "q8_0": 8}
 
 
-def bf16_round(a: np.ndarray) -> np.ndarray:
-    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
-    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
-    return u.astype(np.uint32).view(np.float32)
+def f16_round(a: np.ndarray) -> np.ndarray:
+    return np.clip(np.ascontiguousarray(a, dtype=np.float32), -65504.0, 65504.0).astype(np.float16).astype(np.float32)
 
 
 @pytest.mark.parametrize("name", list(TYPES))
@@ -33,21 +31,49 @@ def test_gemm_matches_oracle(oracle, name, rows, k, tokens):
     X = rng.standard_normal((tokens, k)).astype(np.float32)
     w = U.gpu_repack(qt, raw, rows, k)
     xd = U.to_dev(X)
-    xb = torch.empty((tokens, k), dtype=torch.bfloat16, device=U.DEV)
-    cabi.check(L.ggb_f32_to_bf16(xd.data_ptr(), xb.data_ptr(), tokens * k, U.stream_ptr()))
+    xb = torch.empty((tokens, k), dtype=torch.float16, device=U.DEV)
+    cabi.check(L.ggb_f32_to_f16(xd.data_ptr(), xb.data_ptr(), tokens * k, U.stream_ptr()))
     y = torch.full((tokens, rows), float("nan"), dtype=torch.float32, device=U.DEV)
     cabi.check(L.ggb_gemm(qt, w.data_ptr(), rows, k, xb.data_ptr(), tokens, y.data_ptr(), rows, U.stream_ptr()))
     U.sync()
     got = y.cpu().numpy()
     assert np.isfinite(got).all()
-    assert np.array_equal(xb.float().cpu().numpy(), bf16_round(X))
+    assert np.array_equal(xb.float().cpu().numpy(), f16_round(X))
     Wd = oracle.dequantize(raw, qt, rows * k).reshape(rows, k)
-    exact = bf16_round(X).astype(np.float64) @ bf16_round(Wd).astype(np.float64).T
+    exact = f16_round(X).astype(np.float64) @ f16_round(Wd).astype(np.float64).T
     scale = np.abs(exact).max()
     assert np.abs(got - exact).max() <= 2e-5 * scale * max(1.0, (k / 1024) ** 0.5), np.abs(got - exact).max() / scale
     if tokens <= 64:   # the reference integer path, column by column (slow on the CPU: keep it small)
         ref = oracle.matmul(qt, raw, rows, k, X)
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+@pytest.mark.parametrize("rows,k,tokens", [(300, 2048, 17), (256, 4096, 33), (64, 14336, 8)])
+def test_gemm_on_requantised_activations_tracks_the_integer_path(oracle, name, rows, k, tokens):
+    """The prefill feeds the GEMM d * q -- the activations quantised exactly as the CPU path quantises them (Q8_K / Q8_0),
+    dequantised to f16 (ggb_act_fakequant_f16).  Against ggml's integer dot (oracle mul_mat) only the f16 rounding of the
+    two operands is left: <= 1e-3 of the largest output, ten times inside the north-star 1e-2."""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    qt = TYPES[name]
+    rng = np.random.default_rng(rows * 7 + k + tokens + qt)
+    be, _ = oracle.BLOCK[qt]
+    raw = rand_blocks(qt, rows * k // be, rng)
+    X = (rng.standard_normal((tokens, k)) * rng.uniform(0.05, 20.0, size=(tokens, 1))).astype(np.float32)
+    w = U.gpu_repack(qt, raw, rows, k)
+    xd = U.to_dev(X)
+    xh = torch.empty((tokens, k), dtype=torch.float16, device=U.DEV)
+    cabi.check(L.ggb_act_fakequant_f16(xd.data_ptr(), xh.data_ptr(), k, tokens, 1 if qt == 8 else 0, U.stream_ptr()))
+    y = torch.full((tokens, rows), float("nan"), dtype=torch.float32, device=U.DEV)
+    cabi.check(L.ggb_gemm(qt, w.data_ptr(), rows, k, xh.data_ptr(), tokens, y.data_ptr(), rows, U.stream_ptr()))
+    U.sync()
+    got = y.cpu().numpy()
+    ref = oracle.matmul(qt, raw, rows, k, X)
+    err = np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err.max() <= 1e-3, err.max()
 
 
 def test_gemm_rejects_bad_arguments():

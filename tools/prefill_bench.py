@@ -16,7 +16,7 @@ def gemm_alone(L, qt, rows, k, T, reps=10):
     dev = torch.device("cuda", 0)
     stride = L.ggb_repacked_row_stride(qt, k)
     w = torch.randint(0, 256, (rows * stride + 16,), dtype=torch.uint8, device=dev)
-    x = torch.randn(T, k, device=dev).to(torch.bfloat16)
+    x = torch.randn(T, k, device=dev).to(torch.float16)
     y = torch.empty(T, rows, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
