@@ -93,6 +93,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout_s: float = 8.0):
+        """block until nvidia-smi has delivered its first row (it needs 0.3-2 s to start on a multi-GPU box): the timed region
+        that follows is short, and a sampler that only starts reporting after it would say nothing about it"""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -216,6 +223,7 @@ def time_decode(eng, steps, warmup, prompt, barrier, sampler=None, rank=0):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler is not None and rank == 0:
         sampler.start()          # the fork happens BEFORE the barriers: no rank waits for it inside the timed region
+        sampler.wait_first()
     barrier()
     barrier()
     torch.cuda.synchronize()
