@@ -6,8 +6,10 @@
 //   * 8 producer warps unpack the packed weights of the current 128-wide K block straight into shared memory as
 //     f16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
 //     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5); the matching f16
-//     activation block arrives next to it by cp.async, issued one K block ahead; weight tiles are prefetched into
-//     L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
+//     activation block arrives next to it by TMA -- two cp.async.bulk.tensor.2d (SASS UTMALDG) per K block from a
+//     SWIZZLE_128B tensor map over X, issued by one thread one K block ahead, completing on the stage's mbarrier
+//     (round 1 used 4096 cp.async per block: a quarter of the producers' instructions); weight tiles are
+//     prefetched into L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
 //   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) eight
 //     times per K block from shared-memory descriptors; the f32 accumulator (128 lanes x 256 columns) lives in
 //     TMEM; tcgen05.commit releases the shared-memory stage back to the producers and, after the last block,
@@ -17,6 +19,7 @@
 // Numerics: weights are dequantised exactly as ggml does (f32) and rounded to f16, activations are f16, products
 // are accumulated in f32 by the tensor core -- the tolerance-level path (like upstream's CUDA backend for batches),
 // not the bit-exact integer path of the decode GEMV.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -76,6 +79,24 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {   /* two dequan
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// ---- packed-half arithmetic of the operand production (round 2).  The producers were the GEMM's bottleneck: ~12 f32
+// instructions per weight (extract, int->float, mul, sub, round, pack) kept the tensor pipe at 31 %.  Now two weights travel
+// per instruction: a byte b becomes the half 1024 + b by ONE byte-permute (0x6400 | b: halves in [1024, 2048) are spaced 1
+// apart), HADD2 removes the bias exactly, and one HFMA2 / HMUL2 applies the sub-block scale (and the Q4_K/Q5_K offset).
+//   Q8_0   d * q with d already an f16: the product is rounded once -- identical to "dequantise exactly, round to f16";
+//   K-quants  the sub-block scale d*sc (and dmin*m) is rounded to f16 BEFORE the multiply: each weight carries up to ~3
+//          f16 roundings instead of one (still ~1e-3 of ggml's integer dot per GEMM, tests/test_gpu_gemm.py).
+__device__ __forceinline__ uint32_t h2_of_bytes(uint32_t x, uint32_t sel) { return __byte_perm(x, 0x64646464u, sel); }   /* sel 0x4140: bytes 0,1; 0x4342: bytes 2,3 */
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+// (byte - bias) * scale + offset for the two selected bytes of x; bias as the f16 pattern of 1024 + bias
+__device__ __forceinline__ uint32_t h2_scale(uint32_t x, uint32_t sel, uint32_t bias1024, __half2 scale, __half2 offset) {
+    return as_u32(__hfma2(__hsub2(as_h2(h2_of_bytes(x, sel)), as_h2(bias1024)), scale, offset));
+}
+__device__ __forceinline__ uint32_t h2_scale0(uint32_t x, uint32_t sel, uint32_t bias1024, __half2 scale) {
+    return as_u32(__hmul2(__hsub2(as_h2(h2_of_bytes(x, sel)), as_h2(bias1024)), scale));
+}
+
 // small unsigned integer -> float without the (quarter-rate) I2F unit: 2^23 + n as a bit pattern, minus the bias (exact)
 __device__ __forceinline__ float u2f(uint32_t n) { return __fsub_rn(__uint_as_float(0x4B000000u | n), 8388608.0f); }
 __device__ __forceinline__ float u2f_bias(uint32_t n, float bias) { return __fsub_rn(__uint_as_float(0x4B000000u | n), bias); }   /* n - (bias - 2^23) */
@@ -109,24 +130,17 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q4_K>& R, Chunk8& 
         s0 = f & 63; s1 = (f >> 6) & 63; m0 = (f >> 12) & 63; m1 = (f >> 18) & 63;
     }
     const float d = h2f((uint16_t)(R.h.x & 0xFFFF)), dmin = h2f((uint16_t)(R.h.x >> 16));
-    const float d0 = __fmul_rn(d, (float)s0), d1 = __fmul_rn(d, (float)s1);
-    const float n0 = __fmul_rn(dmin, (float)m0), n1 = __fmul_rn(dmin, (float)m1);
+    const __half2 dd[2] = {__float2half2_rn(__fmul_rn(d, (float)s0)), __float2half2_rn(__fmul_rn(d, (float)s1))};
+    const __half2 nn[2] = {__float2half2_rn(-__fmul_rn(dmin, (float)m0)), __float2half2_rn(-__fmul_rn(dmin, (float)m1))};
     const uint32_t w[8] = {R.q0.x, R.q0.y, R.q0.z, R.q0.w, R.q1.x, R.q1.y, R.q1.z, R.q1.w};   /* bytes 0..31 of the 32-byte group */
     // elements 0..31 = low nibbles (sub-block 2g), 32..63 = high nibbles (sub-block 2g+1)
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const float dd = half ? d1 : d0, nn = half ? n1 : n0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {       /* 8 elements = bytes 8c..8c+7 = words 2c, 2c+1 */
-            uint32_t r[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t word = w[2 * c + (j >> 1)];
-                const uint32_t b0 = (word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF;
-                const uint32_t b1 = (word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF;
-                r[j] = pack_f16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
-            }
-            o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
+            const uint32_t x0 = (half ? (w[2 * c] >> 4) : w[2 * c]) & 0x0F0F0F0Fu, x1 = (half ? (w[2 * c + 1] >> 4) : w[2 * c + 1]) & 0x0F0F0F0Fu;
+            o.c[4 * half + c] = make_uint4(h2_scale(x0, 0x4140u, 0x64006400u, dd[half], nn[half]), h2_scale(x0, 0x4342u, 0x64006400u, dd[half], nn[half]),
+                                           h2_scale(x1, 0x4140u, 0x64006400u, dd[half], nn[half]), h2_scale(x1, 0x4342u, 0x64006400u, dd[half], nn[half]));
         }
     }
 }
@@ -150,25 +164,18 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q5_K>& R, Chunk8& 
         s0 = f & 63; s1 = (f >> 6) & 63; m0 = (f >> 12) & 63; m1 = (f >> 18) & 63;
     }
     const float d = h2f((uint16_t)(R.h.x & 0xFFFF)), dmin = h2f((uint16_t)(R.h.x >> 16));
-    const float d0 = __fmul_rn(d, (float)s0), d1 = __fmul_rn(d, (float)s1);
-    const float n0 = __fmul_rn(dmin, (float)m0), n1 = __fmul_rn(dmin, (float)m1);
+    const __half2 dd[2] = {__float2half2_rn(__fmul_rn(d, (float)s0)), __float2half2_rn(__fmul_rn(d, (float)s1))};
+    const __half2 nn[2] = {__float2half2_rn(-__fmul_rn(dmin, (float)m0)), __float2half2_rn(-__fmul_rn(dmin, (float)m1))};
     const uint32_t w[8] = {R.q0.x, R.q0.y, R.q0.z, R.q0.w, R.q1.x, R.q1.y, R.q1.z, R.q1.w};
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const float dd = half ? d1 : d0, nn = half ? n1 : n0;
         const uint32_t bits = half ? R.qhu.y : R.qhu.x;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {       /* elements 8c..8c+7 of the sub-block */
-            uint32_t r[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t word = w[2 * c + (j >> 1)];
-                const int e0 = 8 * c + 2 * j;
-                const uint32_t b0 = ((word >> (16 * (j & 1) + (half ? 4 : 0))) & 0xF) | (((bits >> e0) & 1) << 4);
-                const uint32_t b1 = ((word >> (16 * (j & 1) + 8 + (half ? 4 : 0))) & 0xF) | (((bits >> (e0 + 1)) & 1) << 4);
-                r[j] = pack_f16(__fsub_rn(__fmul_rn(dd, u2f(b0)), nn), __fsub_rn(__fmul_rn(dd, u2f(b1)), nn));
-            }
-            o.c[4 * half + c] = make_uint4(r[0], r[1], r[2], r[3]);
+        for (int c = 0; c < 4; c++) {       /* elements 8c..8c+7 of the sub-block: nibble | fifth bit << 4, four bits spread per word */
+            const uint32_t f0 = (((bits >> (8 * c)) & 0xFu) * 0x02040810u) & 0x10101010u, f1 = (((bits >> (8 * c + 4)) & 0xFu) * 0x02040810u) & 0x10101010u;
+            const uint32_t x0 = ((half ? (w[2 * c] >> 4) : w[2 * c]) & 0x0F0F0F0Fu) | f0, x1 = ((half ? (w[2 * c + 1] >> 4) : w[2 * c + 1]) & 0x0F0F0F0Fu) | f1;
+            o.c[4 * half + c] = make_uint4(h2_scale(x0, 0x4140u, 0x64006400u, dd[half], nn[half]), h2_scale(x0, 0x4342u, 0x64006400u, dd[half], nn[half]),
+                                           h2_scale(x1, 0x4140u, 0x64006400u, dd[half], nn[half]), h2_scale(x1, 0x4342u, 0x64006400u, dd[half], nn[half]));
         }
     }
 }
@@ -196,26 +203,15 @@ __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q6_K>& R, Chunk8& 
 #pragma unroll
         for (int t = 0; t < 2; t++) {       /* 16 elements l = 16t..16t+15 of row-group r */
             const uint4 ql = R.ql[2 * rr + t], qh = R.qh[t];
-            const float ds = __fmul_rn(d, (float)(int8_t)((sc64 >> (8 * (2 * r + t))) & 0xFF));
+            const __half2 ds = __float2half2_rn(__fmul_rn(d, (float)(int8_t)((sc64 >> (8 * (2 * r + t))) & 0xFF)));
             const uint32_t lw[4] = {ql.x, ql.y, ql.z, ql.w}, hw[4] = {qh.x, qh.y, qh.z, qh.w};
+            uint32_t q[4];                  /* the 6-bit codes of 4 bytes per word: low or high nibble | two bits of qh << 4 */
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t pk[4];
+            for (int i = 0; i < 4; i++) q[i] = (((r & 2) ? (lw[i] >> 4) : lw[i]) & 0x0F0F0F0Fu) | (((hw[i] >> (2 * r)) & 0x03030303u) << 4);
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    float v[2];
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int i = 8 * c + 2 * jj + e;                 /* byte index 0..15 */
-                        const uint32_t lb = (lw[i >> 2] >> (8 * (i & 3))) & 0xFF, hb = (hw[i >> 2] >> (8 * (i & 3))) & 0xFF;
-                        const uint32_t lo = (r & 2) ? (lb >> 4) : (lb & 0xF);
-                        const uint32_t q6 = lo | (((hb >> (2 * r)) & 3) << 4);
-                        v[e] = __fmul_rn(ds, u2f_bias(q6, 8388640.0f));      /* (float)(q6 - 32), exactly */
-                    }
-                    pk[jj] = pack_f16(v[0], v[1]);
-                }
-                o.c[4 * rr + 2 * t + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            for (int c = 0; c < 2; c++)     /* (q - 32) * (d * sc): bias pattern 1024 + 32 = 0x6420 */
+                o.c[4 * rr + 2 * t + c] = make_uint4(h2_scale0(q[2 * c], 0x4140u, 0x64206420u, ds), h2_scale0(q[2 * c], 0x4342u, 0x64206420u, ds),
+                                                     h2_scale0(q[2 * c + 1], 0x4140u, 0x64206420u, ds), h2_scale0(q[2 * c + 1], 0x4342u, 0x64206420u, ds));
         }
     }
 }
@@ -229,27 +225,19 @@ __device__ __forceinline__ void dq_fetch(Raw<GGB_TYPE_Q8_0>& R, const uint8_t* t
 __device__ __forceinline__ void dq_convert(const Raw<GGB_TYPE_Q8_0>& R, Chunk8& o) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float d = h2f((uint16_t)((i >> 1) ? (R.dd >> 16) : (R.dd & 0xFFFF)));
-        const uint32_t w[4] = {R.w[i].x, R.w[i].y, R.w[i].z, R.w[i].w};
+        const uint32_t dbits = (i >> 1) ? (R.dd >> 16) : (R.dd & 0xFFFF);
+        const __half2 d2 = as_h2(dbits | (dbits << 16));              /* the block's f16 scale, as stored */
+        const uint32_t w[4] = {R.w[i].x ^ 0x80808080u, R.w[i].y ^ 0x80808080u, R.w[i].z ^ 0x80808080u, R.w[i].w ^ 0x80808080u};   /* q + 128 */
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i0 = 8 * c + 2 * j;
-                /* int8 -> float: flip the sign bit (value + 128 as unsigned), then subtract 2^23 + 128 (exact) */
-                const float a = __fmul_rn(u2f_bias(((w[i0 >> 2] >> (8 * (i0 & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
-                const float b = __fmul_rn(u2f_bias(((w[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFF) ^ 0x80u, 8388736.0f), d);
-                pk[j] = pack_f16(a, b);
-            }
-            o.c[2 * i + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+        for (int c = 0; c < 2; c++)         /* (byte - 128) * d: bias pattern 1024 + 128 = 0x6480; one rounding, as exact-then-round */
+            o.c[2 * i + c] = make_uint4(h2_scale0(w[2 * c], 0x4140u, 0x64806480u, d2), h2_scale0(w[2 * c], 0x4342u, 0x64806480u, d2),
+                                        h2_scale0(w[2 * c + 1], 0x4140u, 0x64806480u, d2), h2_scale0(w[2 * c + 1], 0x4342u, 0x64806480u, d2));
     }
 }
 
 template <int TYPE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, const __half* __restrict__ X, int tokens,
+gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, const __grid_constant__ CUtensorMap tmapX, int tokens,
             float* __restrict__ Y, int64_t y_stride) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], bar_acc;
@@ -261,7 +249,8 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
     uint8_t* stage_base = (uint8_t*)(((uintptr_t)gsm + 1023) & ~(uintptr_t)1023);
 
     if (tid == 0) {
-        for (int s = 0; s < GM_STAGES; s++) { gm_mbar_init(gm_smem_u32(&bar_full[s]), GM_PRODUCER_WARPS); gm_mbar_init(gm_smem_u32(&bar_empty[s]), 1); }
+        /* full: one arrival per producer warp (A stored) + the expect_tx arrival of the thread that issued the TMA copies of B */
+        for (int s = 0; s < GM_STAGES; s++) { gm_mbar_init(gm_smem_u32(&bar_full[s]), GM_PRODUCER_WARPS + 1); gm_mbar_init(gm_smem_u32(&bar_empty[s]), 1); }
         gm_mbar_init(gm_smem_u32(&bar_acc), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -281,18 +270,14 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         // tiles (2048 elements per row) are pulled into L2 one tile ahead so the dequantiser's loads are L2 hits.
         const int pt = tid;                                   /* 0..255 */
         const int tile_bytes = ggb_sb_bytes(TYPE) * GGB_TILE_SB;
-        auto issue_b = [&](int kb) {
-            uint8_t* sB = stage_base + (kb % GM_STAGES) * GM_STAGE_BYTES + GM_A_BYTES;
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {
-                const int id = i * 256 + pt;
-                const int tk = id >> 4, kc = id & 15;          /* kc: 16 chunks of 8 f16 = 128 K */
-                const bool live = tok0 + tk < tokens;
-                const __half* src = X + (int64_t)(live ? tok0 + tk : 0) * K + kb * GM_BK + kc * 8;
-                const uint32_t dst = gm_smem_u32(sB + (kc >> 3) * (GM_BN * 128) + gm_sw(tk, kc & 7));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(live ? 16 : 0) : "memory");   /* src-size 0: zero fill */
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+        auto issue_b = [&](int kb) {   /* ONE thread: the 256-token x 128-K activation block as two 64-wide swizzle atoms */
+            const int st = kb % GM_STAGES;
+            const uint32_t sB = gm_smem_u32(stage_base + st * GM_STAGE_BYTES + GM_A_BYTES), bar = gm_smem_u32(&bar_full[st]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)GM_B_BYTES) : "memory");
+#pragma unroll
+            for (int h = 0; h < 2; h++)   /* rows beyond `tokens` are zero-filled by the copy engine */
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(sB + h * (GM_BN * 128)), "l"(&tmapX), "r"(kb * GM_BK + h * 64), "r"(tok0), "r"(bar) : "memory");
         };
         auto prefetch_tile = [&](int t) {                      /* one thread per row pulls tile t of its row into L2 */
             if (pt < GM_BM && row0 + pt < rows && t * GGB_TILE_ELEMS < K) {
@@ -313,8 +298,7 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
             dq_fetch(raw, W + (int64_t)grow * w_stride + (int64_t)t * tile_bytes, 4 * nsb, nsb, ek);
         };
         if (arow) fetch_a(0);
-        gm_mbar_wait(gm_smem_u32(&bar_empty[0]), 1);           /* fresh barrier: returns at once */
-        issue_b(0);
+        if (tid == 0) issue_b(0);
         for (int kb = 0; kb < nkb; kb++) {
             const int s = kb % GM_STAGES;
             uint8_t* sA = stage_base + s * GM_STAGE_BYTES;
@@ -340,13 +324,10 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
                 for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(atom + gm_sw(r, c)) = ch.c[c];
                 if (!FETCH_EARLY && arow && kb + 1 < nkb) fetch_a(kb + 1);
             }
-            if (kb + 1 < nkb) {
+            if (kb + 1 < nkb) {   /* the next stage must be free before anybody writes A into it; its B copy starts now */
                 const int s1 = (kb + 1) % GM_STAGES;
                 gm_mbar_wait(gm_smem_u32(&bar_empty[s1]), (((kb + 1) / GM_STAGES) & 1) ^ 1);
-                issue_b(kb + 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");    /* B(kb) has landed; B(kb+1) may still fly */
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (tid == 0) issue_b(kb + 1);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the tensor core */
             __syncwarp();
@@ -435,8 +416,30 @@ extern "C" int ggb_f32_to_f16(const float* x, void* y_f16, int64_t n, void* stre
     return GGB_OK;
 }
 
+// tensor map over X [tokens][k] f16: box = 64 K-elements (128 B, one swizzle atom row) x GM_BN tokens, SWIZZLE_128B -- the
+// shared-memory image is exactly the K-major layout the UMMA descriptors describe (16-byte chunk c of row r at c ^ (r & 7))
+typedef CUresult (*ggb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ggb_encode_tiled_fn encode_tiled() {
+    static ggb_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (ggb_encode_tiled_fn)p;
+    }
+    return fn;
+}
+
 template <int TYPE>
 static int launch_gemm(const void* w, int rows, int k, const void* x, int tokens, float* y, int64_t y_stride, cudaStream_t st) {
+    ggb_encode_tiled_fn enc = encode_tiled();
+    if (!enc) GGB_FAIL(GGB_ERR_CUDA, "ggb_gemm: the driver does not export cuTensorMapEncodeTiled");
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)tokens}, strides[1] = {(cuuint64_t)k * 2};
+    const cuuint32_t box[2] = {64, GM_BN}, estr[2] = {1, 1};
+    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) GGB_FAIL(GGB_ERR_CUDA, "ggb_gemm: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     static bool attr = false;
     const size_t smem = GM_STAGES * GM_STAGE_BYTES + 1024;
     if (!attr) {
@@ -444,7 +447,7 @@ static int launch_gemm(const void* w, int rows, int k, const void* x, int tokens
         attr = true;
     }
     dim3 grid((rows + GM_BM - 1) / GM_BM, (tokens + GM_BN - 1) / GM_BN);
-    gemm_kernel<TYPE><<<grid, GM_THREADS, smem, st>>>((const uint8_t*)w, ggb_row_stride(TYPE, k), rows, k, (const __half*)x, tokens, y, y_stride);
+    gemm_kernel<TYPE><<<grid, GM_THREADS, smem, st>>>((const uint8_t*)w, ggb_row_stride(TYPE, k), rows, k, tmap, tokens, y, y_stride);
     GGB_CHECK_LAUNCH("ggb_gemm");
     return GGB_OK;
 }

@@ -108,13 +108,19 @@ class Slot:
         self.y64 = torch.zeros(hp.d, dtype=torch.float64, device=dev)       # row-split partial sums (tensor parallel)
         self.key = torch.zeros(1, dtype=torch.int64, device=dev)            # sharded arg-max key
         self.attn_ws = torch.zeros(max(16, self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim)), dtype=torch.uint8, device=dev)
-        self.tok_dev, self.pos_dev, self.step_dev = i32(1), i32(1), i32(1)
+        self._tokpos = i32(2)      # token id and position side by side: the host sets both with ONE 8-byte copy
+        self.tok_dev, self.pos_dev, self.step_dev = self._tokpos[0:1], self._tokpos[1:2], i32(1)
         self.out_tokens = i32(self.max_new)
         self.part_val, self.part_idx = f32(1), i32(1)
         a = self._head_args()
         self.n_part = self.lib.ggb_gemv_grid(C.byref(a))
         self.part_val, self.part_idx = f32(self.n_part), i32(self.n_part)
-        self.host_i32 = torch.zeros(4, dtype=torch.int32).pin_memory()
+        # pinned staging for (token, position): a ring with one event per entry, so that a host-driven step needs no
+        # synchronisation of its own before the buffer can be rewritten (the read-back of the token is the step's only sync)
+        self.host_ring = torch.zeros((8, 2), dtype=torch.int32).pin_memory()
+        self.host_ev = [torch.cuda.Event() for _ in range(8)]
+        self.host_used = [False] * 8
+        self.host_i = 0
         self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.host_logits = None
         self._graphs = {}
@@ -255,10 +261,16 @@ class Slot:
         self.n_past = 0
 
     def _set_tok_pos(self, tok: int, pos: int):
-        self.host_i32[0] = tok
-        self.host_i32[1] = pos
-        self.tok_dev.copy_(self.host_i32[0:1], non_blocking=True)
-        self.pos_dev.copy_(self.host_i32[1:2], non_blocking=True)
+        i = self.host_i
+        self.host_i = (i + 1) % len(self.host_ev)
+        if self.host_used[i]:
+            self.host_ev[i].synchronize()     # the copy that last read this entry has run (8 entries ago: normally long done)
+        buf = self.host_ring[i]
+        buf[0] = tok
+        buf[1] = pos
+        self._tokpos.copy_(buf, non_blocking=True)
+        self.host_ev[i].record(self.torch.cuda.current_stream())
+        self.host_used[i] = True
 
     def warmup(self):
         """Run every graph once (sets kernel attributes, captures graphs), then clear the state."""
@@ -303,7 +315,6 @@ class Slot:
             for i in range(first, len(tokens)):
                 self._set_tok_pos(int(tokens[i]), start + i)
                 self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
-                self.stream.synchronize()  # host_i32 is reused for the next token
         self.n_past = start + len(tokens)
         self.chain_valid = True
 

@@ -42,7 +42,11 @@ def test_gemm_matches_oracle(oracle, name, rows, k, tokens):
     Wd = oracle.dequantize(raw, qt, rows * k).reshape(rows, k)
     exact = f16_round(X).astype(np.float64) @ f16_round(Wd).astype(np.float64).T
     scale = np.abs(exact).max()
-    assert np.abs(got - exact).max() <= 2e-5 * scale * max(1.0, (k / 1024) ** 0.5), np.abs(got - exact).max() / scale
+    # Q8_0 operands are exactly "dequantise, round to f16" (d is an f16, d * q is rounded once): only f32-accumulation noise
+    # is left.  K-quant operands round the sub-block scale d * sc (and dmin * m) to f16 before the packed-half multiply
+    # (csrc/gemm.cu): up to ~3 f16 roundings per weight, coherent inside a sub-block.
+    tol = 2e-5 * max(1.0, (k / 1024) ** 0.5) if name == "q8_0" else 1e-3
+    assert np.abs(got - exact).max() <= tol * scale, np.abs(got - exact).max() / scale
     if tokens <= 64:   # the reference integer path, column by column (slow on the CPU: keep it small)
         ref = oracle.matmul(qt, raw, rows, k, X)
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
