@@ -155,6 +155,11 @@ int ggb_f32_to_f16(const float* x, void* y_f16, int64_t n, void* stream);
  * when q8_0 != 0) and dequantised again -- the activation operand of ggb_gemm that keeps it within f16 rounding of ggml's
  * integer dot (quantize_row_q8_K / q8_0 + vec_dot) */
 int ggb_act_fakequant_f16(const float* x, void* y_f16, int64_t k, int m, int q8_0, void* stream);
+/* the same on silu(gate) * up (ggml silu + mul + the quantisation of ffn_down's activation operand in one pass) */
+int ggb_swiglu_fakequant_f16(const float* gate, const float* up, void* y_f16, int64_t k, int m, int q8_0, void* stream);
+/* x [m][k] += add (optional, may be NULL), then y = the quantised-dequantised f16 of rms_norm(x) * w: ggml add + rms_norm + mul +
+ * the activation quantisation in front of the next ggb_gemm, one pass per token row */
+int ggb_add_rmsnorm_fakequant_f16(float* x, const float* add, const float* w, void* y_f16, int64_t k, int m, float eps, int q8_0, void* stream);
 
 /* ---- batched glue of the prefill path (ggml get_rows / rope / cpy / flash_attn_ext / add on T tokens) */
 int ggb_embed_rows(int type, const void* token_embd, int64_t k, const int32_t* ids_dev, int tokens, float* out, void* stream);

@@ -43,13 +43,22 @@ __global__ void quantize_q8_0_kernel(const float* __restrict__ x, int8_t* __rest
 // and dequantised again, d * q, as f16.  The tensor-core product then differs from ggml's integer dot only by the f16
 // rounding of the two operands (2^-11 each) -- feeding the GEMM the unquantised activations instead makes it a DIFFERENT
 // (more precise) computation than the reference's, 1-4e-2 away from it in the logits of the synthetic models.
-__global__ void act_fakequant_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t nblocks, int q8_0) {
+// `up` != nullptr: x is the gate projection and the quantised vector is silu(x) * up (ggml silu + mul fused in front of the
+// quantisation: the SwiGLU output never makes a round trip through HBM as floats)
+__global__ void act_fakequant_f16_kernel(const float* __restrict__ x, const float* __restrict__ up, __half* __restrict__ y, int64_t nblocks, int q8_0) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   /* one warp per 256 elements */
     if (b >= nblocks) return;
     const float4* p = reinterpret_cast<const float4*>(x + b * 256 + lane * 8);
     const float4 v0 = p[0], v1 = p[1];
-    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (up) {
+        const float4* pu = reinterpret_cast<const float4*>(up + b * 256 + lane * 8);
+        const float4 u0 = pu[0], u1 = pu[1];
+        const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = silu_mul_ref(v[i], u[i]);
+    }
     float dd;
     Q8Codes c;
     if (q8_0) { uint16_t db; c = warp_quantize_q8_0(v, dd, db); }
@@ -71,8 +80,19 @@ extern "C" int ggb_act_fakequant_f16(const float* x, void* y_f16, int64_t k, int
     const int64_t nb = k / 256 * m;
     if (nb == 0) return GGB_OK;
     if (!x || !y_f16 || ((uintptr_t)x & 15) || ((uintptr_t)y_f16 & 15)) GGB_FAIL(GGB_ERR_ARG, "ggb_act_fakequant_f16: null or unaligned pointer");
-    act_fakequant_f16_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y_f16, nb, q8_0);
+    act_fakequant_f16_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, nullptr, (__half*)y_f16, nb, q8_0);
     GGB_CHECK_LAUNCH("ggb_act_fakequant_f16");
+    return GGB_OK;
+}
+
+extern "C" int ggb_swiglu_fakequant_f16(const float* gate, const float* up, void* y_f16, int64_t k, int m, int q8_0, void* stream) {
+    if (k < 0 || (k % 256) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_swiglu_fakequant_f16: k=%lld must be a multiple of 256", (long long)k);
+    const int64_t nb = k / 256 * m;
+    if (nb == 0) return GGB_OK;
+    if (!gate || !up || !y_f16 || ((uintptr_t)gate & 15) || ((uintptr_t)up & 15) || ((uintptr_t)y_f16 & 15))
+        GGB_FAIL(GGB_ERR_ARG, "ggb_swiglu_fakequant_f16: null or unaligned pointer");
+    act_fakequant_f16_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, (cudaStream_t)stream>>>(gate, up, (__half*)y_f16, nb, q8_0);
+    GGB_CHECK_LAUNCH("ggb_swiglu_fakequant_f16");
     return GGB_OK;
 }
 
@@ -129,6 +149,76 @@ extern "C" int ggb_rms_norm(const float* x, const float* w, float* y, int64_t k,
     if (!x || !y) GGB_FAIL(GGB_ERR_ARG, "ggb_rms_norm: null pointer");
     rms_norm_kernel<<<m, 512, 0, (cudaStream_t)stream>>>(x, w, y, k, eps);
     GGB_CHECK_LAUNCH("ggb_rms_norm");
+    return GGB_OK;
+}
+
+// Prefill glue in one pass per token row: x += add (ggml_add of the previous projection, optional), rms_norm(x) * w,
+// quantised as the CPU path quantises the next matmul's activation operand, written as f16 (d * q) for ggb_gemm.
+// The arithmetic is rms_norm_kernel's + act_fakequant_f16_kernel's; three launches and two f32 round trips less per use.
+__global__ void __launch_bounds__(256) add_rmsnorm_fakequant_f16_kernel(float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ w,
+                                                                      __half* __restrict__ y, int64_t k, float eps, int q8_0) {
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* xr = x + (int64_t)blockIdx.x * k;
+    const float* ar = add ? add + (int64_t)blockIdx.x * k : nullptr;
+    __half* yr = y + (int64_t)blockIdx.x * k;
+    const int nblk = (int)(k / 256);
+    double s = 0.0;
+    for (int b = warp; b < nblk; b += 8) {
+        float4* p = reinterpret_cast<float4*>(xr + b * 256 + lane * 8);
+        float4 v0 = p[0], v1 = p[1];
+        if (ar) {
+            const float4* q = reinterpret_cast<const float4*>(ar + b * 256 + lane * 8);
+            const float4 a0 = q[0], a1 = q[1];
+            v0 = make_float4(__fadd_rn(v0.x, a0.x), __fadd_rn(v0.y, a0.y), __fadd_rn(v0.z, a0.z), __fadd_rn(v0.w, a0.w));
+            v1 = make_float4(__fadd_rn(v1.x, a1.x), __fadd_rn(v1.y, a1.y), __fadd_rn(v1.z, a1.z), __fadd_rn(v1.w, a1.w));
+            p[0] = v0; p[1] = v1;
+        }
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += (double)__fmul_rn(v[i], v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float mean = (float)(tot / (double)k);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(mean + eps));
+    for (int b = warp; b < nblk; b += 8) {
+        const float4* p = reinterpret_cast<const float4*>(xr + b * 256 + lane * 8);   /* this thread's own stores: L1 hits */
+        const float4* g = reinterpret_cast<const float4*>(w + b * 256 + lane * 8);
+        const float4 v0 = p[0], v1 = p[1], g0 = g[0], g1 = g[1];
+        const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}, gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(xv[i], scale), gv[i]);
+        float dd;
+        Q8Codes c;
+        if (q8_0) { uint16_t db; c = warp_quantize_q8_0(v, dd, db); }
+        else c = warp_quantize_q8_K(v, lane, dd);
+        uint32_t out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t wd = i < 2 ? c.q.x : c.q.y;
+            const int q0 = (int)(int8_t)((wd >> (16 * (i & 1))) & 0xFF), q1 = (int)(int8_t)((wd >> (16 * (i & 1) + 8)) & 0xFF);
+            const float a = fminf(fmaxf(__fmul_rn(dd, (float)q0), -65504.0f), 65504.0f), bb = fminf(fmaxf(__fmul_rn(dd, (float)q1), -65504.0f), 65504.0f);
+            const __half2 h = __floats2half2_rn(a, bb);
+            out[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(yr + b * 256 + lane * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+extern "C" int ggb_add_rmsnorm_fakequant_f16(float* x, const float* add, const float* w, void* y_f16, int64_t k, int m, float eps, int q8_0, void* stream) {
+    if (k <= 0 || (k % 256) || m < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_add_rmsnorm_fakequant_f16: k=%lld must be a positive multiple of 256", (long long)k);
+    if (m == 0) return GGB_OK;
+    if (!x || !w || !y_f16 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y_f16 & 15) || ((uintptr_t)add & 15))
+        GGB_FAIL(GGB_ERR_ARG, "ggb_add_rmsnorm_fakequant_f16: null or unaligned pointer");
+    add_rmsnorm_fakequant_f16_kernel<<<m, 256, 0, (cudaStream_t)stream>>>(x, add, w, (__half*)y_f16, k, eps, q8_0);
+    GGB_CHECK_LAUNCH("ggb_add_rmsnorm_fakequant_f16");
     return GGB_OK;
 }
 

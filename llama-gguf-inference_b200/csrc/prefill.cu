@@ -333,15 +333,3 @@ extern "C" int ggb_attn_prefill(const float* q, const uint16_t* kcache, const ui
     if (head_dim == 64) return launch_attn_prefill<64>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out, st);
     GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_attn_prefill: head_dim=%d (supported: 64, 128)", head_dim);
 }
-
-// embedding gather for a list of tokens: out[t][k] = dequant(token_embd row ids[t]) -- one launch per token would do,
-// but prompts are long; this reuses ggb_dequant's element decode through a per-token row pointer.
-extern "C" int ggb_embed_row(int type, const void* token_embd, int64_t k, const int32_t* tok_dev, float* x, void* stream);
-extern "C" int ggb_embed_rows(int type, const void* token_embd, int64_t k, const int32_t* ids_dev, int tokens, float* out, void* stream) {
-    if (tokens < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_embed_rows: negative token count");
-    for (int t = 0; t < tokens; t++) {
-        const int rc = ggb_embed_row(type, token_embd, k, ids_dev + t, out + (int64_t)t * k, stream);
-        if (rc) return rc;
-    }
-    return GGB_OK;
-}

@@ -573,9 +573,20 @@ class Engine:
             meta = torch.tensor([ids, pos, slots], dtype=torch.int32).to(self.dev)
             X, XN, Y = B["x"], B["xn"], B["y"]
             cabi.check(lib.ggb_embed_rows(self.emb_type, self.emb_canon.data_ptr(), hp.d, meta[0].data_ptr(), T, X.data_ptr(), s), "embed_rows")
+            def norm_quant(add, norm_w, w):
+                """X += add (the previous projection's output, or None), then the GEMM operand of rms_norm(X) * norm_w for weight w"""
+                if self.prefill_raw_act:
+                    if add is not None:
+                        cabi.check(lib.ggb_add_f32(X.data_ptr(), add.data_ptr(), T * hp.d, s), "add")
+                    cabi.check(lib.ggb_rms_norm(X.data_ptr(), norm_w.data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
+                    to_f16(XN, hp.d, w)
+                else:
+                    cabi.check(lib.ggb_add_rmsnorm_fakequant_f16(X.data_ptr(), add.data_ptr() if add is not None else 0, norm_w.data_ptr(),
+                                                                 B["xb"].data_ptr(), hp.d, T, hp.eps, 1 if w.type == G.GGML_Q8_0 else 0, s),
+                               "add_rmsnorm_fakequant_f16")
+
             for i, L in enumerate(self.layers):
-                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["attn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_f16(XN, hp.d, L["wq"])
+                norm_quant(Y if i > 0 else None, L["attn_norm"], L["wq"])      # the previous layer's ffn_down output joins here
                 gemm(L["wq"], B["xb"], B["q"]); gemm(L["wk"], B["xb"], B["k"]); gemm(L["wv"], B["xb"], B["v"])
                 cabi.check(lib.ggb_rope_kv_batch(B["q"].data_ptr(), B["k"].data_ptr(), B["v"].data_ptr(), T, meta[1].data_ptr(), meta[2].data_ptr(),
                                                  slot_stride, hp.n_head, hp.n_kv, hp.head_dim, hp.n_rot, self.rope_tab.data_ptr(),
@@ -591,14 +602,16 @@ class Engine:
                     off += len(toks)
                 to_f16(B["att"], qd, L["wo"])
                 gemm(L["wo"], B["xb"], Y)
-                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
-                cabi.check(lib.ggb_rms_norm(X.data_ptr(), L["ffn_norm"].data_ptr(), XN.data_ptr(), hp.d, T, hp.eps, s), "rms_norm")
-                to_f16(XN, hp.d, L["wg"])
+                norm_quant(Y, L["ffn_norm"], L["wg"])
                 gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
-                cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
-                to_f16(B["gate"], hp.ff, L["wd"])
+                if self.prefill_raw_act:
+                    cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
+                    to_f16(B["gate"], hp.ff, L["wd"])
+                else:   # silu(gate) * up, quantised like the CPU path quantises ffn_down's input, as f16: one pass
+                    cabi.check(lib.ggb_swiglu_fakequant_f16(B["gate"].data_ptr(), B["up"].data_ptr(), B["xb"].data_ptr(), hp.ff, T,
+                                                            1 if L["wd"].type == G.GGML_Q8_0 else 0, s), "swiglu_fakequant_f16")
                 gemm(L["wd"], B["xb"], Y)
-                cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")
+            cabi.check(lib.ggb_add_f32(X.data_ptr(), Y.data_ptr(), T * hp.d, s), "add")     # the last layer's ffn_down
             off = 0
             for sl, toks, start in jobs:
                 slot = self.slots[sl]

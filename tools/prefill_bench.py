@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=2048)
     ap.add_argument("--gemm-only", action="store_true")
     ap.add_argument("--one", action="store_true", help="a single GEMM shape (for ncu)")
+    ap.add_argument("--profile-last", action="store_true", help="cudaProfilerStart/Stop around the last timed prefill (ncu --profile-from-start off)")
     a = ap.parse_args()
     L = cabi.lib()
     T = a.tokens
@@ -59,10 +60,14 @@ def main():
     for rep in range(3):
         eng.reset()
         torch.cuda.synchronize()
+        if a.profile_last and rep == 2:
+            torch.cuda.profiler.start()
         t0 = time.perf_counter()
         eng.prefill(prompt)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if a.profile_last and rep == 2:
+            torch.cuda.profiler.stop()
         flops = 2.0 * cfg.n_params_matmul * T
         print(f"prefill {a.model} {a.ftype} {T} tokens: {dt*1e3:8.1f} ms  {T/dt:9.0f} tok/s  {flops/dt/1e12:6.1f} TFLOP/s (matmul flops only)", flush=True)
     eng.decode(16)
