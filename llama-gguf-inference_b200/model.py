@@ -118,10 +118,12 @@ class Slot:
         # pinned staging for (token, position): a ring with one event per entry, so that a host-driven step needs no
         # synchronisation of its own before the buffer can be rewritten (the read-back of the token is the step's only sync)
         self.host_ring = torch.zeros((8, 2), dtype=torch.int32).pin_memory()
+        self.host_ring_np = self.host_ring.numpy()      # the same pinned memory: plain stores instead of tensor indexing
         self.host_ev = [torch.cuda.Event() for _ in range(8)]
         self.host_used = [False] * 8
         self.host_i = 0
         self.host_tok = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.host_tok_np = self.host_tok.numpy()
         self.host_logits = None
         self._graphs = {}
         # every GEMV of this model has k % 2048 == 0: all launches share the kernel instance without partial-tile code
@@ -265,10 +267,9 @@ class Slot:
         self.host_i = (i + 1) % len(self.host_ev)
         if self.host_used[i]:
             self.host_ev[i].synchronize()     # the copy that last read this entry has run (8 entries ago: normally long done)
-        buf = self.host_ring[i]
-        buf[0] = tok
-        buf[1] = pos
-        self._tokpos.copy_(buf, non_blocking=True)
+        self.host_ring_np[i, 0] = tok
+        self.host_ring_np[i, 1] = pos
+        self._tokpos.copy_(self.host_ring[i], non_blocking=True)
         self.host_ev[i].record(self.torch.cuda.current_stream())
         self.host_used[i] = True
 
@@ -330,15 +331,26 @@ class Slot:
         self.n_past += n_steps
 
     def feed(self, tok: int):
-        """Sampled decoding: the host chose `tok`; run it through the model and produce logits."""
-        self.prefill([tok])
+        """Sampled / host-driven decoding: the host chose `tok`; run it through the model and produce logits and the next
+        greedy token.  One 8-byte H2D copy (token, position) from pinned memory + one graph launch, no host synchronisation."""
+        if self.eng.tp_size > 1:
+            return self.prefill([tok])
+        if isinstance(tok, bool) or not 0 <= int(tok) < self.hp.vocab:
+            raise ValueError(f"token id {tok!r} is outside the vocabulary (0..{self.hp.vocab - 1})")
+        if self.n_past + 1 >= self.n_ctx:
+            raise ValueError(f"prompt of 1 tokens does not fit the context ({self.n_ctx})")
+        with self.torch.cuda.stream(self.stream):
+            self._set_tok_pos(int(tok), self.n_past)
+            self._run("prompt_last")
+        self.n_past += 1
+        self.chain_valid = True
 
     def read_last_token(self) -> int:
         """Device -> pinned host read of the newest greedy token (what a streaming server does per step)."""
         with self.torch.cuda.stream(self.stream):
             self.host_tok.copy_(self.tok_dev, non_blocking=True)
         self.stream.synchronize()
-        return int(self.host_tok[0])
+        return int(self.host_tok_np[0])
 
     def read_logits(self) -> np.ndarray:
         if self.host_logits is None:
