@@ -87,6 +87,69 @@ class Weight:
         return self.t.data_ptr()
 
 
+class _Stager:
+    """Pipelined weight upload (the load path behind start.sh's 30 s /health gate, scripts/start.sh:600-635): reader
+    threads copy row chunks of the memory-mapped GGUF file into a ring of pinned staging buffers while the chunks before
+    them travel host -> device (async copies from pinned memory) and are re-ordered into the tile-SoA layout on the GPU.
+    Buffers are handed out by the consumer in order, so a chunk is always uploaded in the order it was requested."""
+
+    _pinned: dict = {}
+    pin_seconds = 0.0
+
+    def __init__(self, torch, lib, stream, dev, n_buf: int = 6, buf_bytes: int = 64 << 20, threads: int = 4):
+        import concurrent.futures as cf
+        from collections import deque
+        self.torch, self.lib, self.stream, self.dev = torch, lib, stream, dev
+        self.buf_bytes = buf_bytes
+        key = (n_buf, buf_bytes)
+        if key not in _Stager._pinned:           # pinning host memory is slow: the ring is allocated once per process
+            t0 = time.time()
+            _Stager._pinned[key] = [torch.empty(buf_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_buf)]
+            _Stager.pin_seconds = time.time() - t0
+        self.bufs = _Stager._pinned[key]
+        self.nps = [b.numpy() for b in self.bufs]
+        self.evs = [torch.cuda.Event() for _ in range(n_buf)]
+        self.used = [False] * n_buf
+        self.free = deque(range(n_buf))
+        self.pending = deque()
+        self.pool = cf.ThreadPoolExecutor(max_workers=threads)
+        with torch.cuda.stream(stream):
+            self.dev_tmp = torch.empty(buf_bytes, dtype=torch.uint8, device=dev)   # canonical bytes of the chunk being re-ordered
+        self.bytes = 0
+
+    def _consume(self):
+        fut, idx, n, finish = self.pending.popleft()
+        fut.result()
+        with self.torch.cuda.stream(self.stream):
+            finish(self.bufs[idx][:n])
+            self.evs[idx].record(self.stream)
+        self.used[idx] = True
+        self.free.append(idx)
+
+    def submit(self, src: np.ndarray, finish):
+        """src: a uint8 view of at most buf_bytes of the mapped file; finish(pinned_tensor) enqueues what happens to it"""
+        n = src.size
+        assert n <= self.buf_bytes
+        if not self.free:
+            self._consume()
+        idx = self.free.popleft()
+        if self.used[idx]:
+            self.evs[idx].synchronize()        # the async copy that last read this buffer has run
+        fut = self.pool.submit(np.copyto, self.nps[idx][:n], src)
+        self.pending.append((fut, idx, n, finish))
+        self.bytes += n
+
+    def drain(self):
+        while self.pending:
+            self._consume()
+        self.stream.synchronize()
+
+    def close(self):
+        self.drain()
+        self.pool.shutdown()
+        self.nps, self.dev_tmp = [], None
+
+
 class Slot:
     """One sequence: KV cache, activations, device-side counters and the captured graphs that advance it."""
 
@@ -470,9 +533,19 @@ class Engine:
         return self.torch.cuda.current_stream().cuda_stream
 
     def _upload(self, name: str):
+        """canonical bytes of a tensor on the device (small tensors directly; large ones through the staging pipeline)"""
         torch = self.torch
-        raw = np.array(self.file.data(name))  # copy: torch refuses read-only mmap views
-        return torch.from_numpy(raw).to(self.dev, non_blocking=False)
+        src = self.file.data(name)
+        st = getattr(self, "_stager", None)
+        if st is None or src.size < (4 << 20):
+            raw = np.array(src)  # copy: torch refuses read-only mmap views
+            return torch.from_numpy(raw).to(self.dev, non_blocking=False)
+        with torch.cuda.stream(self.stream):
+            dst = torch.empty(src.size, dtype=torch.uint8, device=self.dev)
+        for o in range(0, src.size, st.buf_bytes):
+            n = min(st.buf_bytes, src.size - o)
+            st.submit(src[o:o + n], lambda pinned, o=o, n=n: dst[o:o + n].copy_(pinned, non_blocking=True))
+        return dst
 
     def _load_matrix(self, name: str, shard_as: str | None = None) -> Weight:
         torch = self.torch
@@ -483,6 +556,26 @@ class Engine:
         if k % 256:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
         sh = parallel.shard_of(shard_as or name, self.hp, self.tp_size, self.tp_rank)
+        st = getattr(self, "_stager", None)
+        if sh.kind == parallel.FULL and st is not None:
+            # row chunks: file -> pinned ring (reader threads) -> device staging (async copy) -> tile-SoA destination (ggb_repack
+            # on the chunk's rows); nothing waits for anything but a free staging buffer
+            rb = G.row_bytes(ti.ggml_type, k)
+            stride = self.lib.ggb_repacked_row_stride(ti.ggml_type, k)
+            with torch.cuda.stream(self.stream):     # the zero fill must be ordered before the chunks' re-ordering kernels
+                dst = torch.zeros(rows * stride + 16, dtype=torch.uint8, device=self.dev)
+            src = self.file.data(name)
+            per = max(1, st.buf_bytes // rb)
+            for r0 in range(0, rows, per):
+                nr = min(per, rows - r0)
+
+                def finish(pinned, r0=r0, nr=nr):
+                    tmp = st.dev_tmp[:nr * rb]
+                    tmp.copy_(pinned, non_blocking=True)
+                    cabi.check(self.lib.ggb_repack(ti.ggml_type, tmp.data_ptr(), dst.data_ptr() + r0 * stride, nr, k, self.stream.cuda_stream), f"repack {name}")
+                st.submit(src[r0 * rb:(r0 + nr) * rb], finish)
+            self.weight_bytes += rows * rb
+            return Weight(dst, ti.ggml_type, rows, k)
         if sh.kind == parallel.FULL:
             canon = self._upload(name)
         else:
@@ -509,6 +602,18 @@ class Engine:
     def _load_weights(self):
         hp, f = self.hp, self.file
         self.weight_bytes = 0
+        self._stager = None
+        if os.environ.get("GGB_LOAD_PIPELINE", "1") != "0":
+            self._stager = _Stager(self.torch, self.lib, self.stream, self.dev)
+        try:
+            self._load_tensors()
+        finally:
+            if self._stager is not None:
+                self._stager.close()
+                self._stager = None
+
+    def _load_tensors(self):
+        hp, f = self.hp, self.file
         emb = f.tensors["token_embd.weight"]
         self.emb_type = emb.ggml_type
         self.emb_canon = self._upload("token_embd.weight")  # canonical layout: get_rows reads one row
