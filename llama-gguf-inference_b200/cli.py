@@ -39,6 +39,8 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--top-p", type=float, default=0.95)
     ap.add_argument("-s", "--seed", type=int, default=None)
     ap.add_argument("--ignore-eos", action="store_true")
+    ap.add_argument("--embeddings", "--embedding", dest="embeddings", action="store_true", help="serve POST /v1/embeddings")
+    ap.add_argument("--pooling", default="mean", choices=["mean", "last"], help="pooling of the embeddings endpoint")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch")
@@ -180,6 +182,11 @@ def main(argv=None, engine_factory=None) -> int:
     sched = Scheduler(leader or eng, tok, ignore_eos=args.ignore_eos, log=log)
     sched.start()
     state.sched = sched
+    if args.embeddings:
+        if leader is not None or not hasattr(eng, "embed"):
+            log("warn: --embeddings is served by the single-GPU prefill path only; /v1/embeddings stays 501")
+        else:
+            state.embeddings = args.pooling
     state.ready.set()
     log(f"main: server is listening on http://{args.host}:{args.port} - starting the main loop")
 

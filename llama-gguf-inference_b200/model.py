@@ -742,6 +742,40 @@ class Engine:
             self.slots[sl].n_past = start + len(toks)
             self.slots[sl].chain_valid = True
 
+    def embed(self, tokens, slot: int = 0, pooling: str = "mean") -> np.ndarray:
+        """Sentence embedding of a prompt (llama-server --embeddings, docs/API_REFERENCE.md:540-590 of the reference): the
+        prompt runs through the tensor-core prefill, the final hidden states go through output_norm, are pooled over the
+        tokens ("mean", or "last") and L2-normalised (llama.cpp's default embd_normalize = 2).  Fills the slot's K/V for the
+        prompt (positions 0..n-1) like any prefill."""
+        if self.tp_size != 1:
+            raise cabi.GGBError("embeddings are served by the single-GPU prefill path")
+        if pooling not in ("mean", "last"):
+            raise ValueError(f"unsupported pooling {pooling!r} (mean, last)")
+        tokens = [int(t) for t in tokens]
+        if not tokens:
+            raise ValueError("empty input")
+        hp, lib = self.hp, self.lib
+        self.slots[slot].reset()
+        acc = np.zeros(hp.d, dtype=np.float64)
+        last = None
+        for c0 in range(0, len(tokens), self.prefill_chunk):
+            chunk = tokens[c0:c0 + self.prefill_chunk]
+            self.prefill_many([(slot, chunk, c0)], head=False)
+            T = len(chunk)
+            B = self._pf
+            with self.torch.cuda.stream(self.stream):
+                cabi.check(lib.ggb_rms_norm(B["x"].data_ptr(), self.out_norm.data_ptr(), B["xn"].data_ptr(), hp.d, T, hp.eps, self.stream.cuda_stream), "rms_norm")
+                h = B["xn"][:T * hp.d].view(T, hp.d)
+                h = h[-1:] if pooling == "last" else h
+                host = h.cpu().numpy()
+            if pooling == "last":
+                last = host[0].astype(np.float64)
+            else:
+                acc += host.astype(np.float64).sum(axis=0)
+        v = last if pooling == "last" else acc / len(tokens)
+        n = float(np.linalg.norm(v))
+        return (v / n if n > 0 else v).astype(np.float32)
+
     def prefill_buffers(self, T: int) -> dict:
         """activation buffers of the GEMM prefill path, sized for the largest chunk seen so far (shared by the slots)"""
         cap = max(T, 64)

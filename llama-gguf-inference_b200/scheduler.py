@@ -56,6 +56,7 @@ class Request:
     stop: list = field(default_factory=list)
     ignore_eos: bool = False
     cache_prompt: bool = True       # reuse the slot's KV cache for the longest common prefix with its previous sequence
+    embed: str = ""                 # "mean" / "last": an embedding request (no generation); the vector arrives as ("embedding", vec, n_tokens)
     events: "queue.Queue" = field(default_factory=queue.Queue)   # ("piece", text, token_id) | ("done", reason, usage) | ("error", msg)
     cancelled: threading.Event = field(default_factory=threading.Event)
     t_submit: float = field(default_factory=time.time)
@@ -233,7 +234,7 @@ class Scheduler(threading.Thread):
         for i in fresh:
             a = self.active[i]
             n = len(a.req.prompt_ids) - self._reusable_prefix(i)      # tokens that actually have to be processed
-            if many is None or n < floor or len(a.req.prompt_ids) + 1 >= a.slot.n_ctx or n > limit:
+            if many is None or a.req.embed or n < floor or len(a.req.prompt_ids) + 1 >= a.slot.n_ctx or n > limit:
                 self._start(i)
                 continue
             if group_tokens + n > limit:
@@ -246,6 +247,18 @@ class Scheduler(threading.Thread):
         a = self.active[i]
         req, slot = a.req, a.slot
         n_ctx = slot.n_ctx
+        if req.embed:                                      # embedding request: one pass over the prompt, no generation
+            try:
+                vec = self.engine.embed(req.prompt_ids, slot=slot.index, pooling=req.embed)
+            except ValueError as e:
+                req.events.put(("error", f"invalid request: {e}"))
+            else:
+                self.stats["requests"] += 1
+                self.stats["prompt_tokens"] += len(req.prompt_ids)
+                req.events.put(("embedding", vec, len(req.prompt_ids)))
+            del self.active[i]
+            self.slot_tokens.pop(i, None)                  # the slot's cached prefix is gone (embed() refilled the slot from 0)
+            return
         if len(req.prompt_ids) + 1 >= n_ctx:
             req.events.put(("error", f"the request exceeds the available context size ({len(req.prompt_ids)} prompt tokens, context {n_ctx})"))
             del self.active[i]

@@ -35,6 +35,7 @@ class ServerState:
         self.ready = threading.Event()
         self.t_start = time.time()
         self.info = info or {}
+        self.embeddings = ""       # "" = not served (501, as llama-server without --embeddings); else the pooling: "mean" / "last"
 
 
 def _err(code: int, message: str, etype: str) -> tuple[int, bytes]:
@@ -149,7 +150,9 @@ class Handler(BaseHTTPRequestHandler):
             if p == "/detokenize":
                 return self._send(200, json.dumps({"content": st.tok.decode([int(t) for t in body.get("tokens", [])])}).encode())
             if p in ("/v1/embeddings", "/embeddings", "/embedding"):
-                return self._send(*_err(501, "embeddings are not served by this engine (decode path only)", "not_supported_error"))
+                if not st.embeddings:   # upstream's answer when the server was not started with --embeddings
+                    return self._send(*_err(501, "This server does not support embeddings. Start it with `--embeddings`", "not_supported_error"))
+                return self._embeddings(body)
         except (BrokenPipeError, ConnectionResetError):
             return
         except (ValueError, TypeError) as e:   # malformed field (wrong type, out-of-range token id, ...): this request only
@@ -212,6 +215,43 @@ class Handler(BaseHTTPRequestHandler):
         stop = [s for s in stop if isinstance(s, str) and s]
         return Request(prompt_ids=ids, max_tokens=max_tokens, sampling=sp, stop=stop, ignore_eos=bool(body.get("ignore_eos", False)),
                        cache_prompt=bool(body.get("cache_prompt", True)))
+
+    def _embeddings(self, body: dict):
+        """POST /v1/embeddings (docs/API_REFERENCE.md:540-590 of the reference): `input` is a string, an array of strings, or
+        token-id arrays; one pooled, L2-normalised vector per input, in order."""
+        st = self.state
+        inp = body.get("input", body.get("content"))
+        if isinstance(inp, str) or (isinstance(inp, list) and inp and all(isinstance(t, int) and not isinstance(t, bool) for t in inp)):
+            inp = [inp]
+        if not isinstance(inp, list) or not inp:
+            raise ValueError("'input' is required: a string, an array of strings, or arrays of token ids")
+        n_vocab = st.tok.n_vocab
+        reqs = []
+        for item in inp:
+            if isinstance(item, str):
+                ids = st.tok.encode(item, add_special=True)
+            elif isinstance(item, list) and item and all(isinstance(t, int) and not isinstance(t, bool) for t in item):
+                if any(not 0 <= t < n_vocab for t in item):
+                    raise ValueError(f"token ids must be in 0..{n_vocab - 1}")
+                ids = list(item)
+            else:
+                raise ValueError("every input must be a non-empty string or a non-empty array of token ids")
+            if not ids:
+                raise ValueError("an input tokenises to nothing")
+            if len(ids) + 1 >= st.n_ctx:
+                raise ValueError(f"input of {len(ids)} tokens exceeds the context size {st.n_ctx}")
+            reqs.append(st.sched.submit(Request(prompt_ids=ids, max_tokens=0, embed=st.embeddings)))
+        data, total = [], 0
+        for i, r in enumerate(reqs):
+            ev = r.events.get(timeout=600)
+            if ev[0] != "embedding":
+                code = 400 if str(ev[1]).startswith("invalid request") else 500
+                return self._send(*_err(code, str(ev[1]), "invalid_request_error" if code == 400 else "server_error"))
+            data.append({"object": "embedding", "embedding": [float(x) for x in ev[1]], "index": i})
+            total += ev[2]
+        out = {"object": "list", "data": data, "model": str(body.get("model") or st.model_name),
+               "usage": {"prompt_tokens": total, "total_tokens": total}}
+        self._send(200, json.dumps(out).encode())
 
     def _completion(self, body: dict, chat: bool):
         st = self.state

@@ -56,6 +56,18 @@ class OracleEngine:
     def warmup(self):
         pass
 
+    def embed(self, tokens, slot=0, pooling="mean"):
+        """the oracle's pooled, L2-normalised final hidden states (what Engine.embed computes on the GPU)"""
+        s = self.slots[slot]
+        s.reset()
+        hs = []
+        for i, t in enumerate(tokens):
+            hs.append(np.asarray(s.m.forward(int(t), i, return_hidden=True), dtype=np.float64))
+        s.n_past = len(tokens)
+        v = hs[-1] if pooling == "last" else np.mean(hs, axis=0)
+        n = np.linalg.norm(v)
+        return (v / n if n > 0 else v).astype(np.float32)
+
     def close(self):
         pass
 

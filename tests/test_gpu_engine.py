@@ -423,3 +423,24 @@ def test_prefix_reuse_equals_cold_prefill(oracle, model_dir):
     assert sl.tokens(6) == cold[0]
     assert np.array_equal(_bits(sl.last_logits()), _bits(cold[1]))
     eng.close()
+
+
+@pytest.mark.parametrize("pooling", ["mean", "last"])
+def test_embeddings_match_the_oracle_hidden_states(oracle, model_dir, pooling):
+    """Engine.embed (llama-server --embeddings): output_norm'd final hidden states of the prompt through the tensor-core
+    prefill, pooled and L2-normalised, against the oracle's token-by-token hidden states (tolerance-level path: cosine)."""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "small", "Q4_K_M")
+    rng = np.random.default_rng(11)
+    prompt = [1] + [int(t) for t in rng.integers(300, 500, size=20)]
+    m = oracle.OracleLlama(path, n_ctx=128, mode="canon")
+    hs = [np.asarray(m.forward(t, i, return_hidden=True), dtype=np.float64) for i, t in enumerate(prompt)]
+    want = hs[-1] if pooling == "last" else np.mean(hs, axis=0)
+    want /= np.linalg.norm(want)
+    eng = Engine(path, n_ctx=128)
+    eng.warmup()
+    got = eng.embed(prompt, pooling=pooling).astype(np.float64)
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-5
+    assert float(got @ want) > 0.999, float(got @ want)
+    assert eng.generate(prompt, 4) == m.greedy(prompt, 4)        # the slot is usable for generation afterwards
+    eng.close()

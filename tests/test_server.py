@@ -226,6 +226,37 @@ def test_batched_and_single_steps_interleave(oracle, backend):
     assert res["short"][1]["usage"]["completion_tokens"] == 6
 
 
+def test_embeddings_endpoint(oracle, backend):
+    """POST /v1/embeddings (docs/API_REFERENCE.md:540-590 of the reference): 501 with upstream's message unless the server was
+    started with --embeddings; then one pooled, L2-normalised vector per input, OpenAI list shape, usage counted."""
+    p, st = backend["port"], backend["state"]
+    code, body = call(p, "POST", "/v1/embeddings", {"model": "any", "input": "Hello world"})
+    assert code == 501 and "--embeddings" in body["error"]["message"]
+    st.embeddings = "mean"
+    try:
+        code, body = call(p, "POST", "/v1/embeddings", {"model": "any", "input": ["Hello world", "The sea"]})
+        assert code == 200 and body["object"] == "list" and [d["index"] for d in body["data"]] == [0, 1]
+        tok = backend["tok"]
+        m = oracle.OracleLlama(backend["path"], n_ctx=160, mode="canon")
+        for d, text in zip(body["data"], ["Hello world", "The sea"]):
+            ids = tok.encode(text, add_special=True)
+            hs = [np.asarray(m.forward(t, i, return_hidden=True), dtype=np.float64) for i, t in enumerate(ids)]
+            want = np.mean(hs, axis=0)
+            want /= np.linalg.norm(want)
+            got = np.asarray(d["embedding"])
+            assert d["object"] == "embedding" and got.shape == want.shape
+            assert abs(np.linalg.norm(got) - 1.0) < 1e-5 and np.abs(got - want).max() < 1e-6
+        n_tok = sum(len(tok.encode(t, add_special=True)) for t in ["Hello world", "The sea"])
+        assert body["usage"] == {"prompt_tokens": n_tok, "total_tokens": n_tok}
+        assert call(p, "POST", "/v1/embeddings", {"input": []})[0] == 400
+        assert call(p, "POST", "/v1/embeddings", {"input": [[1, 10 ** 9]]})[0] == 400
+        # a completion still works on the slot the embedding used (its prompt cache was dropped, not corrupted)
+        code, body = call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 6, "temperature": 0})
+        assert code == 200 and body["choices"][0]["message"]["content"] == expected_text(oracle, backend, MSG, 6)[0]
+    finally:
+        st.embeddings = ""
+
+
 def test_cli_version_and_argv_contract():
     exe = os.path.join(ROOT, "bin", "llama-server")
     r = subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=60)
