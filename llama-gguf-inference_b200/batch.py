@@ -38,7 +38,9 @@ class BatchDecoder:
         self.meta = torch.zeros((3, NB), dtype=torch.int32, device=dev)          # token ids | positions | slots
         self.meta_host = torch.zeros((3, NB), dtype=torch.int32).pin_memory()
         self.next_tok = torch.zeros(NB, dtype=torch.int32, device=dev)
-        self.next_host = torch.zeros(NB, dtype=torch.int32).pin_memory()
+        self.next_host = [torch.zeros(NB, dtype=torch.int32).pin_memory() for _ in range(2)]   # two launches may be outstanding
+        self.events = [torch.cuda.Event() for _ in range(2)]
+        self._seq, self._last, self._warm = 0, None, set()
         self.logits_host = None
         self.slot_stride = hp.n_layer * eng.n_ctx * kvd                         # elements between two slots' caches
         self._graphs = {}
@@ -95,6 +97,11 @@ class BatchDecoder:
         A slot may appear several times with CONSECUTIVE positions (a prompt chunk): all K/V of the batch are written
         before attention runs and entry j attends positions <= pos[j], so the result is the token-by-token one.
         head=False skips the lm-head (prompt chunks whose logits nobody reads); returns []."""
+        return self.collect(self.launch(entries, head))
+
+    def launch(self, entries, head: bool = True):
+        """step() without the wait: enqueues the pass and the read-back of its greedy tokens, returns a handle for collect().
+        At most two launches may be outstanding (the host buffers alternate), collected in launch order."""
         nb = len(entries)
         if not 0 < nb <= self.nb_max:
             raise ValueError(f"batch of {nb} entries (1..{self.nb_max})")
@@ -114,25 +121,62 @@ class BatchDecoder:
         mh[2, :nb] = torch.tensor(slots, dtype=torch.int32)
         with torch.cuda.stream(self.stream):
             self.meta.copy_(mh, non_blocking=True)
-            if not e.use_graph:
-                self._enqueue(nb, self.stream.cuda_stream, head)
-            else:
-                g = self._graphs.get((nb, head))
-                if g is None:
-                    self._enqueue(nb, self.stream.cuda_stream, head)   # first use: sets kernel attributes outside capture
-                    self.stream.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=self.stream):
-                        self._enqueue(nb, torch.cuda.current_stream().cuda_stream, head)
-                    self._graphs[(nb, head)] = g
-                g.replay()
-            if head:
-                self.next_host.copy_(self.next_tok, non_blocking=True)
-        self.stream.synchronize()
+        self._last = (nb, slots, [en[2] for en in entries]) if head and len(seen) == nb else None
         for sl, _, pos in entries:
             e.slots[sl].n_past = pos + 1
             e.slots[sl].chain_valid = False     # the slot's own device-side (token, position, x) no longer match
-        return self.next_host[:nb].tolist() if head else []
+        return self._run(nb, head, False)
+
+    def launch_chained(self):
+        """The next decode step of the SAME sequences as the last launch, entirely from device state: token ids = that
+        launch's arg-max results, positions + 1.  The host can therefore enqueue step k+1 before it has seen the tokens of
+        step k (and emit them while k+1 runs).  Returns None when a sequence would leave its context."""
+        if self._last is None:
+            raise cabi.GGBError("launch_chained: no decode launch to continue")
+        nb, slots, pos = self._last
+        pos = [p + 1 for p in pos]
+        if max(pos) >= self.eng.n_ctx:
+            return None
+        self._last = (nb, slots, pos)
+        for sl, p in zip(slots, pos):
+            self.eng.slots[sl].n_past = p + 1
+        return self._run(nb, True, True)
+
+    def _run(self, nb: int, head: bool, chained: bool):
+        e, torch = self.eng, self.torch
+
+        def enqueue(s):
+            if chained:     # device-side hand-over of (token, position) from the previous step
+                self.meta[0, :nb].copy_(self.next_tok[:nb])
+                self.meta[1, :nb].add_(1)
+            self._enqueue(nb, s, head)
+
+        buf = self._seq & 1
+        self._seq += 1
+        with torch.cuda.stream(self.stream):
+            if not e.use_graph:
+                enqueue(self.stream.cuda_stream)
+            else:
+                g = self._graphs.get((nb, head, chained))
+                if g is None:
+                    if (nb, head) not in self._warm:   # (a chained launch always follows a plain one of the same size)
+                        self._enqueue(nb, self.stream.cuda_stream, head)   # first use: sets kernel attributes outside capture
+                        self.stream.synchronize()
+                        self._warm.add((nb, head))
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        enqueue(torch.cuda.current_stream().cuda_stream)
+                    self._graphs[(nb, head, chained)] = g
+                g.replay()
+            if head:
+                self.next_host[buf].copy_(self.next_tok, non_blocking=True)
+            self.events[buf].record(self.stream)
+        return (buf, nb, head)
+
+    def collect(self, handle) -> list[int]:
+        buf, nb, head = handle
+        self.events[buf].synchronize()
+        return self.next_host[buf][:nb].tolist() if head else []
 
     def prefill(self, slot: int, tokens: list[int], start: int):
         """Write the K/V of `tokens` at positions start.. of one slot, 16 tokens per pass over the weights (bit-identical

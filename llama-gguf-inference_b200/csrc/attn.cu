@@ -21,9 +21,11 @@
 
 namespace cg = cooperative_groups;
 
-#ifdef GGB_TIMELINE   /* debug builds: %globaltimer stamps of the LAST launch [cta][entry, wait done, pass 1 done, pass 2 done, exit] */
-__device__ unsigned long long ggb_tl_attn[512 * 8];
-#define ATL(i) do { if (threadIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); ggb_tl_attn[(blockIdx.x & 511) * 8 + (i)] = t_; } } while (0)
+#ifdef GGB_TIMELINE   /* debug builds: stamps of the LAST launch [cta][entry, wait done, max exchanged, sums exchanged, exit, pass-1 loop done,
+                       * pass-2 loop done, partials pushed]: %globaltimer (256 ns ticks, common origin) and the SM's clock64 (durations) */
+__device__ unsigned long long ggb_tl_attn[2 * 512 * 8];
+#define ATL(i) do { if (threadIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); \
+    ggb_tl_attn[(blockIdx.x & 511) * 8 + (i)] = t_; ggb_tl_attn[512 * 8 + (blockIdx.x & 511) * 8 + (i)] = (unsigned long long)clock64(); } } while (0)
 extern "C" int ggb_debug_timeline_attn(unsigned long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, ggb_tl_attn, sizeof(ggb_tl_attn)) == cudaSuccess ? 0 : -2;
 }
@@ -139,6 +141,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
             }
         }
     }
+    ATL(5);
     mx = warp_max(mx);
     if (lane == 0) sm_max[warp] = mx;
     __syncthreads();
@@ -182,6 +185,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
             }
         }
     }
+    ATL(6);
     const int slot = warp * PPW + sub;
     if (li == 0) sm_sum[slot] = sum;
 #pragma unroll
@@ -202,6 +206,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
             cluster.map_shared_rank(cl_sum, 0)[crank] = t;
         }
     }
+    ATL(7);
     cluster.sync();
     ATL(3);
     if (crank == 0) {                           /* rank order, as before: the same f64 sums */

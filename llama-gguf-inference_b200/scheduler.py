@@ -142,6 +142,7 @@ class Scheduler(threading.Thread):
         self.log = log or (lambda *a: None)
         self.stats = {"requests": 0, "prompt_tokens": 0, "completion_tokens": 0, "decode_seconds": 0.0}
         self.fatal: str | None = None
+        self._inflight = None                       # (BatchDecoder handle, [(slot index, _Active)]) of a launched, uncollected step
 
     # ------------------------------------------------------------------ public
     def submit(self, req: Request) -> Request:
@@ -166,10 +167,14 @@ class Scheduler(threading.Thread):
         try:
             while True:
                 with self.cv:
-                    while not self.stop_flag and not self.pending and not self.active:
+                    while not self.stop_flag and not self.pending and not self.active and self._inflight is None:
                         self.cv.wait()
                     if self.stop_flag:
                         break
+                    admit = bool(self.pending) and len(self.active) < len(self.engine.slots)
+                if admit or not self.active:
+                    self._drain()                      # the batch composition is about to change: no step may be in flight
+                with self.cv:
                     fresh = []
                     while self.pending and len(self.active) < len(self.engine.slots):
                         req = self.pending.popleft()
@@ -179,11 +184,11 @@ class Scheduler(threading.Thread):
                         self.active[free] = _Active(req, self.engine.slots[free], self.tok)
                         fresh.append(free)
                 self._start_many(fresh)
-                live = list(self.active)
-                if len(live) >= 2 and getattr(self.engine, "batch_capable", False):
-                    self._step_batch(live)
+                if len(self.active) >= 2 and getattr(self.engine, "batch_capable", False):
+                    self._step_batch()
                 else:
-                    for i in live:
+                    self._drain()
+                    for i in list(self.active):
                         self._step(i)
         except Exception as e:  # a CUDA error is fatal: surface it to every waiter, then let the process die loudly
             self.fatal = f"engine failure: {e!r}"
@@ -317,26 +322,71 @@ class Scheduler(threading.Thread):
         a.fed.append(a.last_tok)
         self._emit(i, self._pick(a))
 
-    def _step_batch(self, live: list[int]):
-        """Two or more busy slots: their next tokens form one batch -- one pass over the weights (batch.py)."""
-        for i in live:
+    def _step_batch(self):
+        """Two or more busy slots: their next tokens form one batch -- one pass over the weights (batch.py).
+
+        Pipelined by one step when every sequence is greedy: the arg-max of step k stays on the device and feeds step k+1
+        (BatchDecoder.launch_chained), which is enqueued BEFORE the host waits for step k; detokenising and streaming the
+        tokens of step k then overlaps the GPU work of step k+1.  A sequence that turns out to have ended at step k (EOS,
+        stop string) was carried through step k+1 in vain -- that token is dropped, the K/V row it wrote lies beyond what the
+        slot's prompt cache claims -- and the next launch is host-fed again with the new composition."""
+        for i in list(self.active):
             if self.active[i].req.cancelled.is_set():
                 self._finish(i, "cancelled")
-        live = [i for i in live if i in self.active]
-        if len(live) < 2:
-            for i in live:
-                self._step(i)
-            return
         bd = self.engine.batch
-        acts = [self.active[i] for i in live]
-        toks = bd.step([(a.slot.index, a.last_tok, a.slot.n_past) for a in acts])
-        for a in acts:
-            a.fed.append(a.last_tok)
-        self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
-        self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
-        for b, (i, a) in enumerate(zip(live, acts)):
-            tok = toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng, a.history)
-            self._emit(i, tok)
+        inf = self._inflight
+        if inf is None:
+            live = list(self.active)
+            if len(live) < 2:
+                for i in live:
+                    self._step(i)
+                return
+            acts = [self.active[i] for i in live]
+            entries = [(a.slot.index, a.last_tok, a.slot.n_past) for a in acts]
+            for a in acts:
+                a.fed.append(a.last_tok)
+            self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
+            self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
+            pairs = list(zip(live, acts))
+            if hasattr(bd, "launch") and all(a.req.sampling.greedy for a in acts):
+                self._inflight = (bd.launch(entries), pairs)           # collected by the next round, after its own launch
+            else:
+                self._deliver(bd.step(entries), pairs)
+            return
+        handle, pairs = inf
+        nxt = None
+        if ([i for i, _ in pairs] == list(self.active) and all(self.active[i] is a for i, a in pairs)
+                and all(a.n_gen + 1 < a.req.max_tokens for _, a in pairs)):
+            with self.cv:
+                waiting = bool(self.pending) and len(self.active) < len(self.engine.slots)
+            if not waiting:
+                nxt = bd.launch_chained()                               # step k+1 from device state; None at the context end
+        self._inflight = None
+        t0 = time.time()
+        toks = bd.collect(handle)
+        self.stats["gpu_wait_seconds"] = self.stats.get("gpu_wait_seconds", 0.0) + time.time() - t0
+        self._deliver(toks, pairs)
+        if nxt is not None:
+            for i, a in pairs:
+                if self.active.get(i) is a:
+                    a.fed.append(a.last_tok)                            # the token step k+1 is processing
+            self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
+            self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(pairs)
+            self.stats["chained_steps"] = self.stats.get("chained_steps", 0) + 1
+            self._inflight = (nxt, pairs)
+
+    def _deliver(self, toks, pairs):
+        bd = self.engine.batch
+        for b, (i, a) in enumerate(pairs):
+            if self.active.get(i) is not a:
+                continue                                                # ended or cancelled while the step was in flight
+            self._emit(i, toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng, a.history))
+
+    def _drain(self):
+        """wait for the step in flight (if any) and deliver its tokens"""
+        inf, self._inflight = self._inflight, None
+        if inf is not None:
+            self._deliver(self.engine.batch.collect(inf[0]), inf[1])
 
     def _emit(self, i: int, tok: int):
         a = self.active[i]

@@ -91,5 +91,22 @@ class OracleBatch:
         self.steps += 1
         return out
 
+    # the asynchronous form the scheduler pipelines with (BatchDecoder.launch / launch_chained / collect)
+    def launch(self, entries):
+        out = self.step(entries)
+        self._last = (list(entries), out)
+        return out
+
+    def launch_chained(self):
+        entries, out = self._last
+        nxt = [(sl, tok, pos + 1) for (sl, _, pos), tok in zip(entries, out)]
+        if max(p for _, _, p in nxt) >= self.eng.slots[0].n_ctx:
+            return None
+        self.chained = getattr(self, "chained", 0) + 1
+        return self.launch(nxt)
+
+    def collect(self, handle):
+        return handle
+
     def logits_row(self, b):
         return self.rows[b]

@@ -316,6 +316,50 @@ def test_batched_decode_is_bit_identical_to_single_sequence_decode(oracle, model
     eng.close()
 
 
+def test_chained_batch_launches_equal_host_fed_steps(oracle, model_dir):
+    """BatchDecoder.launch / launch_chained / collect (the scheduler's one-step-ahead pipeline): step k+1 takes its token ids
+    and positions from device state and is enqueued before step k is collected; tokens must be those of host-fed steps."""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "small", "Q4_K_M")
+    n_seq, n_new = 5, 24
+    prompts = [[1] + [300 + 7 * s + j for j in range(2 + (s * 3) % 7)] for s in range(n_seq)]
+    eng = Engine(path, n_ctx=64, n_slots=n_seq)
+    eng.warmup()
+
+    def start():
+        for s, p in enumerate(prompts):
+            eng.slots[s].reset()
+            eng.slots[s].prefill(p)
+        return [eng.slots[s].read_last_token() for s in range(n_seq)]
+
+    last = start()
+    want = [[t] for t in last]
+    for _ in range(n_new - 1):
+        last = eng.batch.step([(s, last[s], eng.slots[s].n_past) for s in range(n_seq)])
+        for s in range(n_seq):
+            want[s].append(last[s])
+    last = start()
+    got = [[t] for t in last]
+    bd = eng.batch
+    h = bd.launch([(s, last[s], eng.slots[s].n_past) for s in range(n_seq)])
+    for _ in range(n_new - 2):
+        h2 = bd.launch_chained()              # enqueued while the previous step may still be running
+        assert h2 is not None
+        for s, t in enumerate(bd.collect(h)):
+            got[s].append(t)
+        h = h2
+    for s, t in enumerate(bd.collect(h)):
+        got[s].append(t)
+    assert got == want
+    assert [eng.slots[s].n_past for s in range(n_seq)] == [len(prompts[s]) + n_new - 1 for s in range(n_seq)]
+    assert got[0] == oracle.OracleLlama(path, n_ctx=64, mode="canon").greedy(prompts[0], n_new)
+    # the context end: a chained launch that would write position n_ctx is refused, not clamped
+    while bd.launch_chained() is not None:
+        pass
+    assert max(eng.slots[s].n_past for s in range(n_seq)) == 64
+    eng.close()
+
+
 def test_batched_decode_subset_of_slots_and_errors(oracle, model_dir):
     from ggufb200.model import Engine
     path = _model(model_dir, "tiny", "Q4_K_M")

@@ -203,8 +203,38 @@ def test_concurrent_requests_and_health_during_generation(backend):
     [t.join() for t in ts]
     assert not errs and all(o[0] == 200 for o in out)
     assert len({o[1]["choices"][0]["message"]["content"] for o in out}) == 1   # same prompt, greedy -> same text on every slot
-    # two busy slots advance together: the scheduler batched their decode steps
+    # two busy slots advance together: the scheduler batched their decode steps, and -- all greedy -- ran them one step
+    # ahead of the host (step k+1 launched from device state before step k's tokens were read back)
     assert backend["state"].sched.stats.get("batched_steps", 0) > 0
+    assert backend["state"].sched.stats.get("chained_steps", 0) > 0
+
+
+def test_pipelined_batch_survives_sequences_ending_in_flight(oracle, backend):
+    """greedy requests of different lengths, one cut by a stop string: a sequence that ends at step k has already been carried
+    into the speculatively launched step k+1 -- its extra token must vanish and the others must not notice"""
+    p = backend["port"]
+    want40, _ = expected_text(oracle, backend, MSG, 40)
+    want9, _ = expected_text(oracle, backend, MSG, 9)
+    stop = want40[len(want40) // 2:len(want40) // 2 + 3]
+    res = {}
+
+    def worker(name, body):
+        res[name] = call(p, "POST", "/v1/chat/completions", body)
+
+    ts = [threading.Thread(target=worker, args=("long", {"messages": MSG, "max_tokens": 40, "temperature": 0})),
+          threading.Thread(target=worker, args=("short", {"messages": MSG, "max_tokens": 9, "temperature": 0})),
+          threading.Thread(target=worker, args=("stop", {"messages": MSG, "max_tokens": 40, "temperature": 0, "stop": [stop]}))]
+    before = backend["state"].sched.stats.get("chained_steps", 0)
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(r[0] == 200 for r in res.values())
+    assert res["long"][1]["choices"][0]["message"]["content"] == want40
+    assert res["short"][1]["choices"][0]["message"]["content"] == want9
+    assert res["stop"][1]["choices"][0]["message"]["content"] == want40[:want40.find(stop)]
+    assert res["stop"][1]["choices"][0]["finish_reason"] == "stop"
+    assert backend["state"].sched.stats.get("chained_steps", 0) > before
+    # the slots' prompt caches are intact: the same request again gives the same text
+    assert call(p, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 40, "temperature": 0})[1]["choices"][0]["message"]["content"] == want40
 
 
 def test_batched_and_single_steps_interleave(oracle, backend):

@@ -41,13 +41,19 @@ for i in range(8):
 try:
     L.ggb_debug_timeline_attn.argtypes = [C.c_void_p]
     L.ggb_debug_timeline_attn.restype = C.c_int
-    ab = np.zeros(512 * 8, dtype=np.uint64)
+    ab = np.zeros(2 * 512 * 8, dtype=np.uint64)
     assert L.ggb_debug_timeline_attn(ab.ctypes.data) == 0
-    a = ab.reshape(512, 8)[:256, :5].astype(np.int64)
-    print("attention of the last layer (256 CTAs), us relative to the same origin: [entry, dependency wait done, max exchanged, sums exchanged, exit]")
-    print("   min   ", " ".join(f"{(a[:, i].min() - t0) / 1e3:9.2f}" for i in range(5)))
-    print("   median", " ".join(f"{(np.median(a[:, i]) - t0) / 1e3:9.2f}" for i in range(5)))
-    print("   max   ", " ".join(f"{(a[:, i].max() - t0) / 1e3:9.2f}" for i in range(5)))
+    a = ab[:512 * 8].reshape(512, 8)[:256, [0, 1, 5, 2, 6, 7, 3, 4]].astype(np.int64)
+    print("attention of the last layer (256 CTAs), us relative to the same origin: [entry, dependency wait done, pass-1 loop done, max exchanged, "
+          "pass-2 loop done, partials pushed, sums exchanged, exit]")
+    print("   min   ", " ".join(f"{(a[:, i].min() - t0) / 1e3:9.2f}" for i in range(8)))
+    print("   median", " ".join(f"{(np.median(a[:, i]) - t0) / 1e3:9.2f}" for i in range(8)))
+    print("   max   ", " ".join(f"{(a[:, i].max() - t0) / 1e3:9.2f}" for i in range(8)))
+    ck = ab[512 * 8:].reshape(512, 8)[:256, [0, 1, 5, 2, 6, 7, 3, 4]].astype(np.int64)
+    d = np.diff(ck, axis=1)
+    print("   the same intervals in SM clock cycles (clock64, per CTA): median / max")
+    print("   median", " ".join(f"{np.median(d[:, i]):9.0f}" for i in range(7)))
+    print("   max   ", " ".join(f"{d[:, i].max():9.0f}" for i in range(7)))
 except AttributeError:
     pass
 eng.close()
