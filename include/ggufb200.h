@@ -253,6 +253,11 @@ int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, const uint16_t
                           const int32_t* slot_dev, int64_t slot_stride, int nb, int n_head, int n_kv, int head_dim,
                           int n_ctx, float* out, int use_pdl, void* stream);
 int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_idx, void* stream);
+/* Tensor-parallel batch: x [nb][n] is this rank's vocabulary shard starting at global row row_offset.  ggb_argmax_rows_key
+ * packs (maximum, global index) of every row into one sortable signed 64-bit key (larger value, then smaller index);
+ * after a MAX all-reduce of the keys ggb_argmax_keys_unpack yields the global first-maximum index of every row. */
+int ggb_argmax_rows_key(const float* x, int64_t n, int nb, int32_t row_offset, int64_t* keys, void* stream);
+int ggb_argmax_keys_unpack(const int64_t* keys, int nb, int32_t* out_idx, void* stream);
 
 #ifdef __cplusplus
 }

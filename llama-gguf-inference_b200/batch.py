@@ -22,18 +22,24 @@ from . import cabi
 class BatchDecoder:
     def __init__(self, eng, max_batch: int | None = None):
         torch = eng.torch
-        if eng.tp_size != 1:
-            raise cabi.GGBError("batched decode is single-GPU (tensor-parallel engines time-slice their slots)")
         self.eng, self.torch, self.lib, self.hp = eng, torch, eng.lib, eng.hp
         hp, dev = eng.hp, eng.dev
         self.nb_max = NB = int(max_batch or max(len(eng.slots), 16))   # >= 16 so that prompts prefill 16 tokens per pass
         self.stream = eng.stream
         self.use_pdl = eng.use_pdl
-        qd, kvd = hp.n_head * hp.head_dim, hp.n_kv * hp.head_dim
+        # tensor parallel: this rank's heads, FFN rows and vocabulary shard (parallel.py); the row-split projections leave
+        # unrounded f64 partials that are all-reduced before the one rounding, the arg-max travels as one sortable key per
+        # token -- the batched step is then bit-identical with the single-GPU one, like the single-sequence step
+        tp = self.tp = eng.tp_size
+        self.nh, self.nkv, self.ffl, self.vl = hp.n_head // tp, hp.n_kv // tp, hp.ff // tp, hp.vocab // tp
+        qd, kvd = self.nh * hp.head_dim, self.nkv * hp.head_dim
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
         self.x, self.q, self.k, self.v, self.att = f32(NB, hp.d), f32(NB, qd), f32(NB, kvd), f32(NB, kvd), f32(NB, qd)
-        self.h, self.logits = f32(NB, hp.ff), f32(NB, hp.vocab)
-        kmax = max(hp.d, hp.ff, qd)
+        self.h, self.logits = f32(NB, self.ffl), f32(NB, self.vl)
+        if tp > 1:
+            self.y64 = torch.zeros((NB, hp.d), dtype=torch.float64, device=dev)
+            self.keys = torch.zeros(NB, dtype=torch.int64, device=dev)
+        kmax = max(hp.d, self.ffl, qd)
         self.act = torch.zeros(NB * self.lib.ggb_act_image_bytes(kmax), dtype=torch.uint8, device=dev)
         self.meta = torch.zeros((3, NB), dtype=torch.int32, device=dev)          # token ids | positions | slots
         self.meta_host = torch.zeros((3, NB), dtype=torch.int32).pin_memory()
@@ -42,15 +48,16 @@ class BatchDecoder:
         self.events = [torch.cuda.Event() for _ in range(2)]
         self._seq, self._last, self._warm = 0, None, set()
         self.logits_host = None
-        self.slot_stride = hp.n_layer * eng.n_ctx * kvd                         # elements between two slots' caches
+        self.slot_stride = hp.n_layer * eng.n_ctx * kvd                         # elements between two slots' caches (this rank's heads)
         self._graphs = {}
 
     # ------------------------------------------------------------------ one forward pass for nb tokens
     def _enqueue(self, nb: int, s: int, head: bool = True):
         lib, hp, e, pdl = self.lib, self.hp, self.eng, self.use_pdl
-        qd = hp.n_head * hp.head_dim
+        qd = self.nh * hp.head_dim
         ids, pos, slot = (self.meta[i].data_ptr() for i in range(3))
         act = self.act.data_ptr()
+        tp = self.tp > 1
 
         def prep(x, norm, k, w):
             cabi.check(lib.ggb_act_prep(x.data_ptr(), norm.data_ptr() if norm is not None else 0, hp.eps, k, nb,
@@ -59,6 +66,14 @@ class BatchDecoder:
         def gemv(segs, k, epi, residual=0):
             a = cabi.make_gemv_batch_args(segs, k, act, nb, epilogue=epi, residual=residual, use_pdl=pdl)
             cabi.check(lib.ggb_gemv_batch(C.byref(a), s), "gemv_batch")
+
+        def row_split(w, k):
+            """x += W h for a projection whose K is split across the ranks"""
+            if not tp:
+                return gemv([(w.ptr, w.type, w.rows, xp)], k, cabi.EPI_RESIDUAL, residual=xp)
+            gemv([(w.ptr, w.type, w.rows, self.y64.data_ptr())], k, cabi.EPI_STORE_F64)
+            e.dist.all_reduce(self.y64[:nb], op=e.dist.ReduceOp.SUM, group=e.pg)
+            cabi.check(lib.ggb_residual_add_f64(xp, self.y64.data_ptr(), nb * hp.d, 0, s), "residual_add_f64")
 
         cabi.check(lib.ggb_embed_rows(e.emb_type, e.emb_canon.data_ptr(), hp.d, ids, nb, self.x.data_ptr(), s), "embed_rows")
         xp = self.x.data_ptr()
@@ -69,21 +84,26 @@ class BatchDecoder:
                   (L["wv"].ptr, L["wv"].type, L["wv"].rows, self.v.data_ptr())], hp.d, cabi.EPI_STORE)
             kc, vc = e.k_all[0, i].data_ptr(), e.v_all[0, i].data_ptr()
             cabi.check(lib.ggb_rope_kv_batch(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), nb, pos, slot, self.slot_stride,
-                                             hp.n_head, hp.n_kv, hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), kc, vc, s), "rope_kv_batch")
-            cabi.check(lib.ggb_attn_decode_batch(self.q.data_ptr(), kc, vc, pos, slot, self.slot_stride, nb, hp.n_head, hp.n_kv,
+                                             self.nh, self.nkv, hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), kc, vc, s), "rope_kv_batch")
+            cabi.check(lib.ggb_attn_decode_batch(self.q.data_ptr(), kc, vc, pos, slot, self.slot_stride, nb, self.nh, self.nkv,
                                                  hp.head_dim, e.n_ctx, self.att.data_ptr(), 0, s), "attn_decode_batch")
             prep(self.att, None, qd, L["wo"])
-            gemv([(L["wo"].ptr, L["wo"].type, L["wo"].rows, xp)], qd, cabi.EPI_RESIDUAL, residual=xp)
+            row_split(L["wo"], qd)
             prep(self.x, L["ffn_norm"], hp.d, L["wg"])
             gemv([(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
                   (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)], hp.d, cabi.EPI_SWIGLU)
-            prep(self.h, None, hp.ff, L["wd"])
-            gemv([(L["wd"].ptr, L["wd"].type, L["wd"].rows, xp)], hp.ff, cabi.EPI_RESIDUAL, residual=xp)
+            prep(self.h, None, self.ffl, L["wd"])
+            row_split(L["wd"], self.ffl)
         if not head:      # prompt tokens whose logits nobody reads: the pass only fills the KV cache
             return
         prep(self.x, e.out_norm, hp.d, e.w_out)
         gemv([(e.w_out.ptr, e.w_out.type, e.w_out.rows, self.logits.data_ptr())], hp.d, cabi.EPI_STORE)
-        cabi.check(lib.ggb_argmax_rows(self.logits.data_ptr(), hp.vocab, nb, self.next_tok.data_ptr(), s), "argmax_rows")
+        if not tp:
+            cabi.check(lib.ggb_argmax_rows(self.logits.data_ptr(), self.vl, nb, self.next_tok.data_ptr(), s), "argmax_rows")
+            return
+        cabi.check(lib.ggb_argmax_rows_key(self.logits.data_ptr(), self.vl, nb, e.tp_rank * self.vl, self.keys.data_ptr(), s), "argmax_rows_key")
+        e.dist.all_reduce(self.keys[:nb], op=e.dist.ReduceOp.MAX, group=e.pg)
+        cabi.check(lib.ggb_argmax_keys_unpack(self.keys.data_ptr(), nb, self.next_tok.data_ptr(), s), "argmax_keys_unpack")
 
     def launches_per_step(self, nb: int) -> int:
         passes = lambda k: -(-nb // 8)   # noqa: E731  (an upper bound: very large K runs more, smaller passes)
@@ -185,9 +205,14 @@ class BatchDecoder:
             chunk = tokens[c0:c0 + self.nb_max]
             self.step([(slot, int(t), start + c0 + j) for j, t in enumerate(chunk)], head=False)
 
+    def logits_row_tensor(self, b: int):
+        """row b of this rank's logits (its vocabulary shard under tensor parallelism), on the device, stream drained"""
+        self.stream.synchronize()
+        return self.logits[b]
+
     def logits_row(self, b: int) -> np.ndarray:
         if self.logits_host is None:
-            self.logits_host = self.torch.zeros(self.hp.vocab, dtype=self.torch.float32).pin_memory()
+            self.logits_host = self.torch.zeros(self.vl, dtype=self.torch.float32).pin_memory()
         with self.torch.cuda.stream(self.stream):
             self.logits_host.copy_(self.logits[b], non_blocking=True)
         self.stream.synchronize()

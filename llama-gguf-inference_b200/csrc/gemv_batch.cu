@@ -369,6 +369,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ggb_dq_gemv_batch_kernel(const 
             const int b = i / cnt0, l = i - b * cnt0;
             P.seg[0].y[(int64_t)b * P.seg[0].rows + r0_0 + l] = silu_mul_ref((float)rowv[l * NBT + b], (float)rowv[(cnt0 + l) * NBT + b]);
         }
+    } else if (P.epi == GGB_EPI_STORE_F64) {   /* tensor-parallel partial: summed across ranks before the one rounding */
+        double* y64 = reinterpret_cast<double*>(P.seg[0].y);
+        for (int i = tid; i < cnt0 * nb; i += GB_THREADS) {
+            const int b = i / cnt0, l = i - b * cnt0;
+            y64[(int64_t)b * P.seg[0].rows + r0_0 + l] = rowv[l * NBT + b];
+        }
     }
 }
 
@@ -547,7 +553,10 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
         case GGB_EPI_SWIGLU:
             if (a->n_seg != 2 || a->seg[0].rows != a->seg[1].rows || !a->seg[0].y) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: SWIGLU needs gate/up segments of equal rows and y on segment 0");
             break;
-        default: GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: epilogue %d is not available in the batched kernel (STORE, RESIDUAL, SWIGLU)", a->epilogue);
+        case GGB_EPI_STORE_F64:
+            if (a->n_seg != 1 || !a->seg[0].y || ((uintptr_t)a->seg[0].y & 7)) GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: STORE_F64 needs one segment and an 8-byte aligned f64 output [nb][rows]");
+            break;
+        default: GGB_FAIL(GGB_ERR_ARG, "ggb_gemv_batch: epilogue %d is not available in the batched kernel (STORE, STORE_F64, RESIDUAL, SWIGLU)", a->epilogue);
     }
     if (total_rows == 0 || a->nb == 0) return GGB_OK;
     // from 5 tokens up the integer dots of pure Q4_K / Q6_K launches go to the tensor cores (same arithmetic, half the
@@ -584,7 +593,7 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
         GemvBK Q = P;
         Q.nb = nb;
         Q.act = (const uint8_t*)a->act + (int64_t)b0 * P.image;
-        for (int s = 0; s < a->n_seg; s++) if (Q.seg[s].y) Q.seg[s].y += (int64_t)b0 * Q.seg[s].rows;
+        for (int s = 0; s < a->n_seg; s++) if (Q.seg[s].y) Q.seg[s].y += (int64_t)b0 * Q.seg[s].rows * (a->epilogue == GGB_EPI_STORE_F64 ? 2 : 1);
         if (Q.residual) Q.residual += (int64_t)b0 * Q.seg[0].rows;
         size_t off = (size_t)GB_NW * Q.ring_bytes + (size_t)nbt * Q.image;
         off = (off + 15) & ~(size_t)15;

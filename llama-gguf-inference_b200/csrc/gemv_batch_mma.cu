@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
                 else if (P.epi == GGB_EPI_RESIDUAL) {
                     const int64_t o = (int64_t)b * P.seg[0].rows + row;
                     P.seg[0].y[o] = __fadd_rn(P.residual[o], (float)v);
-                } else rowv[(lr + rl) * NBT + b] = v;
+                } else if (P.epi == GGB_EPI_STORE_F64) reinterpret_cast<double*>(P.seg[0].y)[(int64_t)b * P.seg[0].rows + row] = v;
+                else rowv[(lr + rl) * NBT + b] = v;
             }
         }
         /* the other half of `red` is used by the next group; the sync of the group after that orders its reuse */
@@ -358,7 +359,7 @@ int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream) {
         GbmK Q = P;
         Q.nb = nb;
         Q.act = (const uint8_t*)a->act + (int64_t)b0 * P.image;
-        for (int s = 0; s < a->n_seg; s++) if (Q.seg[s].y) Q.seg[s].y += (int64_t)b0 * Q.seg[s].rows;
+        for (int s = 0; s < a->n_seg; s++) if (Q.seg[s].y) Q.seg[s].y += (int64_t)b0 * Q.seg[s].rows * (a->epilogue == GGB_EPI_STORE_F64 ? 2 : 1);
         if (Q.residual) Q.residual += (int64_t)b0 * Q.seg[0].rows;
         const int rc = (nbt == 16) ? gbm_launch_nt<2>(Q, grid, smem, a->use_pdl, st) : gbm_launch_nt<1>(Q, grid, smem, a->use_pdl, st);
         if (rc) return rc;

@@ -154,6 +154,59 @@ extern "C" int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_i
     return GGB_OK;
 }
 
+// Vocabulary-sharded arg-max of a batch (tensor parallel): every rank packs (value, global index) of each row of ITS logits
+// shard into one sortable signed 64-bit key (ops.cu: same key as the single-sequence path), the keys are MAX-all-reduced,
+// and the index is unpacked.  First index wins ties, exactly as on one GPU.
+__global__ void argmax_rows_key_kernel(const float* __restrict__ x, int64_t n, int32_t row_offset, long long* __restrict__ keys) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const float* xr = x + (int64_t)blockIdx.x * n;
+    float v = -FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float o = xr[i];
+        if (o > v || (o == v && (int)i < idx)) { v = o; idx = (int)i; }
+    }
+    auto comb = [&](float ov, int oi) { if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; } };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) comb(__shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : -FLT_MAX;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) comb(__shfl_xor_sync(0xffffffffu, v, o), __shfl_xor_sync(0xffffffffu, idx, o));
+        if (threadIdx.x == 0) {
+            if (idx == 0x7fffffff) { v = -FLT_MAX; idx = 0x7ffffffe - row_offset; }
+            const unsigned b = __float_as_uint(v);
+            const unsigned mono = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+            const unsigned long long k = ((unsigned long long)mono << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(idx + row_offset));
+            keys[blockIdx.x] = (long long)(k ^ 0x8000000000000000ull);
+        }
+    }
+}
+__global__ void argmax_keys_unpack_kernel(const long long* __restrict__ keys, int nb, int32_t* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const unsigned long long k = (unsigned long long)keys[b] ^ 0x8000000000000000ull;
+    out[b] = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+}
+extern "C" int ggb_argmax_rows_key(const float* x, int64_t n, int nb, int32_t row_offset, int64_t* keys, void* stream) {
+    if (n <= 0 || nb < 0 || (nb && (!x || !keys))) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_rows_key: bad argument");
+    if (nb == 0) return GGB_OK;
+    argmax_rows_key_kernel<<<nb, 1024, 0, (cudaStream_t)stream>>>(x, n, row_offset, (long long*)keys);
+    GGB_CHECK_LAUNCH("ggb_argmax_rows_key");
+    return GGB_OK;
+}
+extern "C" int ggb_argmax_keys_unpack(const int64_t* keys, int nb, int32_t* out_idx, void* stream) {
+    if (nb < 0 || (nb && (!keys || !out_idx))) GGB_FAIL(GGB_ERR_ARG, "ggb_argmax_keys_unpack: bad argument");
+    if (nb == 0) return GGB_OK;
+    argmax_keys_unpack_kernel<<<(nb + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const long long*)keys, nb, out_idx);
+    GGB_CHECK_LAUNCH("ggb_argmax_keys_unpack");
+    return GGB_OK;
+}
+
 // Causal attention for T query tokens at positions pos0..pos0+T-1 over the f16 cache, flash-attention style on the
 // tensor cores (mma.sync m16n8k16, f16 operands, f32 accumulate): CTA = one query head x 64 query tokens, 4 warps of
 // 16 query rows each; K/V tiles of 64 positions are staged in shared memory by cp.async; S = Q.K^T and O += P.V are

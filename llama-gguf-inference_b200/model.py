@@ -371,8 +371,9 @@ class Slot:
                 e.prefill_many([(self.index, tokens[c0:c0 + e.prefill_chunk], start + c0)], head=c0 + e.prefill_chunk >= len(tokens))
             return
         first = 0
-        if e.tp_size == 1 and len(tokens) >= 4:
-            # all but the last token only fill the KV cache: 16 per pass through the batched kernels (same arithmetic)
+        if len(tokens) >= 4:
+            # all but the last token only fill the KV cache: 16 per pass through the batched kernels (same arithmetic;
+            # under tensor parallelism every rank runs the same passes, csrc exchange = f64 all-reduce, batch.py)
             e.batch.prefill(self.index, tokens[:-1], start)
             first = len(tokens) - 1
         with self.torch.cuda.stream(self.stream):
@@ -501,7 +502,7 @@ class Engine:
         self.v_all = torch.zeros((n_slots, self.hp.n_layer, self.n_ctx, kvd), dtype=torch.float16, device=self.dev)
         self.slots = [Slot(self, i) for i in range(n_slots)]
         self._batch = None
-        self.batch_capable = self.tp_size == 1 and n_slots > 1
+        self.batch_capable = n_slots > 1
         if verbose:
             print(f"[engine] loaded {path}: {self.hp} in {self.load_seconds:.2f}s, weights {self.weight_bytes/1e9:.3f} GB", flush=True)
 

@@ -48,14 +48,53 @@ class TPSlot:
         return self._l.gather_logits(self._s)
 
 
+class TPBatch:
+    """BatchDecoder (batch.py) behind the same mirroring: every launch is announced, then executed on every rank (its
+    all-reduces are collective).  Only rank 0 collects results; the followers' state advances with the launches."""
+
+    def __init__(self, leader: "TPLeader", bd):
+        self._l, self._bd = leader, bd
+        self.nb_max = bd.nb_max
+
+    def launch(self, entries, head: bool = True):
+        entries = [(int(a), int(b), int(c)) for a, b, c in entries]
+        self._l.cmd("b_launch", entries, bool(head))
+        return self._bd.launch(entries, head)
+
+    def launch_chained(self):
+        self._l.cmd("b_chain")                       # whether the context end refuses it is decided identically on every rank
+        return self._bd.launch_chained()
+
+    def collect(self, handle):
+        return self._bd.collect(handle)
+
+    def step(self, entries, head: bool = True):
+        return self.collect(self.launch(entries, head))
+
+    def prefill(self, slot: int, tokens, start: int):
+        self._l.cmd("b_prefill", int(slot), [int(t) for t in tokens], int(start))
+        self._bd.prefill(slot, tokens, start)
+
+    def logits_row(self, b: int) -> np.ndarray:
+        self._l.cmd("b_logits", int(b))
+        bd = self._bd
+        return _gather_rows(self._l.dist, self._l.group, bd.logits_row_tensor(b) if hasattr(bd, "logits_row_tensor") else bd.logits_row(b))
+
+
 class TPLeader:
     """What rank 0 hands to the Scheduler instead of the Engine (same duck-typed surface)."""
-
-    batch_capable = False                           # batched decode is single-GPU; tensor-parallel slots are time-sliced
 
     def __init__(self, engine, dist, group=None):
         self.engine, self.dist, self.group = engine, dist, group
         self.slots = [TPSlot(self, s) for s in engine.slots]
+        self.batch_capable = bool(getattr(engine, "batch_capable", False))   # concurrent requests share one pass over the shards
+        self._batch = None
+
+    @property
+    def batch(self):
+        if self._batch is None:
+            self._batch = TPBatch(self, self.engine.batch)
+        return self._batch
 
     def cmd(self, *msg):
         self.dist.broadcast_object_list([msg], src=0, group=self.group)
@@ -67,14 +106,17 @@ class TPLeader:
         self.cmd("stop")
 
 
-def _gather_logits(dist, group, slot) -> np.ndarray:
-    part = slot.logits_tensor() if hasattr(slot, "logits_tensor") else None
-    if part is None:                                # duck-typed test engines: numpy logits
+def _gather_rows(dist, group, part) -> np.ndarray:
+    if isinstance(part, np.ndarray):                # duck-typed test engines: numpy logits
         import torch
-        part = torch.from_numpy(np.ascontiguousarray(slot.read_logits(), dtype=np.float32))
+        part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float32))
     parts = [part.new_empty(part.shape) for _ in range(dist.get_world_size(group))]
     dist.all_gather(parts, part.contiguous(), group=group)
     return np.concatenate([p.float().cpu().numpy() for p in parts])
+
+
+def _gather_logits(dist, group, slot) -> np.ndarray:
+    return _gather_rows(dist, group, slot.logits_tensor() if hasattr(slot, "logits_tensor") else slot.read_logits())
 
 
 def follower_loop(engine, dist, group=None):
@@ -85,6 +127,19 @@ def follower_loop(engine, dist, group=None):
         op, *args = box[0]
         if op == "stop":
             return
+        if op.startswith("b_"):                     # batched steps (TPBatch): launched, never collected here
+            bd = engine.batch
+            if op == "b_launch":
+                bd.launch(args[0], args[1])
+            elif op == "b_chain":
+                bd.launch_chained()
+            elif op == "b_prefill":
+                bd.prefill(args[0], args[1], args[2])
+            elif op == "b_logits":
+                _gather_rows(dist, group, bd.logits_row_tensor(args[0]) if hasattr(bd, "logits_row_tensor") else bd.logits_row(args[0]))
+            else:
+                raise RuntimeError(f"unknown operation from rank 0: {op!r}")
+            continue
         slot = engine.slots[args[0]]
         if op == "reset":
             slot.reset()

@@ -75,8 +75,16 @@ class OracleEngine:
 class OracleBatch:
     """the duck-typed BatchDecoder (llama-gguf-inference_b200/batch.py): one oracle forward per entry"""
 
+    nb_max = 16
+
     def __init__(self, eng):
         self.eng, self.rows, self.steps = eng, [], 0
+
+    def prefill(self, slot, tokens, start):
+        s = self.eng.slots[slot]
+        for j, t in enumerate(tokens):
+            s.logits = s.m.forward(int(t), start + j)
+        s.n_past, s.chain_valid = start + len(tokens), False
 
     def step(self, entries):
         assert len({e[0] for e in entries}) == len(entries)
@@ -92,7 +100,7 @@ class OracleBatch:
         return out
 
     # the asynchronous form the scheduler pipelines with (BatchDecoder.launch / launch_chained / collect)
-    def launch(self, entries):
+    def launch(self, entries, head=True):
         out = self.step(entries)
         self._last = (list(entries), out)
         return out

@@ -123,6 +123,29 @@ def test_tensor_parallel_llama_server_under_torchrun(oracle, model_dir, tmp_path
         assert body["choices"][0]["message"]["content"] == tok.decode(ref.greedy(ids, 24))
         st, body = call(port, "POST", "/v1/chat/completions", {"messages": MSG, "max_tokens": 8, "temperature": 1.0, "seed": 5})
         assert st == 200 and body["usage"]["completion_tokens"] == 8
+        # concurrent requests share ONE pass over the sharded weights per step (TPBatch: launches mirrored on rank 1, f64
+        # all-reduce per row-split projection), pipelined one step ahead when all are greedy; a sampled one rides along
+        import threading
+        res = {}
+
+        def worker(name, req):
+            res[name] = call(port, "POST", "/v1/chat/completions", req)
+
+        ts = [threading.Thread(target=worker, args=("a", {"messages": MSG, "max_tokens": 24})),
+              threading.Thread(target=worker, args=("b", {"messages": MSG, "max_tokens": 16})),
+              threading.Thread(target=worker, args=("c", {"messages": MSG, "max_tokens": 8, "temperature": 1.0, "seed": 5}))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert all(r[0] == 200 for r in res.values()), res
+        assert res["a"][1]["choices"][0]["message"]["content"] == tok.decode(ref.greedy(ids, 24))
+        assert res["b"][1]["choices"][0]["message"]["content"] == tok.decode(ref.greedy(ids, 16))
+        assert res["c"][1]["usage"]["completion_tokens"] == 8
+        c = http.client.HTTPConnection("127.0.0.1", port, timeout=30)
+        c.request("GET", "/metrics", headers={"Authorization": f"Bearer {KEY}"})
+        metrics = c.getresponse().read().decode()
+        c.close()
+        batched = [float(ln.split()[1]) for ln in metrics.splitlines() if ln.startswith("ggufb200:batched_steps_total")]
+        assert batched and batched[0] > 0, metrics
     finally:
         if proc.poll() is None:
             os.killpg(proc.pid, signal.SIGTERM)     # the process group WE started (torchrun + both ranks)

@@ -186,6 +186,67 @@ def test_tensor_parallel_engine_bit_exact_vs_oracle(oracle, model_dir, tmp_path,
     assert np.array_equal(got.view(np.uint32), np.stack(ref_logits).view(np.uint32))
 
 
+TP_PROMPTS = [[1, 300, 301, 302, 303], [1, 310, 311], [1, 320, 321, 322, 323, 324, 325, 326, 327]]
+
+
+def _tp_batch_worker(rank, world, port, path, n_new, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from ggufb200.model import Engine
+    eng = Engine(path, n_ctx=128, device=rank, tp_rank=rank, tp_size=world, n_slots=len(TP_PROMPTS))
+    assert eng.batch_capable
+    eng.warmup()
+    for s, p in enumerate(TP_PROMPTS):
+        eng.slots[s].reset()
+        eng.slots[s].prefill(p)               # >= 4 tokens: 16-per-pass batched prompt path, f64 all-reduce per row-split projection
+    last = [eng.slots[s].read_last_token() for s in range(len(TP_PROMPTS))]
+    got = [[t] for t in last]
+    bd = eng.batch
+    h = bd.launch([(s, last[s], eng.slots[s].n_past) for s in range(len(TP_PROMPTS))])
+    for _ in range(n_new - 2):
+        h2 = bd.launch_chained()
+        for s, t in enumerate(bd.collect(h)):
+            got[s].append(t)
+        h = h2
+    for s, t in enumerate(bd.collect(h)):
+        got[s].append(t)
+    rows = torch.stack([bd.logits_row_tensor(b) for b in range(len(TP_PROMPTS))]).cpu().numpy()
+    np.savez(os.path.join(out_dir, f"tpb{rank}.npz"), toks=np.array(got), logits=rows)
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_tensor_parallel_batched_decode_bit_exact_vs_oracle(oracle, model_dir, tmp_path):
+    """several sequences advance together on a tensor-parallel engine (BatchDecoder under tp: f64 partials of the row-split
+    projections all-reduced before the one rounding, arg-max as one sortable key per token), one step ahead of the host:
+    every sequence's tokens and final logits are the single-process canon oracle's, bit for bit"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from ggufb200 import synth
+    from dataclasses import replace
+    world = 2
+    cfg = replace(synth.PRESETS["medium"], n_layer=4, ff=3072)
+    path = os.path.join(model_dir, "tp-medium.gguf")
+    if not os.path.exists(path):
+        synth.write_gguf(path, cfg, "Q4_K_M", seed=0xB200)
+    n_new = 12
+    mp.spawn(_tp_batch_worker, args=(world, _free_port(), path, n_new, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"tpb{r}.npz") for r in range(world)]
+    assert np.array_equal(parts[0]["toks"], parts[1]["toks"])
+    logits = np.concatenate([p["logits"] for p in parts], axis=1)
+    for s, prompt in enumerate(TP_PROMPTS):
+        ref = oracle.OracleLlama(path, n_ctx=128, mode="canon")
+        ref_toks, ref_logits = ref.greedy(prompt, n_new, return_logits=True)
+        assert list(parts[0]["toks"][s]) == ref_toks, f"sequence {s}"
+        assert np.array_equal(logits[s].view(np.uint32), np.asarray(ref_logits[-1]).view(np.uint32)), f"sequence {s}"
+
+
 def _tp_serve_worker(rank, world, port, path, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -202,6 +263,17 @@ def _tp_serve_worker(rank, world, port, path, out_dir):
         full = s1.read_logits()
         assert full.shape[0] == world * eng.slots[1].read_logits().shape[0]      # one shard per rank, concatenated
         assert np.array_equal(full[: full.shape[0] // world], eng.slots[1].read_logits())
+        # batched steps (TPBatch): launches are mirrored, only the leader collects
+        assert lead.batch_capable
+        bd = lead.batch
+        last = [s0.read_last_token(), s1.read_last_token()]
+        h = bd.launch([(0, last[0], s0.n_past), (1, last[1], s1.n_past)])
+        h2 = bd.launch_chained()
+        t1, t2 = bd.collect(h), bd.collect(h2)
+        assert len(t1) == len(t2) == 2
+        row = bd.logits_row(1)
+        assert row.shape[0] == full.shape[0]
+        bd.prefill(0, [301, 302, 303], s0.n_past)
         lead.shutdown()
     else:
         follower_loop(eng, dist)
@@ -218,5 +290,5 @@ def test_tp_serving_followers_mirror_the_leader(model_dir, tmp_path):
         synth.write_gguf(path, "tiny", "Q4_K_M", seed=0xB200)
     mp.spawn(_tp_serve_worker, args=(2, _free_port(), path, str(tmp_path)), nprocs=2, join=True)
     a, b = np.load(tmp_path / "serve0.npz"), np.load(tmp_path / "serve1.npz")
-    assert list(a["past"]) == list(b["past"]) == [3, 7]
+    assert list(a["past"]) == list(b["past"]) == [8, 9]
     assert list(a["last"]) == list(b["last"])

@@ -48,7 +48,7 @@ def main():
             last = eng.batch.step([(s, last[s], eng.slots[s].n_past) for s in range(B)])
         torch.cuda.synchronize()
         # device time of the graph alone
-        g = eng.batch._graphs[(B, True)]
+        g = eng.batch._graphs[(B, True, False)]
         with torch.cuda.stream(eng.stream):
             ev0.record(eng.stream)
             for _ in range(10):
