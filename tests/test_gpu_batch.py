@@ -173,18 +173,21 @@ def test_gemv_batch_bad_args():
     assert L.ggb_act_image_bytes(100) == -1
 
 
-def test_rope_kv_attn_argmax_batch(oracle):
-    """per-token (slot, position) addressing: every entry equals the one-token kernels' / the oracle's result"""
+@pytest.mark.parametrize("n_head,n_kv,hd,n_ctx", [(8, 2, 64, 96), (8, 2, 128, 96), (16, 2, 128, 2048), (16, 2, 128, 2304), (4, 4, 128, 96)])
+def test_rope_kv_attn_argmax_batch(oracle, n_head, n_kv, hd, n_ctx):
+    """per-token (slot, position) addressing: every entry equals the one-token kernels' / the oracle's result.  head_dim 128
+    with 4 or 8 query heads per KV head and a context of up to 2048 positions takes the grouped-query kernel (one cluster of
+    four CTAs per four query heads); the other shapes the per-head kernel."""
     import torch
     import gpu_util as U
     from ggufb200 import cabi
     from ggufb200.model import rope_table
     L = cabi.lib()
-    n_head, n_kv, hd, n_ctx, n_slots = 8, 2, 64, 96, 4
+    n_slots = 4
     qd, kvd = n_head * hd, n_kv * hd
     rng = np.random.default_rng(5)
     slots = np.array([2, 0, 3, 1, 0], dtype=np.int32)       # entry 4 is idle (pos -1)
-    pos = np.array([17, 0, 95, 40, -1], dtype=np.int32)
+    pos = np.array([17, 0, n_ctx - 1, n_ctx // 2 + 3, -1], dtype=np.int32)
     nb = len(slots)
     q = rng.standard_normal((nb, qd)).astype(np.float32)
     k = rng.standard_normal((nb, kvd)).astype(np.float32)

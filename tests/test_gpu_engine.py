@@ -31,7 +31,10 @@ def _model(model_dir, preset, ftype, seed=0xB200):
     from ggufb200 import synth
     path = os.path.join(model_dir, f"{preset}-{ftype}-{seed}.gguf")
     if not os.path.exists(path):
-        synth.write_gguf(path, preset, ftype, seed)
+        cfg = preset
+        if preset == "gqa128":      # Llama-3's head geometry at test size: head_dim 128, four query heads per KV head
+            cfg = synth.LlamaConfig("gqa128", 2, 1024, 8, 2, 128, 1536, 2048)
+        synth.write_gguf(path, cfg, ftype, seed)
     return path
 
 
@@ -271,7 +274,7 @@ def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_di
 
 # ----------------------------------------------------------------------------- batched decode (BASELINE.json config 5)
 @pytest.mark.parametrize("preset,ftype,n_seq", [("tiny", "Q4_K_M", 3), ("small", "Q4_K_M", 5), ("small", "Q5_K_M", 7), ("small", "Q8_0", 2), ("medium", "Q4_K_M", 11),
-                                                ("medium", "Q6_K", 16)])
+                                                ("medium", "Q6_K", 16), ("gqa128", "Q4_K_M", 6)])
 def test_batched_decode_is_bit_identical_to_single_sequence_decode(oracle, model_dir, preset, ftype, n_seq):
     """n_seq sequences with different prompts (so different positions) advance together through gemv_batch.cu;
     each must produce exactly the tokens and logits it produces alone -- and sequence 0 those of the canon oracle."""
