@@ -60,7 +60,9 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int head = blockIdx.x / CL;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so that the loops below (whose bounds depend on
+    // it) count as convergent and their shuffles are plain SHFL instead of WARPSYNC / ENDCOLLECTIVE sequences
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int sub = lane / LPG, li = lane % LPG;
     const int kvh = head / (n_head / n_kv);
     const int64_t kv_stride = (int64_t)n_kv * HD;
@@ -80,7 +82,10 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 
     // K and V rows of positions < pos were written by earlier tokens: request the first batch of them BEFORE waiting for
     // the QKV launch that is producing q and row `pos` -- their L2 / HBM latency then hides behind that launch
-    constexpr int AU = 4;
+#ifndef GGB_ATTN_AU
+#define GGB_ATTN_AU 4
+#endif
+    constexpr int AU = GGB_ATTN_AU;
     uint4 kpre[AU], vpre[AU];
 #pragma unroll
     for (int u = 0; u < AU; u++) {
@@ -250,7 +255,7 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int hg = blockIdx.x / CL, head0 = hg * GQ;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   /* warp-uniform for the compiler */
     const int sub = lane / LPG, li = lane % LPG;
     const int kvh = head0 / (n_head / n_kv);
     const int64_t kv_stride = (int64_t)n_kv * HD;
