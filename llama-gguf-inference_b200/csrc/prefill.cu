@@ -376,11 +376,19 @@ static int launch_attn_prefill(const float* q, const uint16_t* kc, const uint16_
     return GGB_OK;
 }
 
+// prefill_tc.cu: the tcgen05 / TMEM / TMA kernel (default); returns 1 when it does not apply
+int ggb_attn_prefill_tc(const float* q, const uint16_t* kcache, const uint16_t* vcache, int tokens, int pos0, int n_head, int n_kv,
+                        int head_dim, float* out, void* stream);
+
 extern "C" int ggb_attn_prefill(const float* q, const uint16_t* kcache, const uint16_t* vcache, int tokens, int pos0, int n_head, int n_kv,
                                 int head_dim, float* out, void* stream) {
     if (tokens < 0 || pos0 < 0 || n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_prefill: bad shape");
     if (tokens == 0) return GGB_OK;
     if (!q || !kcache || !vcache || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_prefill: null pointer");
+    {
+        const int rc = ggb_attn_prefill_tc(q, kcache, vcache, tokens, pos0, n_head, n_kv, head_dim, out, stream);
+        if (rc != 1) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return launch_attn_prefill<128>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out, st);
     if (head_dim == 64) return launch_attn_prefill<64>(q, kcache, vcache, tokens, pos0, n_head, n_kv, out, st);

@@ -91,13 +91,16 @@ def test_gemm_rejects_bad_arguments():
     assert L.ggb_gemm(12, t.data_ptr(), 0, 256, t.data_ptr(), 4, t.data_ptr(), 4, 0) == 0
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma.sync"])
 @pytest.mark.parametrize("hd,n_head,n_kv", [(128, 8, 2), (64, 4, 4), (128, 4, 1)])
-@pytest.mark.parametrize("T,pos0", [(1, 0), (150, 37), (64, 0), (200, 300)])
-def test_attn_prefill_tensor_core_matches_oracle(oracle, hd, n_head, n_kv, T, pos0):
-    """flash-attention on mma.sync (csrc/prefill.cu) against the oracle's one-token attention, token by token"""
+@pytest.mark.parametrize("T,pos0", [(1, 0), (150, 37), (64, 0), (200, 300), (300, 517), (128, 128)])
+def test_attn_prefill_tensor_core_matches_oracle(oracle, monkeypatch, kernel, hd, n_head, n_kv, T, pos0):
+    """causal prefill attention against the oracle's one-token attention, token by token: the tcgen05 / TMEM / TMA kernel
+    (csrc/prefill_tc.cu, the default) and the mma.sync flash-attention it falls back to (csrc/prefill.cu)"""
     import torch
     import gpu_util as U
     from ggufb200 import cabi
+    monkeypatch.setenv("GGB_ATTN_PREFILL_TC", "1" if kernel == "tcgen05" else "0")
     L = cabi.lib()
     n_ctx = pos0 + T
     rng = np.random.default_rng(hd + T + pos0)
@@ -110,6 +113,6 @@ def test_attn_prefill_tensor_core_matches_oracle(oracle, hd, n_head, n_kv, T, po
     U.sync()
     got = out.cpu().numpy()
     assert np.isfinite(got).all()
-    for t in sorted({min(x, T - 1) for x in (0, 1, T // 2, max(T - 2, 0), T - 1, 63, 64)}):
+    for t in sorted({min(x, T - 1) for x in (0, 1, T // 2, max(T - 2, 0), T - 1, 63, 64, 127, 128, 255, 256)}):
         ref = oracle.attn_decode(q[t], kc.view(np.uint16), vc.view(np.uint16), n_head, n_kv, hd, pos0 + t + 1)
         assert np.abs(got[t] - ref).max() <= 3e-3 * max(np.abs(ref).max(), 1e-3), f"token {t}"
