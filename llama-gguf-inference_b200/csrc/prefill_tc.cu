@@ -3,8 +3,9 @@
 // prefill.cu (ggb_attn_prefill: T query tokens at positions pos0.. over the f16 cache of one slot and layer), which stays as
 // the fallback (GGB_ATTN_PREFILL_TC=0).
 //
-// One CTA = one query head x 128 query tokens: 4 softmax warps -- thread r owns query row r (= TMEM lane r), so the softmax
-// needs no cross-thread reduction at all -- plus one warp whose elected lane issues every TMA copy and every MMA, so that
+// One CTA = one query head x 128 query tokens: 8 softmax warps -- two threads per query row (= TMEM lane), each owning half of
+// the row's 128 positions and half of the output dims; the only cross-thread step of the softmax is one exchange of the
+// halves' maxima per tile -- plus one warp whose elected lane issues every TMA copy and every MMA, so that
 // S of the NEXT tile is computed (into the second of two S buffers in TMEM) while the softmax of the current one runs.
 // Per tile of 128 cache positions:
 //   K tile   two cp.async.bulk.tensor.2d (TMA, SWIZZLE_128B) from a tensor map over the cache -> K-major UMMA layout;
@@ -24,7 +25,7 @@
 
 #define PT_BM 128          /* query tokens per CTA (UMMA M) */
 #define PT_BN 128          /* cache positions per tile */
-#define PT_SOFTMAX_WARPS 4  /* one thread per query row */
+#define PT_SOFTMAX_WARPS 8  /* two threads per query row: warp w owns TMEM lanes 32 (w & 3) .., column half w >> 2 */
 #define PT_THREADS ((PT_SOFTMAX_WARPS + 1) * 32)   /* + the warp that issues the TMA copies and the MMAs */
 
 __device__ __forceinline__ uint32_t pt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) ggb_attn_prefill_tc_kernel(cons
     extern __shared__ __align__(1024) uint8_t pt_sm_raw[];
     __shared__ __align__(8) uint64_t bar_k, bar_v, bar_s[2], bar_p, bar_o;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float s_half[2][2][PT_BM];          /* [tile parity][column half][row]: the two threads of a row exchange maxima / sums */
     uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)pt_sm_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = sm;                                 /* NA atoms: [128 tokens][64 dims] f16, K-major */
     uint8_t* sK = sQ + NA * ATOM;                     /* NA atoms: [128 positions][64 dims], K-major (N = positions) */
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) ggb_attn_prefill_tc_kernel(cons
     if (tid == 0) {
         pt_mbar_init(pt_smem_u32(&bar_k), 1); pt_mbar_init(pt_smem_u32(&bar_v), 1);
         pt_mbar_init(pt_smem_u32(&bar_s[0]), 1); pt_mbar_init(pt_smem_u32(&bar_s[1]), 1);
-        pt_mbar_init(pt_smem_u32(&bar_p), PT_BM); pt_mbar_init(pt_smem_u32(&bar_o), 1);
+        pt_mbar_init(pt_smem_u32(&bar_p), PT_SOFTMAX_WARPS * 32); pt_mbar_init(pt_smem_u32(&bar_o), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == PT_SOFTMAX_WARPS) {                   /* the issuing warp owns the TMEM allocation: S0 | S1 | O_j */
@@ -192,27 +194,30 @@ __global__ void __launch_bounds__(PT_THREADS, 1) ggb_attn_prefill_tc_kernel(cons
             }
         }
     } else {
-        // ===== softmax warps: thread r owns query row r (TMEM lane r) =====
+        // ===== softmax warps: threads (row, half) own 64 of the 128 positions of a row of S and HD / 2 of the dims of O =====
+        constexpr int HC = PT_BN / 2, HDH = HD / 2;
+        const int row = tid & (PT_BM - 1), half = tid >> 7;
         const float sl2 = __fdiv_rn(1.0f, __fsqrt_rn((float)HD)) * 1.4426950408889634f;   /* scale * log2(e): exponentials as ex2 */
-        const int lim = pos0 + q0 + tid;              /* the last position query row `tid` may attend */
-        float acc[HD];
+        const int lim = pos0 + q0 + row;              /* the last position query row `row` may attend */
+        float acc[HDH];
 #pragma unroll
-        for (int d = 0; d < HD; d++) acc[d] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;          /* running maximum in the scaled log2 domain, running sum */
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-        uint8_t* prow = sP + (uint32_t)tid * 128u;
-        const uint32_t x7 = (uint32_t)(tid & 7) << 4;
+        for (int d = 0; d < HDH; d++) acc[d] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;          /* running maximum (scaled log2 domain, whole row), running sum (my half) */
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        uint8_t* prow = sP + half * ATOM + (uint32_t)row * 128u;   /* my 64 positions = one 128-byte row of atom `half` */
+        const uint32_t x7 = (uint32_t)(row & 7) << 4;
+        auto pair_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PT_SOFTMAX_WARPS * 32) : "memory"); };
 
         for (int j = 0; j < n_tiles; j++) {
-            const int p0 = j * PT_BN;
-            const uint32_t tmem_s = tmem_base + (uint32_t)((j & 1) * 128) + lane_base;
-            const bool diag = p0 + PT_BN - 1 > pos0 + q0;   /* the tile reaches past the first row's limit: mask (CTA-uniform) */
+            const int p0 = j * PT_BN + half * HC;     /* first position of my columns */
+            const uint32_t tmem_s = tmem_base + (uint32_t)((j & 1) * 128 + half * HC) + lane_base;
+            const bool diag = j * PT_BN + PT_BN - 1 > pos0 + q0;   /* the tile reaches past the first row's limit: mask (CTA-uniform) */
             pt_mbar_wait(pt_smem_u32(&bar_s[j & 1]), (uint32_t)((j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // pass 1: row maximum of the raw scores (scale > 0 commutes with max)
+            // pass 1: maximum of the raw scores of my half (scale > 0 commutes with max), exchanged with the other half
             float mraw = -INFINITY;
 #pragma unroll 1
-            for (int cb = 0; cb < PT_BN / 32; cb++) {
+            for (int cb = 0; cb < HC / 32; cb++) {
                 uint32_t v[32];
                 pt_ld32(tmem_s + (uint32_t)(cb * 32), v);
                 if (!diag) {
@@ -223,12 +228,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) ggb_attn_prefill_tc_kernel(cons
                     for (int i = 0; i < 32; i++) mraw = fmaxf(mraw, (p0 + cb * 32 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
                 }
             }
+            s_half[j & 1][half][row] = mraw;
+            pair_sync();
+            mraw = fmaxf(mraw, s_half[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m_run, mraw * sl2);   /* position 0 is visible to every query: finite from the first tile on */
             const float alpha = pt_ex2(m_run - m_new);
-            // pass 2: P = 2^(s * sl2 - m) as f16 into my 256-byte row of the K-major tile
+            // pass 2: P = 2^(s * sl2 - m) as f16 into my 128-byte row of the K-major tile
             float l_add = 0.f;
 #pragma unroll 1
-            for (int cb = 0; cb < PT_BN / 32; cb++) {
+            for (int cb = 0; cb < HC / 32; cb++) {
                 uint32_t v[32];
                 pt_ld32(tmem_s + (uint32_t)(cb * 32), v);
                 uint32_t pk[16];
@@ -243,34 +251,37 @@ __global__ void __launch_bounds__(PT_THREADS, 1) ggb_attn_prefill_tc_kernel(cons
                     l_add += e0 + e1;
                     pk[i] = pt_pack_h2(e0, e1);
                 }
-                uint8_t* pa = prow + (cb >> 1) * ATOM;   /* 32 positions = chunks 4*(cb&1) .. +3 of atom cb >> 1 */
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    *reinterpret_cast<uint4*>(pa + ((((uint32_t)(4 * (cb & 1) + c)) << 4) ^ x7)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                for (int c = 0; c < 4; c++)       /* 32 positions = chunks 4 cb .. 4 cb + 3 of my row */
+                    *reinterpret_cast<uint4*>(prow + ((((uint32_t)(4 * cb + c)) << 4) ^ x7)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             }
             l_run = fmaf(l_run, alpha, l_add);
             m_run = m_new;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     /* P: generic-proxy writes -> visible to the tensor core */
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             pt_mbar_arrive(pt_smem_u32(&bar_p));
-            // acc = acc * alpha + O_j
+            // acc = acc * alpha + O_j (my half of the dims)
             pt_mbar_wait(pt_smem_u32(&bar_o), (uint32_t)(j & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int cb = 0; cb < HD / 32; cb++) {
+            for (int cb = 0; cb < HDH / 32; cb++) {
                 uint32_t v[32];
-                pt_ld32(tmem_o + lane_base + (uint32_t)(cb * 32), v);
+                pt_ld32(tmem_o + lane_base + (uint32_t)(half * HDH + cb * 32), v);
 #pragma unroll
                 for (int i = 0; i < 32; i++) acc[cb * 32 + i] = fmaf(acc[cb * 32 + i], alpha, __uint_as_float(v[i]));
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
-        const int tq = q0 + tid;
+        // the row's sum = both halves' sums (same running maximum on both sides)
+        s_half[n_tiles & 1][half][row] = l_run;
+        pair_sync();
+        const float l_row = l_run + s_half[n_tiles & 1][half ^ 1][row];
+        const int tq = q0 + row;
         if (tq < T) {
-            const float inv = __fdiv_rn(1.0f, l_run);
-            float* dst = out + (int64_t)tq * qd + (int64_t)head * HD;
+            const float inv = __fdiv_rn(1.0f, l_row);
+            float* dst = out + (int64_t)tq * qd + (int64_t)head * HD + half * HDH;
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+            for (int d = 0; d < HDH; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
         }
     }
     __syncthreads();
