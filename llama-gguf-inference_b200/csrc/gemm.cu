@@ -2,20 +2,20 @@
 //   Y[tokens][rows] = X[tokens][K] . W[rows][K]^T      W quantised (tile-SoA Q4_K / Q6_K / Q8_0), X f16
 // Stands in for ggml-cuda's mul_mat_q / dequantise+cuBLAS path of the reference's backend [UPSTREAM-MEM].
 //
-// One CTA computes a 128 (weight rows) x 256 (tokens) output tile:
-//   * 8 producer warps unpack the packed weights of the current 128-wide K block straight into shared memory as
-//     f16 in the K-major SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the
-//     "B operand must be produced by a dequant stage", SURVEY.md section 7 hard part 5); the matching f16
-//     activation block arrives next to it by TMA -- two cp.async.bulk.tensor.2d (SASS UTMALDG) per K block from a
-//     SWIZZLE_128B tensor map over X, issued by one thread one K block ahead, completing on the stage's mbarrier
-//     (round 1 used 4096 cp.async per block: a quarter of the producers' instructions); weight tiles are
-//     prefetched into L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
-//   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) eight
-//     times per K block from shared-memory descriptors; the f32 accumulator (128 lanes x 256 columns) lives in
-//     TMEM; tcgen05.commit releases the shared-memory stage back to the producers and, after the last block,
-//     signals the epilogue;
-//   * epilogue: the 8 producer warps read the accumulator with tcgen05.ld (32x32b.x32) and store Y.
-// Two shared-memory stages (2 x 96 KB); TMEM allocation = 256 columns.
+// One CTA computes a 128 (weight rows) x 512 (tokens) output tile as TWO accumulators of UMMA N = 256: every dequantised
+// weight tile feeds two MMAs (round 2; with one N = 256 accumulator the producers, not the tensor pipe, set the pace):
+//   * 8 producer warps unpack the packed weights of a 64-wide K block straight into shared memory as f16 in the K-major
+//     SWIZZLE_128B layout the tensor core reads (no TMA path exists for K-quants: the "B operand must be produced by a
+//     dequant stage", SURVEY.md section 7 hard part 5).  Warps 0-3 own the even K blocks and stage 0, warps 4-7 the odd
+//     ones and stage 1: the two halves run one block apart, which is the whole software pipeline.  The matching f16
+//     activation block (512 tokens x 64 K) arrives next to it by TMA -- two cp.async.bulk.tensor.2d (SASS UTMALDG) from a
+//     SWIZZLE_128B tensor map over X, issued the moment the stage is free, completing on the stage's mbarrier; weight
+//     tiles are prefetched into L2 one tile ahead; fence.proxy.async + mbarrier hand the stage to the MMA warp;
+//   * 1 MMA warp: a single elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) four K steps x
+//     two token halves per block from shared-memory descriptors; the f32 accumulators (128 lanes x 2 x 256 columns = all
+//     of TMEM) ; tcgen05.commit releases the stage back to its producers and, after the last block, signals the epilogue;
+//   * epilogue: the 8 producer warps read the accumulators with tcgen05.ld (32x32b.x32) and store Y.
+// Two shared-memory stages (2 x 80 KB); TMEM allocation = 512 columns.
 // Numerics: weights are dequantised exactly as ggml does (f32) and rounded to f16, activations are f16, products
 // are accumulated in f32 by the tensor core -- the tolerance-level path (like upstream's CUDA backend for batches),
 // not the bit-exact integer path of the decode GEMV.
@@ -26,15 +26,16 @@
 #include "layout.cuh"
 
 #define GM_BM 128      /* weight rows per CTA  (UMMA M) */
-#define GM_BN 256      /* tokens per CTA       (UMMA N) */
-#define GM_BK 128      /* K elements per stage (two 64-element swizzle atoms, eight K=16 MMAs) */
+#define GM_BN 512      /* tokens per CTA: TWO accumulators of UMMA N = 256 -- every dequantised weight tile feeds two MMAs */
+#define GM_NH 256      /* UMMA N */
+#define GM_BK 64       /* K elements per stage (one 64-element swizzle atom, four K=16 steps x two token halves) */
 #define GM_STAGES 2
-#define GM_PRODUCER_WARPS 8
+#define GM_PRODUCER_WARPS 8              /* warps 0-3 produce the even K blocks (stage 0), warps 4-7 the odd ones (stage 1) */
 #define GM_THREADS ((GM_PRODUCER_WARPS + 1) * 32)
-#define GM_A_BYTES (GM_BM * GM_BK * 2)   /* 32 KB */
+#define GM_A_BYTES (GM_BM * GM_BK * 2)   /* 16 KB */
 #define GM_B_BYTES (GM_BN * GM_BK * 2)   /* 64 KB */
 #define GM_STAGE_BYTES (GM_A_BYTES + GM_B_BYTES)
-#define GM_TMEM_COLS 256
+#define GM_TMEM_COLS 512
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gm_mbar_init(uint32_t bar, uint32_t count) {
@@ -68,7 +69,7 @@ __device__ __forceinline__ uint64_t gm_desc(uint32_t smem_addr) {
 // N>>3 at [17,23), M>>4 at [24,29).  fp16 operands, not f16: the same UTCHMMA rate with 11 significand bits instead of
 // 8 -- the prefill's end-to-end error against the integer path drops 8x (tests/test_gpu_engine.py).
 __device__ __forceinline__ uint32_t gm_idesc() {
-    return (1u << 4) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(GM_NH >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
 }
 
 // byte offset of the 16-byte chunk `c` (0..7 inside a 128-byte swizzle row) of row `r` in a [rows][64 f16] atom
@@ -250,7 +251,7 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
 
     if (tid == 0) {
         /* full: one arrival per producer warp (A stored) + the expect_tx arrival of the thread that issued the TMA copies of B */
-        for (int s = 0; s < GM_STAGES; s++) { gm_mbar_init(gm_smem_u32(&bar_full[s]), GM_PRODUCER_WARPS + 1); gm_mbar_init(gm_smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < GM_STAGES; s++) { gm_mbar_init(gm_smem_u32(&bar_full[s]), GM_PRODUCER_WARPS / 2 + 1); gm_mbar_init(gm_smem_u32(&bar_empty[s]), 1); }
         gm_mbar_init(gm_smem_u32(&bar_acc), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -270,14 +271,14 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         // tiles (2048 elements per row) are pulled into L2 one tile ahead so the dequantiser's loads are L2 hits.
         const int pt = tid;                                   /* 0..255 */
         const int tile_bytes = ggb_sb_bytes(TYPE) * GGB_TILE_SB;
-        auto issue_b = [&](int kb) {   /* ONE thread: the 256-token x 128-K activation block as two 64-wide swizzle atoms */
+        const int n_half = (tokens - tok0 > GM_NH) ? 2 : 1;   /* token halves this CTA really has */
+        auto issue_b = [&](int kb) {   /* ONE thread: the 512-token x 64-K activation block, one 256-token box per half */
             const int st = kb % GM_STAGES;
             const uint32_t sB = gm_smem_u32(stage_base + st * GM_STAGE_BYTES + GM_A_BYTES), bar = gm_smem_u32(&bar_full[st]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)GM_B_BYTES) : "memory");
-#pragma unroll
-            for (int h = 0; h < 2; h++)   /* rows beyond `tokens` are zero-filled by the copy engine */
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(n_half * GM_NH * GM_BK * 2)) : "memory");
+            for (int h = 0; h < n_half; h++)   /* rows beyond `tokens` are zero-filled by the copy engine */
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                             ::"r"(sB + h * (GM_BN * 128)), "l"(&tmapX), "r"(kb * GM_BK + h * 64), "r"(tok0), "r"(bar) : "memory");
+                             ::"r"(sB + h * (GM_NH * 128)), "l"(&tmapX), "r"(kb * GM_BK), "r"(tok0 + h * GM_NH), "r"(bar) : "memory");
         };
         auto prefetch_tile = [&](int t) {                      /* one thread per row pulls tile t of its row into L2 */
             if (pt < GM_BM && row0 + pt < rows && t * GGB_TILE_ELEMS < K) {
@@ -287,51 +288,45 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         };
         prefetch_tile(0);
         prefetch_tile(1);
-        const int r = pt & 127, hk = pt >> 7;                 /* A: thread -> (row, which 64-wide atom of the 128-wide K block) */
+        // thread -> (row, parity): the half `par` of the producers owns the K blocks kb = par, par + 2, ... and with them
+        // stage `par` -- the two halves run one block apart, which is the whole software pipeline
+        const int r = pt & 127, par = pt >> 7;
         const int grow = row0 + r;
         const bool arow = grow < rows;
         Raw<TYPE> raw;
         auto fetch_a = [&](int kb) {
-            const int k0 = kb * GM_BK + hk * 64;
+            const int k0 = kb * GM_BK;
             const int t = k0 / GGB_TILE_ELEMS, ek = k0 - t * GGB_TILE_ELEMS;
             const int nsb = ggb_tile_nsb(K, t);
             dq_fetch(raw, W + (int64_t)grow * w_stride + (int64_t)t * tile_bytes, 4 * nsb, nsb, ek);
         };
-        if (arow) fetch_a(0);
-        if (tid == 0) issue_b(0);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % GM_STAGES;
-            uint8_t* sA = stage_base + s * GM_STAGE_BYTES;
-            // stage s is free (waited for when B(kb) was issued)
-            {
-                if ((kb * GM_BK) % GGB_TILE_ELEMS == 0) prefetch_tile(kb * GM_BK / GGB_TILE_ELEMS + 2);
-                Chunk8 ch;
-                // Where the next block's packed bytes are requested is a measured choice per format: the loads of two
-                // iterations share a scoreboard, so requesting early makes the first use of the CURRENT bytes wait for the
-                // new loads too (ncu: stall_long_sb).  Q4_K (3 loads, short conversion) is better off requesting after the
-                // conversion; Q6_K / Q8_0 (long conversions) before it.
-                constexpr bool FETCH_EARLY = (TYPE != GGB_TYPE_Q4_K);
-                if (arow) {
-                    const Raw<TYPE> cur = raw;
-                    if (FETCH_EARLY && kb + 1 < nkb) fetch_a(kb + 1);
-                    dq_convert(cur, ch);
-                } else {
+        if (arow && par < nkb) fetch_a(par);
+        uint8_t* sA = stage_base + par * GM_STAGE_BYTES;
+        for (int kb = par; kb < nkb; kb += 2) {
+            // my stage is free once the MMAs of block kb - 2 have read it; its activation block starts travelling at once
+            if (kb >= 2) gm_mbar_wait(gm_smem_u32(&bar_empty[par]), ((kb >> 1) & 1) ^ 1);
+            if (r == 0) issue_b(kb);
+            if (par == 0 && (kb * GM_BK) % GGB_TILE_ELEMS == 0) prefetch_tile(kb * GM_BK / GGB_TILE_ELEMS + 2);
+            Chunk8 ch;
+            // Where the next block's packed bytes are requested is a measured choice per format: the loads of two
+            // iterations share a scoreboard, so requesting early makes the first use of the CURRENT bytes wait for the
+            // new loads too (ncu: stall_long_sb).  Q4_K (3 loads, short conversion) is better off requesting after the
+            // conversion; Q6_K / Q8_0 (long conversions) before it.
+            constexpr bool FETCH_EARLY = (TYPE != GGB_TYPE_Q4_K);
+            if (arow) {
+                const Raw<TYPE> cur = raw;
+                if (FETCH_EARLY && kb + 2 < nkb) fetch_a(kb + 2);
+                dq_convert(cur, ch);
+            } else {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) ch.c[c] = make_uint4(0, 0, 0, 0);
-                }
-                uint8_t* atom = sA + hk * (GM_BM * 128);
+                for (int c = 0; c < 8; c++) ch.c[c] = make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(atom + gm_sw(r, c)) = ch.c[c];
-                if (!FETCH_EARLY && arow && kb + 1 < nkb) fetch_a(kb + 1);
-            }
-            if (kb + 1 < nkb) {   /* the next stage must be free before anybody writes A into it; its B copy starts now */
-                const int s1 = (kb + 1) % GM_STAGES;
-                gm_mbar_wait(gm_smem_u32(&bar_empty[s1]), (((kb + 1) / GM_STAGES) & 1) ^ 1);
-                if (tid == 0) issue_b(kb + 1);
-            }
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(sA + gm_sw(r, c)) = ch.c[c];
+            if (!FETCH_EARLY && arow && kb + 2 < nkb) fetch_a(kb + 2);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the tensor core */
             __syncwarp();
-            if (lane == 0) gm_mbar_arrive(gm_smem_u32(&bar_full[s]));
+            if (lane == 0) gm_mbar_arrive(gm_smem_u32(&bar_full[par]));
         }
         // ===== epilogue: TMEM -> registers -> Y =====
         gm_mbar_wait(gm_smem_u32(&bar_acc), 0);
@@ -339,8 +334,9 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
         const int q = warp & 3, colh = warp >> 2;              /* TMEM lane quarter, column half */
         const int erow = row0 + 32 * q + lane;
 #pragma unroll 1
-        for (int cb = 0; cb < 4; cb++) {                       /* 4 x 32 columns = this warp's 128 tokens */
-            const int col = colh * 128 + cb * 32;
+        for (int cb = 0; cb < GM_NH / 32; cb++) {              /* 8 x 32 columns = this warp's 256 tokens */
+            const int col = colh * GM_NH + cb * 32;
+            if (tok0 + col >= tokens) break;
             uint32_t v[32];
             const uint32_t taddr = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)col;
             asm volatile(
@@ -371,17 +367,19 @@ gemm_kernel(const uint8_t* __restrict__ W, int64_t w_stride, int rows, int K, co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t a0 = gm_smem_u32(stage_base + s * GM_STAGE_BYTES), b0 = a0 + GM_A_BYTES;
+                const int n_half = (tokens - tok0 > GM_NH) ? 2 : 1;
 #pragma unroll
                 for (int k = 0; k < GM_BK / 16; k++) {
-                    const uint32_t aoff = (k >> 2) * (GM_BM * 128) + (k & 3) * 32;   /* atom, then 32 B per K=16 step */
-                    const uint32_t boff = (k >> 2) * (GM_BN * 128) + (k & 3) * 32;
-                    const uint64_t da = gm_desc(a0 + aoff), db = gm_desc(b0 + boff);
+                    const uint64_t da = gm_desc(a0 + k * 32);                              /* 32 B per K=16 step inside the atom */
                     const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t"
-                        "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                    for (int h = 0; h < n_half; h++) {                                     /* the same weight tile against both token halves */
+                        const uint64_t db = gm_desc(b0 + h * (GM_NH * 128) + k * 32);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_acc + (uint32_t)(h * GM_NH)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                    }
                 }
                 // tcgen05.commit implies fence::before_thread_sync; frees the smem stage when the MMAs have read it
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gm_smem_u32(&bar_empty[s])) : "memory");
@@ -436,7 +434,7 @@ static int launch_gemm(const void* w, int rows, int k, const void* x, int tokens
     if (!enc) GGB_FAIL(GGB_ERR_CUDA, "ggb_gemm: the driver does not export cuTensorMapEncodeTiled");
     CUtensorMap tmap;
     const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)tokens}, strides[1] = {(cuuint64_t)k * 2};
-    const cuuint32_t box[2] = {64, GM_BN}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {64, GM_NH}, estr[2] = {1, 1};
     const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) GGB_FAIL(GGB_ERR_CUDA, "ggb_gemm: cuTensorMapEncodeTiled failed (%d)", (int)cr);
