@@ -33,6 +33,15 @@ extern "C" int ggb_debug_timeline_attn(unsigned long long* out_host) {
 #define ATL(i) do { } while (0)
 #endif
 
+// f16 -> f64 in one conversion (SASS F2F.F64.F16).  Both dot products of the attention are sums of EXACT products in f64:
+// f16 x f16 (K.Q) and f32 x f16 (e.V) fit 53 bits, so one DFMA per element replaces h2f + FMUL + F2F + DADD, and a K / V element
+// converted once serves every query head that shares it (oracle: gref_attn_decode_canon, the same definition).
+__device__ __forceinline__ double h2d(uint32_t h16) {
+    double d;
+    asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"((uint16_t)h16));
+    return d;
+}
+
 #define ATTN_CL 8      /* CTAs per cluster = position slices per head (batch-1 decode) */
 #define ATTN_CL_BATCH 2 /* batched decode: many (entry, head) clusters are in flight, fewer CTAs each is cheaper (measured) */
 #define ATTN_WARPS 8        /* batch-1 decode: warps per CTA (4 / 8 / 16 measured: 516 / 527 / 456 tok/s) */
@@ -104,13 +113,13 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
     // spread over 20 us).  Hence a flag, set by the host when it has padded the projection.
     if (trigger) pdl_launch_dependents();
 
-    float qr[8];
+    double qd[8];
     {
         const float4 a = *reinterpret_cast<const float4*>(q + (int64_t)head * HD + li * 8);
         const float4 b = *reinterpret_cast<const float4*>(q + (int64_t)head * HD + li * 8 + 4);
         const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) qr[i] = h2f(f2h(t[i]));
+        for (int i = 0; i < 8; i++) qd[i] = h2d(f2h(t[i]));
     }
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
 
@@ -131,12 +140,13 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
             const int p = p0 + u * SLOTS + sub;
             const bool live = p < p_end;
             const uint32_t kw[4] = {kraw[u].x, kraw[u].y, kraw[u].z, kraw[u].w};
-            double s = 0.0;
+            double s = 0.0, s1 = 0.0;                                   // exact products, two chains
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                s += (double)__fmul_rn(h2f((uint16_t)(kw[i] & 0xFFFF)), qr[2 * i]);      // exact products
-                s += (double)__fmul_rn(h2f((uint16_t)(kw[i] >> 16)), qr[2 * i + 1]);
+                s = __fma_rn(h2d(kw[i] & 0xFFFF), qd[2 * i], s);
+                s1 = __fma_rn(h2d(kw[i] >> 16), qd[2 * i + 1], s1);
             }
+            s += s1;
 #pragma unroll
             for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const float sf = __fmul_rn((float)s, scale);
@@ -179,13 +189,13 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
         for (int u = 0; u < AU; u++) {
             const int p = p0 + u * SLOTS + sub;
             if (p < p_end) {
-                const float e = exp_ref(__fsub_rn(s_scores[p - p_begin], M));
+                const double e = (double)exp_ref(__fsub_rn(s_scores[p - p_begin], M));
                 const uint32_t vw[4] = {vraw[u].x, vraw[u].y, vraw[u].z, vraw[u].w};
-                sum += (double)e;
+                sum += e;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    acc[2 * i] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] & 0xFFFF)));
-                    acc[2 * i + 1] += (double)__fmul_rn(e, h2f((uint16_t)(vw[i] >> 16)));
+                    acc[2 * i] = __fma_rn(e, h2d(vw[i] & 0xFFFF), acc[2 * i]);
+                    acc[2 * i + 1] = __fma_rn(e, h2d(vw[i] >> 16), acc[2 * i + 1]);
                 }
             }
         }
@@ -236,7 +246,7 @@ attn_decode_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc,
 //           a transposing butterfly (log2 GQ levels halve the values a lane holds, the rest are plain levels): lane li ends up
 //           with the score of query head li / (LPG / GQ);
 //   pass 2  per position one V load, GQ exponentials, GQ x 8 f64 accumulators per lane.
-template <int HD, int CL, int NW, int GQ>
+template <int HD, int CL, int NW, int GQ, int AU>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NW * 32)
 attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                        const int32_t* __restrict__ pos_dev, int n_head, int n_kv, float* __restrict__ out,
@@ -271,20 +281,19 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
     const int p_begin = min(n, crank * chunk), p_end = min(n, p_begin + chunk);
     pdl_wait();
 
-    float qr[GQ][8];
+    double qd[GQ][8];
 #pragma unroll
     for (int g = 0; g < GQ; g++) {
         const float4 a = *reinterpret_cast<const float4*>(q + (int64_t)(head0 + g) * HD + li * 8);
         const float4 b = *reinterpret_cast<const float4*>(q + (int64_t)(head0 + g) * HD + li * 8 + 4);
         const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) qr[g][i] = h2f(f2h(t[i]));
+        for (int i = 0; i < 8; i++) qd[g][i] = h2d(f2h(t[i]));
     }
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
     const int myg = li / LQ;                       /* the query head whose reduced score this lane holds */
 
-    // ---- pass 1
-    constexpr int AU = 2;
+    // ---- pass 1 (AU positions per lane group in flight: the loop is bound by the latency of the cache reads, not by their volume)
     float mx = -INFINITY;
     for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
         uint4 kraw[AU];
@@ -297,16 +306,16 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
         for (int u = 0; u < AU; u++) {
             const int p = p0 + u * SLOTS + sub;
             const uint32_t kw[4] = {kraw[u].x, kraw[u].y, kraw[u].z, kraw[u].w};
-            float kf[8];
+            double kd[8];                                                  // converted ONCE for the four query heads
 #pragma unroll
-            for (int i = 0; i < 4; i++) { kf[2 * i] = h2f((uint16_t)(kw[i] & 0xFFFF)); kf[2 * i + 1] = h2f((uint16_t)(kw[i] >> 16)); }
+            for (int i = 0; i < 4; i++) { kd[2 * i] = h2d(kw[i] & 0xFFFF); kd[2 * i + 1] = h2d(kw[i] >> 16); }
             double s[GQ];
 #pragma unroll
             for (int g = 0; g < GQ; g++) {
-                double a = 0.0;
+                double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int i = 0; i < 8; i++) a += (double)__fmul_rn(kf[i], qr[g][i]);      // exact products
-                s[g] = a;
+                for (int i = 0; i < 4; i++) { a = __fma_rn(kd[2 * i], qd[g][2 * i], a); b = __fma_rn(kd[2 * i + 1], qd[g][2 * i + 1], b); }   // exact products
+                s[g] = a + b;
             }
             // transposing butterfly: 4 values -> 2 -> 1 per lane, then the plain levels below LQ
             {
@@ -350,6 +359,7 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
         M[g] = m;
     }
 
+    const float M_mine = (li & 3) == 0 ? M[0] : ((li & 3) == 1 ? M[1] : ((li & 3) == 2 ? M[2] : M[3]));
     // ---- pass 2
     double acc[GQ][8], sum[GQ];
 #pragma unroll
@@ -368,17 +378,20 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
 #pragma unroll
         for (int u = 0; u < AU; u++) {
             const int p = p0 + u * SLOTS + sub;
-            if (p < p_end) {
-                const uint32_t vw[4] = {vraw[u].x, vraw[u].y, vraw[u].z, vraw[u].w};
-                float vf[8];
+            const bool live = p < p_end;                 /* the two positions of a warp step may differ: shuffles stay outside the branch */
+            const uint32_t vw[4] = {vraw[u].x, vraw[u].y, vraw[u].z, vraw[u].w};
+            double vd[8];
 #pragma unroll
-                for (int i = 0; i < 4; i++) { vf[2 * i] = h2f((uint16_t)(vw[i] & 0xFFFF)); vf[2 * i + 1] = h2f((uint16_t)(vw[i] >> 16)); }
+            for (int i = 0; i < 4; i++) { vd[2 * i] = h2d(vw[i] & 0xFFFF); vd[2 * i + 1] = h2d(vw[i] >> 16); }
+            // one exponential per lane (lane li takes head li & 3), handed round the position's lanes by four shuffles
+            const float e_mine = live ? exp_ref(__fsub_rn(s_scores[(li & 3) * chunk_max + (p - p_begin)], M_mine)) : 0.f;
 #pragma unroll
-                for (int g = 0; g < GQ; g++) {
-                    const float e = exp_ref(__fsub_rn(s_scores[g * chunk_max + (p - p_begin)], M[g]));
-                    sum[g] += (double)e;
+            for (int g = 0; g < GQ; g++) {
+                const double e = (double)__shfl_sync(0xffffffffu, e_mine, (lane & ~(LPG - 1)) | g);
+                if (live) {
+                    sum[g] += e;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[g][i] += (double)__fmul_rn(e, vf[i]);
+                    for (int i = 0; i < 8; i++) acc[g][i] = __fma_rn(e, vd[i], acc[g][i]);
                 }
             }
         }
@@ -418,7 +431,7 @@ attn_decode_gqa_kernel(const float* __restrict__ q, const uint16_t* __restrict__
     }
 }
 
-template <int HD, int CL, int NW, int GQ>
+template <int HD, int CL, int NW, int GQ, int AU>
 static int launch_attn_gqa(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv,
                            int n_ctx, float* out, int use_pdl, cudaStream_t st, const int32_t* slot_dev, int64_t slot_stride, int nb) {
     constexpr int SLOTS = NW * (32 / (HD / 8));
@@ -429,8 +442,8 @@ static int launch_attn_gqa(const float* q, const uint16_t* kc, const uint16_t* v
     if (smem > 200 * 1024) return 1;            /* context too long for this variant: the caller falls back */
     static bool attr = false;
     if (!attr) {
-        GGB_CUDA(cudaFuncSetAttribute(attn_decode_gqa_kernel<HD, CL, NW, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        GGB_CUDA(cudaFuncSetAttribute(attn_decode_gqa_kernel<HD, CL, NW, GQ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_gqa_kernel<HD, CL, NW, GQ, AU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GGB_CUDA(cudaFuncSetAttribute(attn_decode_gqa_kernel<HD, CL, NW, GQ, AU>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -443,7 +456,7 @@ static int launch_attn_gqa(const float* q, const uint16_t* kc, const uint16_t* v
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = (use_pdl & 1) ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_gqa_kernel<HD, CL, NW, GQ>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride, chunk_max));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_gqa_kernel<HD, CL, NW, GQ, AU>, q, kc, vc, pos_dev, n_head, n_kv, out, slot_dev, slot_stride, chunk_max));
     return GGB_OK;
 }
 
@@ -509,20 +522,16 @@ extern "C" int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, con
     // contexts still want the 8-way position split (GGB_ATTN_BATCH_CL overrides: 2, 4 or 8)
     static const int cl_env = []() { const char* v = getenv("GGB_ATTN_BATCH_CL"); return v && *v ? atoi(v) : 0; }();
     const int cl = cl_env ? cl_env : (n_ctx <= 4096 ? ATTN_CL_BATCH : (n_ctx <= 16384 ? 4 : 8));
-    // grouped-query variant: four query heads of a KV head per cluster (each K / V row loaded once for the four).  Measured
-    // on Llama-3-8B, 16 sequences (tools/batch_bench.py): ~930 positions each 7.24 -> 6.13 ms per step (4 CTAs per cluster;
-    // 2: 6.97, 8: 6.94); ~50 positions 4.58 -> 4.52; but ~8000 positions 23.4 -> 27.4 ms: there the kernel is bound by its f64
-    // arithmetic, not by the cache reads, and the leaner per-head CTAs (80 registers, 20 KB) keep five times more warps
-    // resident.  Hence: contexts up to 2048 positions per slot (GGB_ATTN_GQA=0 / 2 force it off / on).
+    // grouped-query variant: four query heads of a KV head per cluster (each K / V row loaded AND converted once for the four).
+    // Measured on Llama-3-8B, 16 sequences (tools/batch_bench.py), per-head kernel -> this one: ~50 positions 4.58 -> 4.5 ms per
+    // step, ~930 positions 7.24 -> 5.34 (4 positions per lane group in flight), ~8000 positions 23.4 -> 15.4 (8 in flight: with 8
+    // warps per SM the loop is bound by the latency of its cache reads).  GGB_ATTN_GQA=0 switches it off.
     static const int gqa_env = []() { const char* v = getenv("GGB_ATTN_GQA"); return v && *v ? atoi(v) : 1; }();
-    static const int gqa_cl_env = []() { const char* v = getenv("GGB_ATTN_GQA_CL"); return v && *v ? atoi(v) : 0; }();
-    if (gqa_env && head_dim == 128 && (n_head / n_kv) % 4 == 0 && (n_ctx <= 2048 || gqa_env == 2)) {
-        const int gcl = gqa_cl_env ? gqa_cl_env : (n_ctx <= 2048 ? 4 : 8);
+    if (gqa_env && head_dim == 128 && (n_head / n_kv) % 4 == 0) {
         int rc;
-        if (gcl == 2) rc = launch_attn_gqa<128, 2, ATTN_WARPS_BATCH, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
-        else if (gcl == 4) rc = launch_attn_gqa<128, 4, ATTN_WARPS_BATCH, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
-        else rc = launch_attn_gqa<128, 8, ATTN_WARPS_BATCH, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
-        if (rc != 1) return rc;
+        if (n_ctx <= 2048) rc = launch_attn_gqa<128, 4, ATTN_WARPS_BATCH, 4, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        else rc = launch_attn_gqa<128, 4, ATTN_WARPS_BATCH, 4, 8>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
+        if (rc != 1) return rc;      /* 1: the context does not fit this variant's shared memory */
     }
     if (head_dim == 128) {
         if (cl == 1) return launch_attn<128, 1>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);

@@ -758,7 +758,7 @@ void gref_attn_decode_canon(const float *q, const uint16_t *kc, const uint16_t *
             const float e = gref_exp_ref(sc[p] - mx);
             sum += (double)e;
             const uint16_t *vr = vc + p * kv_stride + (int64_t)kvh * hd;
-            for (int i = 0; i < hd; i++) o[i] += (double)(e * gref_fp16_to_fp32(vr[i]));
+            for (int i = 0; i < hd; i++) o[i] += (double)e * (double)gref_fp16_to_fp32(vr[i]);   /* exact product (24 x 11 bits), like K.Q */
         }
         for (int i = 0; i < hd; i++) out[(int64_t)h * hd + i] = (float)(o[i] / sum);
         free(sc); free(qh); free(o);
