@@ -150,6 +150,9 @@ int ggb_gemv_grid(const ggb_gemv_args* args);
  *   Y[tokens][y_stride >= rows] (f32) = X[tokens][k] (f16) . W[rows][k]^T,  W in tile-SoA layout, k % 128 == 0.
  * Weights are dequantised exactly (f32) and rounded to f16 inside the kernel (kind::f16 with fp16 operands: 11 significand bits); accumulation is f32 in TMEM. */
 int ggb_gemm(int type, const void* w, int rows, int k, const void* x_f16, int tokens, float* y, int64_t y_stride, void* stream);
+/* two weight matrices of the same format and shape (ffn_gate, ffn_up) against the same activations in one launch */
+int ggb_gemm2(int type, const void* w0, const void* w1, int rows, int k, const void* x_f16, int tokens, float* y0, float* y1,
+              int64_t y_stride, void* stream);
 int ggb_f32_to_f16(const float* x, void* y_f16, int64_t n, void* stream);
 /* y = f16(d * q): x [m][k] quantised as the CPU path quantises the activation operand (Q8_K per 256 elements; Q8_0 per 32
  * when q8_0 != 0) and dequantised again -- the activation operand of ggb_gemm that keeps it within f16 rounding of ggml's

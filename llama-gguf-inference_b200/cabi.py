@@ -22,7 +22,7 @@ EXPORTS = [
     "ggb_abi_version", "ggb_last_error", "ggb_device_info",
     "ggb_dequant", "ggb_repacked_row_stride", "ggb_repack", "ggb_dequant_repacked",
     "ggb_quantize_q8_K", "ggb_quantize_q8_0",
-    "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemm", "ggb_f32_to_f16", "ggb_act_fakequant_f16", "ggb_swiglu_fakequant_f16", "ggb_add_rmsnorm_fakequant_f16",
+    "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemm", "ggb_gemm2", "ggb_f32_to_f16", "ggb_act_fakequant_f16", "ggb_swiglu_fakequant_f16", "ggb_add_rmsnorm_fakequant_f16",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
     "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
         "ggb_gemv_grid": ([C.POINTER(GemvArgs)], i32),
         "ggb_gemv_smem_bytes": ([C.POINTER(GemvArgs)], i64),
         "ggb_gemm": ([i32, vp, i32, i32, vp, i32, vp, i64, vp], i32),
+        "ggb_gemm2": ([i32, vp, vp, i32, i32, vp, i32, vp, vp, i64, vp], i32),
         "ggb_f32_to_f16": ([vp, vp, i64, vp], i32),
         "ggb_act_fakequant_f16": ([vp, vp, i64, i32, i32, vp], i32),
         "ggb_swiglu_fakequant_f16": ([vp, vp, vp, i64, i32, i32, vp], i32),

@@ -721,7 +721,12 @@ class Engine:
                 to_f16(B["att"], qd, L["wo"])
                 gemm(L["wo"], B["xb"], Y)
                 norm_quant(Y, L["ffn_norm"], L["wg"])
-                gemm(L["wg"], B["xb"], B["gate"]); gemm(L["wu"], B["xb"], B["up"])
+                wg, wu = L["wg"], L["wu"]
+                if wg.type == wu.type and wg.rows == wu.rows and wg.k == wu.k:     # one launch: 6.05 waves instead of 2 x 3.03
+                    cabi.check(lib.ggb_gemm2(wg.type, wg.ptr, wu.ptr, wg.rows, wg.k, B["xb"].data_ptr(), T, B["gate"].data_ptr(),
+                                             B["up"].data_ptr(), wg.rows, s), "gemm2")
+                else:
+                    gemm(wg, B["xb"], B["gate"]); gemm(wu, B["xb"], B["up"])
                 if self.prefill_raw_act:
                     cabi.check(lib.ggb_swiglu(B["gate"].data_ptr(), B["up"].data_ptr(), B["gate"].data_ptr(), T * hp.ff, s), "swiglu")
                     to_f16(B["gate"], hp.ff, L["wd"])

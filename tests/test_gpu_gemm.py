@@ -52,6 +52,30 @@ def test_gemm_matches_oracle(oracle, name, rows, k, tokens):
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("name,rows,k,tokens", [("q4_k", 300, 2048, 700), ("q6_k", 128, 256, 17), ("q8_0", 1000, 1024, 513)])
+def test_gemm2_equals_two_gemms(name, rows, k, tokens):
+    """ggb_gemm2 (ffn_gate + ffn_up in one launch: the second matrix's row tiles ride behind the first's) must give exactly what
+    two ggb_gemm launches give"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    qt = TYPES[name]
+    rng = np.random.default_rng(rows + k + tokens)
+    import oracle.oracle as O
+    be, _ = O.BLOCK[qt]
+    w0 = U.gpu_repack(qt, rand_blocks(qt, rows * k // be, rng), rows, k)
+    w1 = U.gpu_repack(qt, rand_blocks(qt, rows * k // be, rng), rows, k)
+    xb = torch.randn((tokens, k), device=U.DEV).to(torch.float16)
+    ya, yb, y0, y1 = (torch.full((tokens, rows), float("nan"), dtype=torch.float32, device=U.DEV) for _ in range(4))
+    s = U.stream_ptr()
+    cabi.check(L.ggb_gemm(qt, w0.data_ptr(), rows, k, xb.data_ptr(), tokens, ya.data_ptr(), rows, s))
+    cabi.check(L.ggb_gemm(qt, w1.data_ptr(), rows, k, xb.data_ptr(), tokens, yb.data_ptr(), rows, s))
+    cabi.check(L.ggb_gemm2(qt, w0.data_ptr(), w1.data_ptr(), rows, k, xb.data_ptr(), tokens, y0.data_ptr(), y1.data_ptr(), rows, s))
+    U.sync()
+    assert torch.isfinite(y0).all() and torch.equal(y0, ya) and torch.equal(y1, yb)
+
+
 @pytest.mark.parametrize("name", list(TYPES))
 @pytest.mark.parametrize("rows,k,tokens", [(300, 2048, 17), (256, 4096, 33), (64, 14336, 8)])
 def test_gemm_on_requantised_activations_tracks_the_integer_path(oracle, name, rows, k, tokens):
