@@ -525,9 +525,12 @@ extern "C" int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, con
     // grouped-query variant: four query heads of a KV head per cluster (each K / V row loaded AND converted once for the four).
     // Measured on Llama-3-8B, 16 sequences (tools/batch_bench.py), per-head kernel -> this one: ~50 positions 4.58 -> 4.5 ms per
     // step, ~930 positions 7.24 -> 5.34 (4 positions per lane group in flight), ~8000 positions 23.4 -> 15.4 (8 in flight: with 8
-    // warps per SM the loop is bound by the latency of its cache reads).  GGB_ATTN_GQA=0 switches it off.
-    static const int gqa_env = []() { const char* v = getenv("GGB_ATTN_GQA"); return v && *v ? atoi(v) : 1; }();
-    if (gqa_env && head_dim == 128 && (n_head / n_kv) % 4 == 0) {
+    // warps per SM the loop is bound by the latency of its cache reads).  GGB_ATTN_GQA=0 switches it off, 2 forces it.
+    const char* gqa_s = getenv("GGB_ATTN_GQA");            /* read per call (launches are captured into graphs): tests force it on / off */
+    const int gqa_env = gqa_s && *gqa_s ? atoi(gqa_s) : 1;
+    // (it needs enough clusters to fill the GPU: with few entries -- 2 sequences x 8 KV groups x 4 CTAs = 64 CTAs measured 20.9 ms
+    // per step at 30 K positions against 2 x 6.2 ms -- the per-head kernel below keeps four times as many CTAs busy)
+    if (gqa_env && head_dim == 128 && (n_head / n_kv) % 4 == 0 && (gqa_env == 2 || nb * (n_head / 4) * 4 >= 2 * ggb_num_sms())) {
         int rc;
         if (n_ctx <= 2048) rc = launch_attn_gqa<128, 4, ATTN_WARPS_BATCH, 4, 4>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);
         else rc = launch_attn_gqa<128, 4, ATTN_WARPS_BATCH, 4, 8>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st, slot_dev, slot_stride, nb);

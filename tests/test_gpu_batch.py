@@ -173,11 +173,14 @@ def test_gemv_batch_bad_args():
     assert L.ggb_act_image_bytes(100) == -1
 
 
+@pytest.mark.parametrize("gqa", ["2", "0"])
 @pytest.mark.parametrize("n_head,n_kv,hd,n_ctx", [(8, 2, 64, 96), (8, 2, 128, 96), (16, 2, 128, 2048), (16, 2, 128, 2304), (4, 4, 128, 96)])
-def test_rope_kv_attn_argmax_batch(oracle, n_head, n_kv, hd, n_ctx):
+def test_rope_kv_attn_argmax_batch(oracle, monkeypatch, gqa, n_head, n_kv, hd, n_ctx):
     """per-token (slot, position) addressing: every entry equals the one-token kernels' / the oracle's result.  head_dim 128
-    with 4 or 8 query heads per KV head takes the grouped-query kernel (one cluster of four CTAs per four query heads; 4 or 8
-    positions per lane group in flight by context size); the other shapes the per-head kernel."""
+    with 4 or 8 query heads per KV head takes the grouped-query kernel when GGB_ATTN_GQA=2 forces it (by default only batches with
+    enough clusters to fill the GPU do): one cluster of four CTAs per four query heads, 4 or 8 positions per lane group in flight by
+    context size; the other shapes, and GGB_ATTN_GQA=0, the per-head kernel."""
+    monkeypatch.setenv("GGB_ATTN_GQA", gqa)
     import torch
     import gpu_util as U
     from ggufb200 import cabi
