@@ -212,8 +212,13 @@ int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int32_t* pos_de
  * q [n_head*hd] f32 (already rotated); caches [n_ctx][n_kv*hd] f16; attends positions 0..*pos_dev inclusive.
  * use_pdl: bit 0 = launch with programmatic stream serialisation; bit 1 = also release the NEXT launch once this one
  * has passed its dependency wait (only useful when that launch cannot land twice on an SM: ggb_gemv_args.min_smem).
- * ws: workspace of ggb_attn_decode_ws_bytes() bytes.  out [n_head*hd] f32. */
+ * bit 2 = the sequence is long (a few thousand positions): run the two softmax passes as launches over the whole GPU (position
+ * slices x groups of four query heads; head_dim 128, 4 or 8 query heads per KV head, n_ctx > 2048) that exchange scores and
+ * partial sums through ws -- same result bit for bit, faster from ~2 000 positions on, slower below.
+ * ws: workspace of ggb_attn_decode_ws_bytes_ctx() bytes, 256-byte aligned (16 bytes when the long-sequence path does not apply).
+ * out [n_head*hd] f32. */
 size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim);
+size_t ggb_attn_decode_ws_bytes_ctx(int n_head, int n_kv, int head_dim, int n_ctx);
 int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
                     int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream);
 

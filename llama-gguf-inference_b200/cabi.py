@@ -24,7 +24,7 @@ EXPORTS = [
     "ggb_quantize_q8_K", "ggb_quantize_q8_0",
     "ggb_gemv", "ggb_gemv_grid", "ggb_gemv_smem_bytes", "ggb_gemm", "ggb_gemm2", "ggb_f32_to_f16", "ggb_act_fakequant_f16", "ggb_swiglu_fakequant_f16", "ggb_add_rmsnorm_fakequant_f16",
     "ggb_embed_row", "ggb_argmax_next", "ggb_rms_norm", "ggb_swiglu", "ggb_argmax",
-    "ggb_attn_decode_ws_bytes", "ggb_attn_decode",
+    "ggb_attn_decode_ws_bytes", "ggb_attn_decode_ws_bytes_ctx", "ggb_attn_decode",
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
     "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "ggb_swiglu": ([vp, vp, vp, i64, vp], i32),
         "ggb_argmax": ([vp, i64, vp, vp], i32),
         "ggb_attn_decode_ws_bytes": ([i32, i32], sz),
+        "ggb_attn_decode_ws_bytes_ctx": ([i32, i32, i32, i32], sz),
         "ggb_attn_decode": ([vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp], i32),
         "ggb_residual_add_f64": ([vp, vp, i64, i32, vp], i32),
         "ggb_embed_rows": ([i32, vp, i64, vp, i32, vp, vp], i32),

@@ -460,6 +460,269 @@ static int launch_attn_gqa(const float* q, const uint16_t* kc, const uint16_t* v
     return GGB_OK;
 }
 
+// ------------------------------------------------------------------ long contexts, one sequence: split over the whole GPU
+// A cluster of 8 CTAs per head reads a long cache at ~0.6 TB/s (8 000 positions: 52 us per layer, 3.1 ms per token on
+// Llama-3-8B): too few warps, one conversion per element per QUERY head.  For contexts beyond ATTN_SPLIT_MIN_CTX the two passes
+// of the same two-pass softmax become two launches over (position slices x groups of four query heads) -- every SM busy, each
+// K / V element loaded and converted once for the four heads of its group -- with the exchange through a global workspace
+// (Llama-3-8B, one sequence: 8 000 positions 3.15 -> 2.33 ms per token, 30 000 positions 7.65 -> 4.08; at 300 positions the
+// three launches cost 1.70 vs 1.45 ms, hence the caller's per-step choice):
+//   scores   slice of positions x 4 heads: scores -> ws, slice maxima -> ws
+//   values   global maximum per head from the slice maxima; e = exp_ref(s - M); f64 partial sums of e and e.V per slice -> ws
+//   merge    per head: partials added in slice order, out = (float)(sum_ev / sum_e)
+// Same arithmetic (exact products, f64 sums, one rounding): bit-identical with the cluster kernel and the oracle.
+#define ATTN_SPLIT_MIN_CTX 2048   /* caches that can hold sequences long enough for the split kernels to pay */
+#define ATTN_SPLIT_NW 8
+#define ATTN_SPLIT_MAX_S 64
+
+struct SplitWs { float* scores; float* smax; double* part; double* psum; };
+
+template <int HD, int GQ, int AU>
+__global__ void __launch_bounds__(ATTN_SPLIT_NW * 32)
+attn_split_scores_kernel(const float* __restrict__ q, const uint16_t* __restrict__ kc, const int32_t* __restrict__ pos_dev,
+                         int n_head, int n_kv, SplitWs W, int n_ctx_pad, int S) {
+    constexpr int NW = ATTN_SPLIT_NW, LPG = HD / 8, PPW = 32 / LPG, SLOTS = NW * PPW, LQ = LPG / GQ;
+    static_assert(GQ == 4, "group of four query heads");
+    __shared__ float sm_max[NW * GQ];
+    const int split = blockIdx.x, head0 = blockIdx.y * GQ;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int sub = lane / LPG, li = lane % LPG;
+    const int kvh = head0 / (n_head / n_kv);
+    const int64_t kv_stride = (int64_t)n_kv * HD;
+    const int n = pos_dev[0] + 1;
+    int chunk = (n + S - 1) / S;
+    chunk = (chunk + SLOTS - 1) / SLOTS * SLOTS;
+    const int p_begin = min(n, split * chunk), p_end = min(n, p_begin + chunk);
+    pdl_wait();
+    pdl_launch_dependents();
+    double qd[GQ][8];
+#pragma unroll
+    for (int g = 0; g < GQ; g++) {
+        const float4 a = *reinterpret_cast<const float4*>(q + (int64_t)(head0 + g) * HD + li * 8);
+        const float4 b = *reinterpret_cast<const float4*>(q + (int64_t)(head0 + g) * HD + li * 8 + 4);
+        const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) qd[g][i] = h2d(f2h(t[i]));
+    }
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn((float)HD));
+    const int myg = li / LQ;
+    float mx = -INFINITY;
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        uint4 kraw[AU];
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            kraw[u] = *reinterpret_cast<const uint4*>(kc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            const uint32_t kw[4] = {kraw[u].x, kraw[u].y, kraw[u].z, kraw[u].w};
+            double kd[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { kd[2 * i] = h2d(kw[i] & 0xFFFF); kd[2 * i + 1] = h2d(kw[i] >> 16); }
+            double s[GQ];
+#pragma unroll
+            for (int g = 0; g < GQ; g++) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { a = __fma_rn(kd[2 * i], qd[g][2 * i], a); b = __fma_rn(kd[2 * i + 1], qd[g][2 * i + 1], b); }
+                s[g] = a + b;
+            }
+            {   /* transposing butterfly, as in attn_decode_gqa_kernel: lane li ends up with head li / LQ */
+                const bool up = li & (LPG / 2);
+                const double k0 = up ? s[2] : s[0], k1 = up ? s[3] : s[1], d0 = up ? s[0] : s[2], d1 = up ? s[1] : s[3];
+                s[0] = k0 + __shfl_xor_sync(0xffffffffu, d0, LPG / 2);
+                s[1] = k1 + __shfl_xor_sync(0xffffffffu, d1, LPG / 2);
+                const bool up2 = li & (LPG / 4);
+                const double k = up2 ? s[1] : s[0], d = up2 ? s[0] : s[1];
+                s[0] = k + __shfl_xor_sync(0xffffffffu, d, LPG / 4);
+#pragma unroll
+                for (int o = LQ / 2; o > 0; o >>= 1) s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+            }
+            const float sf = __fmul_rn((float)s[0], scale);
+            if (p < p_end) {
+                if (li % LQ == 0) W.scores[(int64_t)(head0 + myg) * n_ctx_pad + p] = sf;
+                mx = fmaxf(mx, sf);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        if (o < LQ || o >= LPG) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (sub == 0 && li % LQ == 0) sm_max[warp * GQ + myg] = mx;
+    __syncthreads();
+    if (threadIdx.x < GQ) {
+        float m = sm_max[threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < NW; w++) m = fmaxf(m, sm_max[w * GQ + threadIdx.x]);
+        W.smax[(head0 + threadIdx.x) * S + split] = m;      /* -inf for an empty slice */
+    }
+}
+
+template <int HD, int GQ, int AU>
+__global__ void __launch_bounds__(ATTN_SPLIT_NW * 32)
+attn_split_values_kernel(const uint16_t* __restrict__ vc, const int32_t* __restrict__ pos_dev, int n_head, int n_kv, SplitWs W,
+                         int n_ctx_pad, int S) {
+    constexpr int NW = ATTN_SPLIT_NW, LPG = HD / 8, PPW = 32 / LPG, SLOTS = NW * PPW;
+    __shared__ double sm_acc[NW][GQ][HD];      /* 32 KB */
+    __shared__ double sm_sum[NW][GQ];
+    __shared__ float sm_M[GQ];
+    const int split = blockIdx.x, head0 = blockIdx.y * GQ;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int sub = lane / LPG, li = lane % LPG;
+    const int kvh = head0 / (n_head / n_kv);
+    const int64_t kv_stride = (int64_t)n_kv * HD;
+    const int n = pos_dev[0] + 1;
+    int chunk = (n + S - 1) / S;
+    chunk = (chunk + SLOTS - 1) / SLOTS * SLOTS;
+    const int p_begin = min(n, split * chunk), p_end = min(n, p_begin + chunk);
+    // V rows of my first iteration do not depend on the scores launch: request them before the dependency wait
+    uint4 vpre[AU];
+#pragma unroll
+    for (int u = 0; u < AU; u++) {
+        const int p = p_begin + warp * PPW + u * SLOTS + sub;
+        vpre[u] = *reinterpret_cast<const uint4*>(vc + (p < p_end && p < n - 1 ? p : 0) * kv_stride + (int64_t)kvh * HD + li * 8);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    if (warp < GQ) {                                  /* global maximum of head head0 + warp over the slices */
+        float m = -INFINITY;
+        for (int s2 = lane; s2 < S; s2 += 32) m = fmaxf(m, W.smax[(head0 + warp) * S + s2]);
+        m = warp_max(m);
+        if (lane == 0) sm_M[warp] = m;
+    }
+    __syncthreads();
+    const float M_mine = sm_M[li & 3];
+    const float* sc_mine = W.scores + (int64_t)(head0 + (li & 3)) * n_ctx_pad;
+    double acc[GQ][8], sum[GQ];
+#pragma unroll
+    for (int g = 0; g < GQ; g++) {
+        sum[g] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[g][i] = 0.0;
+    }
+    for (int p0 = p_begin + warp * PPW; p0 < p_end; p0 += AU * SLOTS) {
+        const bool first = (p0 == p_begin + warp * PPW);
+        uint4 vraw[AU];
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            if (first && p < n - 1) vraw[u] = vpre[u];
+            else vraw[u] = *reinterpret_cast<const uint4*>(vc + (p < p_end ? p : p_begin) * kv_stride + (int64_t)kvh * HD + li * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const int p = p0 + u * SLOTS + sub;
+            const bool live = p < p_end;
+            const uint32_t vw[4] = {vraw[u].x, vraw[u].y, vraw[u].z, vraw[u].w};
+            double vd[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { vd[2 * i] = h2d(vw[i] & 0xFFFF); vd[2 * i + 1] = h2d(vw[i] >> 16); }
+            const float e_mine = live ? exp_ref(__fsub_rn(sc_mine[p], M_mine)) : 0.f;
+#pragma unroll
+            for (int g = 0; g < GQ; g++) {
+                const double e = (double)__shfl_sync(0xffffffffu, e_mine, (lane & ~(LPG - 1)) | g);
+                if (live) {
+                    sum[g] += e;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[g][i] = __fma_rn(e, vd[i], acc[g][i]);
+                }
+            }
+        }
+    }
+    // the two positions of a warp step meet by one shuffle level, the warps in shared memory, the slices in the workspace
+#pragma unroll
+    for (int g = 0; g < GQ; g++) {
+        if (PPW == 2) {
+            sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], LPG);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[g][i] += __shfl_xor_sync(0xffffffffu, acc[g][i], LPG);
+        }
+        if (lane == 0) sm_sum[warp][g] = sum[g];
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) sm_acc[warp][g][li * 8 + i] = acc[g][i];
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < GQ * HD; o += NW * 32) {
+        const int g = o / HD, d = o % HD;
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) a += sm_acc[w][g][d];
+        W.part[((int64_t)(head0 + g) * S + split) * HD + d] = a;
+    }
+    if (threadIdx.x < GQ) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) t += sm_sum[w][threadIdx.x];
+        W.psum[(head0 + threadIdx.x) * S + split] = t;
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(HD) attn_split_merge_kernel(SplitWs W, int S, float* __restrict__ out, int trigger) {
+    const int head = blockIdx.x, d = threadIdx.x;
+    pdl_wait();
+    if (trigger) pdl_launch_dependents();
+    double a = 0.0, t = 0.0;
+    for (int s2 = 0; s2 < S; s2++) {                  /* slice order: the same f64 sums for any split */
+        a += W.part[((int64_t)head * S + s2) * HD + d];
+        t += W.psum[head * S + s2];
+    }
+    out[(int64_t)head * HD + d] = (float)(a / t);
+}
+
+static int split_count(int n_head) {
+    static const int per_sm = []() { const char* v = getenv("GGB_ATTN_SPLIT_CTAS_PER_SM"); return v && *v ? atoi(v) : 2; }();
+    int s = per_sm * ggb_num_sms() / (n_head / 4);
+    return s < 1 ? 1 : (s > ATTN_SPLIT_MAX_S ? ATTN_SPLIT_MAX_S : s);
+}
+static size_t split_ws_layout(int n_head, int head_dim, int n_ctx, SplitWs* W, void* base) {
+    const int S = split_count(n_head);
+    const size_t n_ctx_pad = ((size_t)n_ctx + 63) & ~(size_t)63;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_part = take((size_t)n_head * S * head_dim * sizeof(double)), o_psum = take((size_t)n_head * S * sizeof(double));
+    const size_t o_sc = take((size_t)n_head * n_ctx_pad * sizeof(float)), o_max = take((size_t)n_head * S * sizeof(float));
+    if (W && base) {
+        uint8_t* b = (uint8_t*)base;
+        W->part = (double*)(b + o_part); W->psum = (double*)(b + o_psum); W->scores = (float*)(b + o_sc); W->smax = (float*)(b + o_max);
+    }
+    return off;
+}
+// geometry the split kernels cover; whether a launch USES them is the caller's choice per step (use_pdl bit 2), because the
+// crossover is a matter of the sequence's current length (~2 000 positions on Llama-3-8B), not of the cache's allocated size
+static bool split_geometry(int n_head, int n_kv, int head_dim, int n_ctx) {
+    const char* e = getenv("GGB_ATTN_SPLIT");         /* 0: never */
+    if (e && *e && atoi(e) == 0) return false;
+    return head_dim == 128 && n_head % n_kv == 0 && (n_head / n_kv) % 4 == 0 && n_ctx > ATTN_SPLIT_MIN_CTX;
+}
+extern "C" size_t ggb_attn_decode_ws_bytes_ctx(int n_head, int n_kv, int head_dim, int n_ctx) {
+    if (n_head <= 0 || n_kv <= 0 || n_head % n_kv || n_ctx <= 0) return 16;
+    if (!split_geometry(n_head, n_kv, head_dim, n_ctx)) return 16;
+    return split_ws_layout(n_head, head_dim, n_ctx, nullptr, nullptr);
+}
+static int launch_attn_split(const float* q, const uint16_t* kc, const uint16_t* vc, const int32_t* pos_dev, int n_head, int n_kv, int n_ctx,
+                             void* ws, float* out, int use_pdl, cudaStream_t st) {
+    constexpr int HD = 128, GQ = 4, AU = 2;          /* measured: 2 positions per lane group in flight, 2 CTAs per SM (AU 1/4/8, 1/3/4 per SM slower) */
+    SplitWs W;
+    split_ws_layout(n_head, HD, n_ctx, &W, ws);
+    const int S = split_count(n_head), n_ctx_pad = (n_ctx + 63) & ~63;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = st; cfg.attrs = at; cfg.numAttrs = (use_pdl & 1) ? 1 : 0;
+    cfg.gridDim = dim3(S, n_head / GQ); cfg.blockDim = dim3(ATTN_SPLIT_NW * 32);
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_split_scores_kernel<HD, GQ, AU>, q, kc, pos_dev, n_head, n_kv, W, n_ctx_pad, S));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_split_values_kernel<HD, GQ, AU>, vc, pos_dev, n_head, n_kv, W, n_ctx_pad, S));
+    cfg.gridDim = dim3(n_head); cfg.blockDim = dim3(HD);
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, attn_split_merge_kernel<HD>, W, S, out, (use_pdl & 2) ? 1 : 0));
+    return GGB_OK;
+}
+
 extern "C" size_t ggb_attn_decode_ws_bytes(int n_head, int head_dim) {
     (void)n_head; (void)head_dim;
     return 16; /* the cluster kernel needs no global workspace; kept in the ABI for split-KV variants */
@@ -496,11 +759,14 @@ static int launch_attn(const float* q, const uint16_t* kc, const uint16_t* vc, c
 
 extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uint16_t* vcache, const int32_t* pos_dev,
                                int n_head, int n_kv, int head_dim, int n_ctx, void* ws, float* out, int use_pdl, void* stream) {
-    (void)ws;
     if (!q || !kcache || !vcache || !pos_dev || !out) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: null pointer");
     if (n_head <= 0 || n_kv <= 0 || n_head % n_kv) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_head=%d must be a multiple of n_kv=%d", n_head, n_kv);
     if (n_ctx <= 0) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: n_ctx must be positive");
     cudaStream_t st = (cudaStream_t)stream;
+    if ((use_pdl & 4) && split_geometry(n_head, n_kv, head_dim, n_ctx)) {   /* the caller says the sequence is long: three launches over the whole GPU */
+        if (!ws || ((uintptr_t)ws & 255)) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: the long-sequence path needs the 256-byte aligned workspace of ggb_attn_decode_ws_bytes_ctx()");
+        return launch_attn_split(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, ws, out, use_pdl, st);
+    }
     static const int cl1 = []() { const char* v = getenv("GGB_ATTN_CL"); return v && *v ? atoi(v) : 0; }();
     if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);

@@ -28,6 +28,7 @@ from . import parallel
 
 SM_SMEM = 227 * 1024            # shared memory an SM can hand out to CTAs (B200)
 HALF_SM_SMEM = SM_SMEM // 2 + 512
+LONG_SEQ = 2560                 # positions from which the decode attention runs as launches over the whole GPU (measured crossover ~2 600 on Llama-3-8B)
 
 QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q5_K, G.GGML_Q6_K, G.GGML_Q8_0)
 
@@ -170,7 +171,9 @@ class Slot:
         self.h, self.logits = f32(self.ffl), f32(self.vl)
         self.y64 = torch.zeros(hp.d, dtype=torch.float64, device=dev)       # row-split partial sums (tensor parallel)
         self.key = torch.zeros(1, dtype=torch.int64, device=dev)            # sharded arg-max key
-        self.attn_ws = torch.zeros(max(16, self.lib.ggb_attn_decode_ws_bytes(hp.n_head, hp.head_dim)), dtype=torch.uint8, device=dev)
+        self.attn_ws = torch.zeros(max(256, self.lib.ggb_attn_decode_ws_bytes_ctx(self.nh, self.nkv, hp.head_dim, eng.n_ctx)), dtype=torch.uint8, device=dev)
+        self.split_ok = self.attn_ws.numel() > 256     # the long-sequence attention path exists for this geometry and context
+        self._long = 0
         self._tokpos = i32(2)      # token id and position side by side: the host sets both with ONE 8-byte copy
         self.tok_dev, self.pos_dev, self.step_dev = self._tokpos[0:1], self._tokpos[1:2], i32(1)
         self.out_tokens = i32(self.max_new)
@@ -271,7 +274,7 @@ class Slot:
             cabi.check(lib.ggb_gemv(C.byref(qkv), s), "gemv qkv")
             cabi.check(lib.ggb_attn_decode(self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
                                            self.pos_dev.data_ptr(), self.nh, self.nkv, hp.head_dim, self.n_ctx,
-                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i], s), "attn_decode")
+                                           self.attn_ws.data_ptr(), self.attn.data_ptr(), self._attn_pdl[i] | self._long, s), "attn_decode")
             cabi.check(lib.ggb_gemv(C.byref(o), s), "gemv o")
             if tp:
                 self._allreduce_residual(s)
@@ -296,9 +299,13 @@ class Slot:
                                        self.out_tokens.data_ptr(), self.max_new, e.emb_type,
                                        e.emb_canon.data_ptr(), self.hp.d, self.x.data_ptr(), s), "argmax_next")
 
-    def _run(self, kind: str):
-        """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head)."""
+    def _run(self, kind: str, pos: int = 0):
+        """kind: 'prompt' (embed + layers), 'prompt_last' (embed + layers + head), 'decode' (layers + head).
+        pos: the position of the token this step processes -- from LONG_SEQ positions on the attention runs as launches over
+        the whole GPU (csrc/attn.cu, use_pdl bit 2), a separately captured graph per kind."""
         torch = self.torch
+        self._long = 4 if (self.split_ok and pos >= LONG_SEQ) else 0
+        key = (kind, self._long)
 
         def body(s):
             if kind != "decode":
@@ -310,12 +317,12 @@ class Slot:
         if not self.eng.use_graph:
             body(self.stream.cuda_stream)
             return
-        g = self._graphs.get(kind)
+        g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.stream):
                 body(torch.cuda.current_stream().cuda_stream)
-            self._graphs[kind] = g
+            self._graphs[key] = g
         g.replay()
 
     # ------------------------------------------------------------------ sequence API
@@ -379,7 +386,7 @@ class Slot:
         with self.torch.cuda.stream(self.stream):
             for i in range(first, len(tokens)):
                 self._set_tok_pos(int(tokens[i]), start + i)
-                self._run("prompt_last" if i == len(tokens) - 1 else "prompt")
+                self._run("prompt_last" if i == len(tokens) - 1 else "prompt", start + i)
         self.n_past = start + len(tokens)
         self.chain_valid = True
 
@@ -390,8 +397,8 @@ class Slot:
         if not self.chain_valid:
             raise RuntimeError("this slot last advanced inside a batch: feed() its newest token before decode()")
         with self.torch.cuda.stream(self.stream):
-            for _ in range(n_steps):
-                self._run("decode")
+            for j in range(n_steps):
+                self._run("decode", self.n_past + j)
         self.n_past += n_steps
 
     def feed(self, tok: int):
@@ -405,7 +412,7 @@ class Slot:
             raise ValueError(f"prompt of 1 tokens does not fit the context ({self.n_ctx})")
         with self.torch.cuda.stream(self.stream):
             self._set_tok_pos(int(tok), self.n_past)
-            self._run("prompt_last")
+            self._run("prompt_last", self.n_past)
         self.n_past += 1
         self.chain_valid = True
 

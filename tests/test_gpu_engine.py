@@ -454,6 +454,31 @@ def test_chunked_long_prompt_prefill_matches_single_chunk(oracle, model_dir):
     eng.close()
 
 
+def test_decode_across_the_long_sequence_boundary_is_bit_exact(oracle, model_dir):
+    """from model.LONG_SEQ positions on a slot's steps replay a second graph whose attention runs as launches over the whole GPU
+    (csrc/attn.cu: position slices x groups of four query heads): the tokens and logits across the switch are the oracle's"""
+    from ggufb200 import model as M
+    path = _model(model_dir, "gqa128", "Q4_K_M")
+    rng = np.random.default_rng(5)
+    n_prompt, n_new = M.LONG_SEQ - 8, 16
+    prompt = [1] + [int(t) for t in rng.integers(300, 2000, n_prompt - 1)]
+    eng = M.Engine(path, n_ctx=M.LONG_SEQ + 256)
+    eng.warmup()
+    assert eng.slots[0].split_ok
+    eng.gemm_prefill_min = 10 ** 9                 # exact path for the prompt
+    eng.reset()
+    eng.prefill(prompt)
+    eng.decode(n_new - 1)
+    got = eng.tokens(n_new)
+    logits = eng.last_logits().copy()
+    assert {k[1] for k in eng.slots[0]._graphs} == {0, 4}      # both graphs were used
+    m = oracle.OracleLlama(path, n_ctx=M.LONG_SEQ + 256, mode="canon")
+    want, wl = m.greedy(prompt, n_new, return_logits=True)
+    assert got == want
+    assert np.array_equal(_bits(logits), _bits(wl[-1]))
+    eng.close()
+
+
 def test_prefix_reuse_equals_cold_prefill(oracle, model_dir):
     """the scheduler's prompt cache: reset() keeps the K/V, prefill(suffix, start_pos=n) continues behind a prefix that
     an earlier sequence left in the slot -- bit-identical to processing the whole prompt"""

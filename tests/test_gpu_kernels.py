@@ -376,6 +376,36 @@ def test_attn_decode_matches_oracle(oracle, hd, n_head, n_kv, pos):
     assert np.abs(out.cpu().numpy() - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6)
 
 
+@pytest.mark.parametrize("n_head,n_kv", [(32, 8), (8, 1)])
+@pytest.mark.parametrize("pos,n_ctx", [(0, 6000), (5, 6000), (4999, 6000), (5999, 6000), (300, 2304), (2303, 2304)])
+def test_attn_decode_long_context_split_matches_oracle(oracle, n_head, n_kv, pos, n_ctx):
+    """use_pdl bit 2 (the caller says the sequence is long): the two softmax passes as launches over position slices x groups of
+    four query heads with the exchange through the workspace -- bit-identical with the oracle's canon attention at any position"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    hd = 128
+    rng = np.random.default_rng(n_head + pos)
+    q = rng.standard_normal(n_head * hd).astype(np.float32)
+    kc = (rng.standard_normal((n_ctx, n_kv * hd)) * 0.5).astype(np.float16)
+    vc = rng.standard_normal((n_ctx, n_kv * hd)).astype(np.float16)
+    canon = oracle.attn_decode(q, kc.view(np.uint16), vc.view(np.uint16), n_head, n_kv, hd, pos + 1, mode="canon")
+    qd, kd, vd = U.to_dev(q), U.to_dev(kc.view(np.int16)), U.to_dev(vc.view(np.int16))
+    nws = L.ggb_attn_decode_ws_bytes_ctx(n_head, n_kv, hd, n_ctx)
+    assert nws > 4 * n_head * n_ctx                      # the split path's workspace, not the 16-byte stub
+    ws = torch.zeros(nws, dtype=torch.uint8, device=U.DEV)
+    out = torch.zeros(n_head * hd, dtype=torch.float32, device=U.DEV)
+    posd = torch.tensor([pos], dtype=torch.int32, device=U.DEV)
+    for use_pdl in (4, 5, 0):              # split path without / with PDL, and the cluster kernel on the same inputs
+        out.zero_()
+        cabi.check(L.ggb_attn_decode(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), posd.data_ptr(), n_head, n_kv, hd, n_ctx,
+                                     ws.data_ptr(), out.data_ptr(), use_pdl, U.stream_ptr()))
+        U.sync()
+        assert np.array_equal(_bits(out.cpu().numpy()), _bits(canon)), f"use_pdl={use_pdl}"
+    assert L.ggb_attn_decode_ws_bytes_ctx(n_head, n_kv, hd, 1024) == 16 and L.ggb_attn_decode_ws_bytes_ctx(6, 2, hd, n_ctx) == 16
+
+
 def test_rms_norm_swiglu_argmax_embed(oracle):
     import torch
     import gpu_util as U
