@@ -35,13 +35,14 @@ _NP = {T_U8: np.uint8, T_I8: np.int8, T_U16: np.uint16, T_I16: np.int16, T_U32: 
 
 # ggml tensor types this engine understands: id -> (name, block elements, block bytes)
 GGML_F32, GGML_F16, GGML_Q8_0, GGML_Q4_K, GGML_Q5_K, GGML_Q6_K, GGML_BF16 = 0, 1, 8, 12, 13, 14, 30
+GGML_Q4_0, GGML_Q5_0 = 2, 6       # legacy 32-element blocks: carried as Q8_0 after an exact load-time conversion (model.py)
 GGML_TYPES = {
     GGML_F32: ("F32", 1, 4), GGML_F16: ("F16", 1, 2), GGML_BF16: ("BF16", 1, 2),
     GGML_Q8_0: ("Q8_0", 32, 34), GGML_Q4_K: ("Q4_K", 256, 144), GGML_Q5_K: ("Q5_K", 256, 176),
-    GGML_Q6_K: ("Q6_K", 256, 210),
+    GGML_Q6_K: ("Q6_K", 256, 210), GGML_Q4_0: ("Q4_0", 32, 18), GGML_Q5_0: ("Q5_0", 32, 22),
 }
 # every id gguf defines, so that unsupported tensors are named in the error instead of "type 10"
-_ALL_TYPE_NAMES = {2: "Q4_0", 3: "Q4_1", 6: "Q5_0", 7: "Q5_1", 9: "Q8_1", 10: "Q2_K", 11: "Q3_K", 15: "Q8_K",
+_ALL_TYPE_NAMES = {3: "Q4_1", 7: "Q5_1", 9: "Q8_1", 10: "Q2_K", 11: "Q3_K", 15: "Q8_K",
                    16: "IQ2_XXS", 17: "IQ2_XS", 18: "IQ3_XXS", 19: "IQ1_S", 20: "IQ4_NL", 21: "IQ3_S", 22: "IQ2_S",
                    23: "IQ4_XS", 24: "I8", 25: "I16", 26: "I32", 27: "I64", 28: "F64", 29: "IQ1_M", 34: "TQ1_0",
                    35: "TQ2_0", 39: "MXFP4"}

@@ -31,6 +31,29 @@ HALF_SM_SMEM = SM_SMEM // 2 + 512
 LONG_SEQ = 2560                 # positions from which the decode attention runs as launches over the whole GPU (measured crossover ~2 600 on Llama-3-8B)
 
 QUANT_TYPES = (G.GGML_Q4_K, G.GGML_Q5_K, G.GGML_Q6_K, G.GGML_Q8_0)
+LEGACY_TYPES = (G.GGML_Q4_0, G.GGML_Q5_0)
+
+
+def legacy_to_q8_0(raw: np.ndarray, ggml_type: int) -> np.ndarray:
+    """Q4_0 / Q5_0 blocks (32 weights: f16 d, 4- / 5-bit codes, value d * (q - 8) / d * (q - 16)) as Q8_0 blocks with the SAME
+    scale and the int8 codes q - 8 / q - 16.  Exact: the dequantised weights are identical, and ggml pairs both formats with
+    Q8_0 activations and computes sum_i * d_w * d_a per block exactly as for Q8_0 weights (ggml_vec_dot_q4_0_q8_0 /
+    q5_0_q8_0 [UPSTREAM-MEM: ggml-cpu/quants.c]) -- so the Q8_0 kernels give the very terms of the legacy dot.  Costs 34
+    instead of 18 / 22 bytes per block in HBM; these formats are the rare case."""
+    bb = 18 if ggml_type == G.GGML_Q4_0 else 22
+    b = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1, bb)
+    out = np.empty((b.shape[0], 34), dtype=np.uint8)
+    out[:, 0:2] = b[:, 0:2]
+    qs = b[:, bb - 16:]
+    lo, hi = (qs & 0x0F).astype(np.int16), (qs >> 4).astype(np.int16)       # elements 0..15 and 16..31
+    if ggml_type == G.GGML_Q4_0:
+        codes = np.concatenate([lo, hi], axis=1) - 8
+    else:
+        qh = b[:, 2:6].copy().view(np.uint32).reshape(-1, 1)
+        bits = ((qh >> np.arange(32, dtype=np.uint32)) & 1).astype(np.int16)  # bit j = fifth bit of element j
+        codes = (np.concatenate([lo, hi], axis=1) | (bits << 4)) - 16
+    out[:, 2:] = codes.astype(np.int8).view(np.uint8)
+    return out.reshape(-1)
 
 
 @dataclass
@@ -558,12 +581,24 @@ class Engine:
     def _load_matrix(self, name: str, shard_as: str | None = None) -> Weight:
         torch = self.torch
         ti = self.file.tensors[name]
-        if ti.ggml_type not in QUANT_TYPES:
-            raise G.GGUFError(f"{name}: tensor type {ti.type_name} is not supported by the GEMV path (supported: Q4_K, Q5_K, Q6_K, Q8_0)")
+        if ti.ggml_type not in QUANT_TYPES + LEGACY_TYPES:
+            raise G.GGUFError(f"{name}: tensor type {ti.type_name} is not supported by the GEMV path (supported: Q4_K, Q5_K, Q6_K, Q8_0, Q4_0, Q5_0)")
         k, rows = ti.ne[0], ti.ne[1]
         if k % 256:
             raise G.GGUFError(f"{name}: K={k} is not a multiple of 256")
         sh = parallel.shard_of(shard_as or name, self.hp, self.tp_size, self.tp_rank)
+        if ti.ggml_type in LEGACY_TYPES:      # exact conversion to Q8_0 blocks on the host, then the Q8_0 path
+            raw = np.asarray(self.file.data(name))
+            if sh.kind != parallel.FULL:
+                raw, rows, k = parallel.slice_canonical(raw, ti.ggml_type, k, rows, sh)
+            q8 = legacy_to_q8_0(raw, ti.ggml_type)
+            canon = torch.from_numpy(q8).to(self.dev)
+            stride = self.lib.ggb_repacked_row_stride(G.GGML_Q8_0, k)
+            dst = torch.zeros(rows * stride + 16, dtype=torch.uint8, device=self.dev)
+            cabi.check(self.lib.ggb_repack(G.GGML_Q8_0, canon.data_ptr(), dst.data_ptr(), rows, k, self._sptr()), f"repack {name}")
+            torch.cuda.current_stream().synchronize()
+            self.weight_bytes += q8.size
+            return Weight(dst, G.GGML_Q8_0, rows, k)
         st = getattr(self, "_stager", None)
         if sh.kind == parallel.FULL and st is not None:
             # row chunks: file -> pinned ring (reader threads) -> device staging (async copy) -> tile-SoA destination (ggb_repack
@@ -624,7 +659,11 @@ class Engine:
         hp, f = self.hp, self.file
         emb = f.tensors["token_embd.weight"]
         self.emb_type = emb.ggml_type
-        self.emb_canon = self._upload("token_embd.weight")  # canonical layout: get_rows reads one row
+        if emb.ggml_type in LEGACY_TYPES:     # same exact conversion: get_rows of the Q8_0 image gives d * (q - 8) / d * (q - 16)
+            self.emb_type = G.GGML_Q8_0
+            self.emb_canon = self.torch.from_numpy(legacy_to_q8_0(np.asarray(f.data("token_embd.weight")), emb.ggml_type)).to(self.dev)
+        else:
+            self.emb_canon = self._upload("token_embd.weight")  # canonical layout: get_rows reads one row
         self.layers = []
         for i in range(hp.n_layer):
             p = f"blk.{i}."

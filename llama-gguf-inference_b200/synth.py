@@ -20,7 +20,7 @@ import numpy as np
 from . import gguf_reader as G
 
 Q4_K_M, Q8_0, Q6_K, Q5_K_M = "Q4_K_M", "Q8_0", "Q6_K", "Q5_K_M"
-_FILE_TYPE_ID = {Q4_K_M: 15, Q8_0: 7, Q6_K: 18, Q5_K_M: 17}  # general.file_type, gguf/constants.py:4107-4125
+_FILE_TYPE_ID = {Q4_K_M: 15, Q8_0: 7, Q6_K: 18, Q5_K_M: 17, "Q4_0": 2, "Q5_0": 8}  # general.file_type, gguf/constants.py:4107-4125
 
 
 @dataclass(frozen=True)
@@ -89,6 +89,9 @@ def tensor_plan(cfg: LlamaConfig, ftype: str):
         base = big = out = G.GGML_Q8_0
     elif ftype == Q6_K:
         base = big = out = G.GGML_Q6_K
+    elif ftype in ("Q4_0", "Q5_0"):     # llama.cpp's legacy mixes: every matrix in the 32-element format, the lm-head in Q6_K
+        base = big = G.GGML_Q4_0 if ftype == "Q4_0" else G.GGML_Q5_0
+        out = G.GGML_Q6_K
     else:
         raise ValueError(f"unknown synthetic file type {ftype}")
     qd, kvd = cfg.n_head * cfg.head_dim, cfg.n_kv * cfg.head_dim
@@ -142,6 +145,9 @@ def _unit_std(tt: int) -> float:
     if tt not in _UNIT_STD:
         if tt == G.GGML_Q8_0:      # d*q, q uniform int8
             v = np.mean(np.arange(-128, 128, dtype=np.float64) ** 2)
+        elif tt in (G.GGML_Q4_0, G.GGML_Q5_0):   # d*(q - 8) / d*(q - 16), q uniform
+            h = 8 if tt == G.GGML_Q4_0 else 16
+            v = np.mean(np.arange(-h, h, dtype=np.float64) ** 2)
         elif tt in (G.GGML_Q4_K, G.GGML_Q5_K):  # d*(sc*q - c*m), dmin = c*d with c = E[q] so the mean is zero
             qmax = 15 if tt == G.GGML_Q4_K else 31
             q = np.arange(0, qmax + 1, dtype=np.float64)
@@ -167,7 +173,7 @@ def random_blocks(tt: int, n_blocks: int, std: float, rng: np.random.Generator) 
     n64 = (n_blocks * bb + 7) // 8
     raw = rng.bit_generator.random_raw(n64).view(np.uint8)[: n_blocks * bb].reshape(n_blocks, bb)
     d = (std / _unit_std(tt)) * rng.uniform(0.5, 1.5, size=n_blocks)
-    if tt == G.GGML_Q8_0:
+    if tt in (G.GGML_Q8_0, G.GGML_Q4_0, G.GGML_Q5_0):
         raw[:, 0:2] = _f16_bytes(d)
     elif tt in (G.GGML_Q4_K, G.GGML_Q5_K):
         raw[:, 0:2] = _f16_bytes(d)
@@ -189,7 +195,7 @@ def random_tensor(name: str, ne: tuple, tt: int, std, rng: np.random.Generator) 
         # the best of the thousands of random word logits, so greedy text is one leading-space word per token
         blocks_per_row = ne[0] // G.GGML_TYPES[tt][1]
         sp = raw[: N_SPECIAL * blocks_per_row]
-        if tt == G.GGML_Q8_0:
+        if tt in (G.GGML_Q8_0, G.GGML_Q4_0, G.GGML_Q5_0):
             sp[:, 0:2] = 0
         elif tt in (G.GGML_Q4_K, G.GGML_Q5_K):
             sp[:, 0:4] = 0

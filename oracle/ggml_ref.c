@@ -36,11 +36,15 @@
 #define QK8_0 32
 
 /* ggml tensor type ids, gguf/constants.py:4059-4093 */
-enum { GREF_F32 = 0, GREF_F16 = 1, GREF_Q8_0 = 8, GREF_Q4_K = 12, GREF_Q5_K = 13, GREF_Q6_K = 14 };
+enum { GREF_F32 = 0, GREF_F16 = 1, GREF_Q4_0 = 2, GREF_Q5_0 = 6, GREF_Q8_0 = 8, GREF_Q4_K = 12, GREF_Q5_K = 13, GREF_Q6_K = 14 };
 
 /* ---- block layouts (gguf/quants.py sizes: Q8_0 (32,34)  Q4_K (256,144)  Q5_K (256,176)  Q6_K (256,210)) ---- */
 #pragma pack(push, 1)
 typedef struct { uint16_t d; int8_t qs[QK8_0]; } blk_q8_0;                                     /* 34 */
+#pragma pack(push, 1)
+typedef struct { uint16_t d; uint8_t qs[16]; } blk_q4_0;                                        /* 18: 32 x 4 bit, value d * (q - 8) */
+typedef struct { uint16_t d; uint8_t qh[4]; uint8_t qs[16]; } blk_q5_0;                         /* 22: 32 x 5 bit, value d * (q - 16) */
+#pragma pack(pop)
 typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qs[QK_K / 2]; } blk_q4_K; /* 144 */
 typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qh[QK_K / 8]; uint8_t qs[QK_K / 2]; } blk_q5_K; /* 176 */
 typedef struct { uint8_t ql[QK_K / 2]; uint8_t qh[QK_K / 4]; int8_t scales[QK_K / 16]; uint16_t d; } blk_q6_K; /* 210 */
@@ -108,11 +112,11 @@ void gref_fp32_to_fp16_row(const float *x, uint16_t *y, int64_t n) { for (int64_
 
 /* ------------------------------------------------------------------ sizes */
 int64_t gref_block_elems(int type) {
-    switch (type) { case GREF_F32: case GREF_F16: return 1; case GREF_Q8_0: return QK8_0; default: return QK_K; }
+    switch (type) { case GREF_F32: case GREF_F16: return 1; case GREF_Q8_0: case GREF_Q4_0: case GREF_Q5_0: return QK8_0; default: return QK_K; }
 }
 int64_t gref_block_bytes(int type) {
     switch (type) {
-        case GREF_F32: return 4; case GREF_F16: return 2; case GREF_Q8_0: return 34;
+        case GREF_F32: return 4; case GREF_F16: return 2; case GREF_Q8_0: return 34; case GREF_Q4_0: return 18; case GREF_Q5_0: return 22;
         case GREF_Q4_K: return 144; case GREF_Q5_K: return 176; case GREF_Q6_K: return 210; default: return -1;
     }
 }
@@ -127,6 +131,30 @@ static inline void k4_scale_min(int j, const uint8_t *s, uint8_t *sc, uint8_t *m
     else {
         *sc = (uint8_t)((s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4));
         *mn = (uint8_t)((s[j + 4] >> 4) | ((s[j] >> 6) << 4));
+    }
+}
+
+/* legacy 32-element blocks [UPSTREAM: ggml-quants.c dequantize_row_q4_0 / q5_0; gguf/quants.py Q4_0 / Q5_0]: element j of the
+ * block is the low nibble of qs[j], element j + 16 the high nibble; Q5_0 adds bit j (resp. j + 16) of the 32-bit qh as bit 4 */
+static inline int q4_0_code(const blk_q4_0 *b, int j) { return (j < 16 ? (b->qs[j] & 0x0F) : (b->qs[j - 16] >> 4)) - 8; }
+static inline int q5_0_code(const blk_q5_0 *b, int j) {
+    uint32_t qh;
+    memcpy(&qh, b->qh, 4);
+    const int lo = j < 16 ? (b->qs[j] & 0x0F) : (b->qs[j - 16] >> 4);
+    return (lo | (int)(((qh >> j) & 1u) << 4)) - 16;
+}
+void gref_dequantize_row_q4_0(const void *vx, float *y, int64_t k) {
+    const blk_q4_0 *x = (const blk_q4_0 *)vx;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        const float d = gref_fp16_to_fp32(x[b].d);
+        for (int j = 0; j < QK8_0; j++) y[b * QK8_0 + j] = q4_0_code(&x[b], j) * d;
+    }
+}
+void gref_dequantize_row_q5_0(const void *vx, float *y, int64_t k) {
+    const blk_q5_0 *x = (const blk_q5_0 *)vx;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        const float d = gref_fp16_to_fp32(x[b].d);
+        for (int j = 0; j < QK8_0; j++) y[b * QK8_0 + j] = q5_0_code(&x[b], j) * d;
     }
 }
 
@@ -206,6 +234,8 @@ int gref_dequantize_row(int type, const void *x, float *y, int64_t k) {
         case GREF_F32: memcpy(y, x, (size_t)k * 4); return 0;
         case GREF_F16: gref_fp16_to_fp32_row((const uint16_t *)x, y, k); return 0;
         case GREF_Q8_0: gref_dequantize_row_q8_0(x, y, k); return 0;
+        case GREF_Q4_0: gref_dequantize_row_q4_0(x, y, k); return 0;
+        case GREF_Q5_0: gref_dequantize_row_q5_0(x, y, k); return 0;
         case GREF_Q4_K: gref_dequantize_row_q4_K(x, y, k); return 0;
         case GREF_Q5_K: gref_dequantize_row_q5_K(x, y, k); return 0;
         case GREF_Q6_K: gref_dequantize_row_q6_K(x, y, k); return 0;
@@ -359,16 +389,41 @@ float gref_vec_dot_q8_0_q8_0(int64_t k, const void *vw, const void *va) {
     return sumf;
 }
 
+/* [UPSTREAM: ggml-cpu/quants.c ggml_vec_dot_q4_0_q8_0 / q5_0_q8_0, generic form]: integer dot of the 32 codes (offset removed)
+ * with the Q8_0 activation block, one f32 term per block */
+float gref_vec_dot_q4_0_q8_0(int64_t k, const void *vw, const void *va) {
+    const blk_q4_0 *w = (const blk_q4_0 *)vw;
+    const blk_q8_0 *a = (const blk_q8_0 *)va;
+    float sumf = 0.f;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        int32_t s = 0;
+        for (int j = 0; j < QK8_0; j++) s += q4_0_code(&w[b], j) * a[b].qs[j];
+        sumf += s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d));
+    }
+    return sumf;
+}
+float gref_vec_dot_q5_0_q8_0(int64_t k, const void *vw, const void *va) {
+    const blk_q5_0 *w = (const blk_q5_0 *)vw;
+    const blk_q8_0 *a = (const blk_q8_0 *)va;
+    float sumf = 0.f;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        int32_t s = 0;
+        for (int j = 0; j < QK8_0; j++) s += q5_0_code(&w[b], j) * a[b].qs[j];
+        sumf += s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d));
+    }
+    return sumf;
+}
+
 /* bytes of the quantised-activation row that pairs with weight type `type` */
 int64_t gref_act_row_bytes(int type, int64_t k) {
-    if (type == GREF_Q8_0) return k / QK8_0 * (int64_t)sizeof(blk_q8_0);
+    if (type == GREF_Q8_0 || type == GREF_Q4_0 || type == GREF_Q5_0) return k / QK8_0 * (int64_t)sizeof(blk_q8_0);
     if (type == GREF_Q4_K || type == GREF_Q5_K || type == GREF_Q6_K) return k / QK_K * (int64_t)sizeof(blk_q8_K);
     return k * 4;
 }
 
 int gref_quantize_act(int wtype, const float *x, void *out, int64_t k) {
     switch (wtype) {
-        case GREF_Q8_0: gref_quantize_row_q8_0(x, out, k); return 0;
+        case GREF_Q8_0: case GREF_Q4_0: case GREF_Q5_0: gref_quantize_row_q8_0(x, out, k); return 0;
         case GREF_Q4_K: case GREF_Q5_K: case GREF_Q6_K: gref_quantize_row_q8_K(x, out, k); return 0;
         case GREF_F32: case GREF_F16: memcpy(out, x, (size_t)k * 4); return 0;
         default: return -1;
@@ -408,6 +463,8 @@ int gref_matmul(int type, const void *W, int64_t rows, int64_t k, const float *X
                 case GREF_Q5_K: v = gref_vec_dot_q5_K_q8_K(k, wr, ar); break;
                 case GREF_Q6_K: v = gref_vec_dot_q6_K_q8_K(k, wr, ar); break;
                 case GREF_Q8_0: v = gref_vec_dot_q8_0_q8_0(k, wr, ar); break;
+                case GREF_Q4_0: v = gref_vec_dot_q4_0_q8_0(k, wr, ar); break;
+                case GREF_Q5_0: v = gref_vec_dot_q5_0_q8_0(k, wr, ar); break;
                 default: v = dot_f32_w(type, k, wr, ar); break;
             }
             Y[j * rows + r] = v;
@@ -643,6 +700,29 @@ static double vec_dot_q8_0_q8_0_f64(int64_t k, const void *vw, const void *va) {
     return acc;
 }
 
+static double vec_dot_q4_0_q8_0_f64(int64_t k, const void *vw, const void *va) {
+    const blk_q4_0 *w = (const blk_q4_0 *)vw;
+    const blk_q8_0 *a = (const blk_q8_0 *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        int32_t s = 0;
+        for (int j = 0; j < QK8_0; j++) s += q4_0_code(&w[b], j) * a[b].qs[j];
+        acc += (double)((float)s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d)));
+    }
+    return acc;
+}
+static double vec_dot_q5_0_q8_0_f64(int64_t k, const void *vw, const void *va) {
+    const blk_q5_0 *w = (const blk_q5_0 *)vw;
+    const blk_q8_0 *a = (const blk_q8_0 *)va;
+    double acc = 0.0;
+    for (int64_t b = 0; b < k / QK8_0; b++) {
+        int32_t s = 0;
+        for (int j = 0; j < QK8_0; j++) s += q5_0_code(&w[b], j) * a[b].qs[j];
+        acc += (double)((float)s * (gref_fp16_to_fp32(w[b].d) * gref_fp16_to_fp32(a[b].d)));
+    }
+    return acc;
+}
+
 float gref_vec_dot_q4_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q4_K_q8_K_f64(k, w, a); }
 float gref_vec_dot_q5_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q5_K_q8_K_f64(k, w, a); }
 float gref_vec_dot_q6_K_q8_K_canon(int64_t k, const void *w, const void *a) { return (float)vec_dot_q6_K_q8_K_f64(k, w, a); }
@@ -666,6 +746,8 @@ int gref_matvec_f64(int type, const void *W, int64_t rows, int64_t k, const floa
             case GREF_Q4_K: Y[r] = vec_dot_q4_K_q8_K_f64(k, wr, act); break;
             case GREF_Q5_K: Y[r] = vec_dot_q5_K_q8_K_f64(k, wr, act); break;
             case GREF_Q6_K: Y[r] = vec_dot_q6_K_q8_K_f64(k, wr, act); break;
+            case GREF_Q4_0: Y[r] = vec_dot_q4_0_q8_0_f64(k, wr, act); break;
+            case GREF_Q5_0: Y[r] = vec_dot_q5_0_q8_0_f64(k, wr, act); break;
             default: Y[r] = vec_dot_q8_0_q8_0_f64(k, wr, act); break;
         }
     }
@@ -695,6 +777,8 @@ int gref_matmul_mode(int type, const void *W, int64_t rows, int64_t k, const flo
                 case GREF_Q4_K: v = gref_vec_dot_q4_K_q8_K_canon(k, wr, ar); break;
                 case GREF_Q5_K: v = gref_vec_dot_q5_K_q8_K_canon(k, wr, ar); break;
                 case GREF_Q6_K: v = gref_vec_dot_q6_K_q8_K_canon(k, wr, ar); break;
+                case GREF_Q4_0: v = (float)vec_dot_q4_0_q8_0_f64(k, wr, ar); break;
+                case GREF_Q5_0: v = (float)vec_dot_q5_0_q8_0_f64(k, wr, ar); break;
                 default: v = gref_vec_dot_q8_0_q8_0_canon(k, wr, ar); break;
             }
             Y[j * rows + r] = v;

@@ -6,7 +6,7 @@ module; the product package never does.
 What it restates: the arithmetic of the reference's backend run with NGL=0 (`/app/llama-server`,
 /root/reference/scripts/start.sh:473-480,516; CPU image /root/reference/Dockerfile.cpu:11,84-89), i.e.
 ggml's CPU path for a llama-architecture model: Q8_K / Q8_0 activation quantisation, integer vec_dot
-against Q4_K / Q5_K / Q6_K / Q8_0 weights, RMSNorm, NORM-mode RoPE, f16 KV cache, f32 softmax, SwiGLU,
+against Q4_K / Q5_K / Q6_K / Q8_0 / Q4_0 / Q5_0 weights, RMSNorm, NORM-mode RoPE, f16 KV cache, f32 softmax, SwiGLU,
 greedy argmax.  The C kernels live in ggml_ref.c (see its header for the parity-pinning status:
 dequantisation and Q8_0 quantisation are pinned bit-exact against gguf-py; the rest is PARITY UNPINNED
 because neither the reference nor this machine holds upstream's sources or any numeric test vector).
@@ -25,8 +25,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libggml_ref.so")
 
-F32, F16, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 8, 12, 13, 14
-BLOCK = {F32: (1, 4), F16: (1, 2), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210)}
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 6, 8, 12, 13, 14
+BLOCK = {F32: (1, 4), F16: (1, 2), Q4_0: (32, 18), Q5_0: (32, 22), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210)}
 
 
 def build(force: bool = False) -> str:

@@ -60,7 +60,7 @@ def rand_blocks(qtype: int, n_blocks: int, rng: np.random.Generator, wild: bool 
     def setf16(col, vals):
         raw[:, col:col + 2] = vals.astype(np.float16).view(np.uint8).reshape(-1, 2)
 
-    if qtype == O.Q8_0:
+    if qtype in (O.Q8_0, O.Q4_0, O.Q5_0):
         setf16(0, rng.normal(0, 0.01, n_blocks))
     elif qtype in (O.Q4_K, O.Q5_K):
         setf16(0, np.abs(rng.normal(0, 0.01, n_blocks)))

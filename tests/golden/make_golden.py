@@ -2,7 +2,7 @@
 
 Sources of truth:
   * gguf-py 0.19.0 (`gguf.quants`, the python package published from the llama.cpp tree; present in this image)
-    for dequantisation of Q8_0/Q4_K/Q5_K/Q6_K blocks and for Q8_0 quantisation -- these PIN the oracle;
+    for dequantisation of Q8_0/Q4_K/Q5_K/Q6_K/Q4_0/Q5_0 blocks and for Q8_0 quantisation -- these PIN the oracle;
   * the oracle itself for end-to-end regression vectors (greedy tokens + logits of the seeded `tiny`
     synthetic model) -- these pin nothing upstream, they only detect drift of the oracle and of the
     synthetic-model generator.
@@ -27,7 +27,10 @@ def main():
     from oracle import oracle as O
 
     rng = np.random.default_rng(20261018)
-    for name, qt, gt in (("q8_0", O.Q8_0, T.Q8_0), ("q4_k", O.Q4_K, T.Q4_K), ("q5_k", O.Q5_K, T.Q5_K), ("q6_k", O.Q6_K, T.Q6_K)):
+    for name, qt, gt in (("q8_0", O.Q8_0, T.Q8_0), ("q4_k", O.Q4_K, T.Q4_K), ("q5_k", O.Q5_K, T.Q5_K), ("q6_k", O.Q6_K, T.Q6_K),
+                         ("q4_0", O.Q4_0, T.Q4_0), ("q5_0", O.Q5_0, T.Q5_0)):
+        if os.path.exists(os.path.join(HERE, f"dequant_{name}.npz")):
+            continue          # committed vectors stay as they are; new formats are added
         tame = rand_blocks(qt, 48, rng)
         wild = rand_blocks(qt, 16, rng, wild=True)
         raw = np.concatenate([tame, wild])

@@ -60,7 +60,7 @@ def _gpu_run(path, n_new, n_ctx=256, **kw):
 
 
 @pytest.mark.parametrize("preset,ftype", [("tiny", "Q4_K_M"), ("tiny", "Q8_0"), ("tiny", "Q6_K"), ("small", "Q4_K_M"), ("small", "Q5_K_M"), ("medium", "Q5_K_M"),
-                                          ("small", "Q8_0"), ("medium", "Q4_K_M"), ("medium", "Q6_K")])
+                                          ("small", "Q8_0"), ("medium", "Q4_K_M"), ("medium", "Q6_K"), ("tiny", "Q4_0"), ("small", "Q5_0")])
 def test_greedy_64_tokens_identical_and_logits_bit_exact_vs_canon_oracle(oracle, model_dir, preset, ftype):
     path = _model(model_dir, preset, ftype)
     ref = oracle.OracleLlama(path, n_ctx=256, mode="canon")

@@ -9,7 +9,7 @@ import pytest
 from conftest import rand_blocks
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = {"q8_0": 8, "q4_k": 12, "q5_k": 13, "q6_k": 14}
+NAMES = {"q8_0": 8, "q4_k": 12, "q5_k": 13, "q6_k": 14, "q4_0": 2, "q5_0": 6}
 
 
 def _bits(a):
@@ -31,7 +31,7 @@ def test_dequant_matches_gguf_py_golden(oracle, name):
 def test_dequant_matches_gguf_py_live(oracle, name):
     gguf = pytest.importorskip("gguf")
     T = gguf.GGMLQuantizationType
-    gt = {"q8_0": T.Q8_0, "q4_k": T.Q4_K, "q5_k": T.Q5_K, "q6_k": T.Q6_K}[name]
+    gt = {"q8_0": T.Q8_0, "q4_k": T.Q4_K, "q5_k": T.Q5_K, "q6_k": T.Q6_K, "q4_0": T.Q4_0, "q5_0": T.Q5_0}[name]
     qt = NAMES[name]
     rng = np.random.default_rng(5)
     raw = rand_blocks(qt, 512, rng)
@@ -79,7 +79,7 @@ def test_quantize_q8_K_properties(oracle):
     assert qs.max() <= 127 and qs.min() >= -127
 
 
-@pytest.mark.parametrize("name", ["q4_k", "q5_k", "q6_k", "q8_0"])
+@pytest.mark.parametrize("name", ["q4_k", "q5_k", "q6_k", "q8_0", "q4_0", "q5_0"])
 def test_vec_dot_equals_exact_integer_formula_and_bounds_float(oracle, name):
     """vec_dot == (dequantised weights) . (dequantised activations) up to f32 summation, and is within the
     activation-quantisation error of the f32 matvec."""
@@ -91,7 +91,7 @@ def test_vec_dot_equals_exact_integer_formula_and_bounds_float(oracle, name):
     x = rng.standard_normal(k).astype(np.float32)
     y = oracle.matmul(qt, raw, rows, k, x)
     W = oracle.dequantize(raw, qt, rows * k).reshape(rows, k).astype(np.float64)
-    if qt == 8:
+    if qt in (8, 2, 6):
         p = oracle.quantize_q8_0(x).reshape(-1, 34)
         xq = (p[:, 2:].copy().view(np.int8).astype(np.float64) * p[:, :2].copy().view(np.float16).astype(np.float64)).reshape(-1)
     else:
@@ -100,6 +100,27 @@ def test_vec_dot_equals_exact_integer_formula_and_bounds_float(oracle, name):
     exact = W @ xq
     assert np.abs(y - exact).max() <= 1e-5 * np.abs(exact).max()
     assert np.abs(y - W @ x.astype(np.float64)).max() <= 2e-2 * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q5_0"])
+def test_legacy_blocks_as_q8_0_blocks_is_exact(oracle, name):
+    """The product carries Q4_0 / Q5_0 matrices as Q8_0 blocks (same f16 scale, codes q - 8 / q - 16; model.legacy_to_q8_0):
+    the dequantised weights and the integer-dot matvec of the converted blocks equal the legacy format's bit for bit, in both
+    the ggml-order and the order-independent mode, wild scales (NaN / Inf / subnormal) included."""
+    from ggufb200.model import legacy_to_q8_0
+    qt = NAMES[name]
+    rng = np.random.default_rng(100 + qt)
+    rows, k = 24, 1024
+    for wild in (False, True):
+        raw = rand_blocks(qt, rows * k // 32, rng, wild=wild)
+        conv = legacy_to_q8_0(raw.reshape(-1), qt)
+        assert conv.size == rows * k // 32 * 34
+        assert np.array_equal(_bits(oracle.dequantize(raw, qt, rows * k)), _bits(oracle.dequantize(conv, 8, rows * k)))
+        if wild:
+            continue
+        x = rng.standard_normal((2, k)).astype(np.float32)
+        for mode in ("ggml", "canon"):
+            assert np.array_equal(_bits(oracle.matmul(qt, raw, rows, k, x, mode=mode)), _bits(oracle.matmul(8, conv, rows, k, x, mode=mode)))
 
 
 def test_matmul_batch_equals_columns_and_is_linear_in_scale(oracle):
