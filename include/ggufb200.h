@@ -245,8 +245,18 @@ typedef struct ggb_gemv_batch_args {
     const float* residual;     /* [nb][rows_0] (GGB_EPI_RESIDUAL) */
     int32_t use_pdl;
     int32_t grid;              /* 0 = one CTA per SM */
+    int32_t act_tiled;         /* 1: act is the tiled layout of ggb_act_prep_tiled (see ggb_gemv_batch_prefers_tiled) */
+    int32_t reserved;
 } ggb_gemv_batch_args;
 int ggb_gemv_batch(const ggb_gemv_batch_args* args, void* stream);
+/* Long vectors, more than 8 tokens: sixteen whole-vector images (ffn_down, K = 14336) do not fit shared memory and the launch
+ * would stream the weights in two 8-token passes.  The tiled layout [K-tile of 2048][token][2448 B] lets the kernel walk its
+ * rows tile by tile and stream the image slices: ONE pass, same integers, same f32 terms, same f64 sums -- bit-identical.
+ * ggb_gemv_batch_prefers_tiled(args) = 1 when a launch of that shape (act ignored) should be fed this way: then fill act with
+ * ggb_act_prep_tiled (K-quant activations, ggb_act_tiled_bytes(k, nb) bytes) and set act_tiled = 1. */
+int ggb_gemv_batch_prefers_tiled(const ggb_gemv_batch_args* args);
+int64_t ggb_act_tiled_bytes(int64_t k, int nb);
+int ggb_act_prep_tiled(const float* x, const float* norm_w, float eps, int64_t k, int nb, void* act, int use_pdl, void* stream);
 
 /* Per-token cache addressing for the batch: token b belongs to slot slot_dev[b] at position pos_dev[b]; the caches
  * of all slots live in one allocation, slot s starting slot_stride elements after slot s-1

@@ -40,7 +40,7 @@ class BatchDecoder:
             self.y64 = torch.zeros((NB, hp.d), dtype=torch.float64, device=dev)
             self.keys = torch.zeros(NB, dtype=torch.int64, device=dev)
         kmax = max(hp.d, self.ffl, qd)
-        self.act = torch.zeros(NB * self.lib.ggb_act_image_bytes(kmax), dtype=torch.uint8, device=dev)
+        self.act = torch.zeros(max(NB * self.lib.ggb_act_image_bytes(kmax), self.lib.ggb_act_tiled_bytes(kmax, NB)), dtype=torch.uint8, device=dev)
         self.meta = torch.zeros((3, NB), dtype=torch.int32, device=dev)          # token ids | positions | slots
         self.meta_host = torch.zeros((3, NB), dtype=torch.int32).pin_memory()
         self.next_tok = torch.zeros(NB, dtype=torch.int32, device=dev)
@@ -59,21 +59,29 @@ class BatchDecoder:
         act = self.act.data_ptr()
         tp = self.tp > 1
 
-        def prep(x, norm, k, w):
+        def prep(x, norm, k, w, tiled=0):
+            if tiled:
+                return cabi.check(lib.ggb_act_prep_tiled(x.data_ptr(), norm.data_ptr() if norm is not None else 0, hp.eps, k, nb, act, pdl, s),
+                                  "act_prep_tiled")
             cabi.check(lib.ggb_act_prep(x.data_ptr(), norm.data_ptr() if norm is not None else 0, hp.eps, k, nb,
                                         int(w.type == cabi.Q8_0), act, pdl, s), "act_prep")
 
-        def gemv(segs, k, epi, residual=0):
-            a = cabi.make_gemv_batch_args(segs, k, act, nb, epilogue=epi, residual=residual, use_pdl=pdl)
+        def gemv(segs, k, epi, residual=0, tiled=0):
+            a = cabi.make_gemv_batch_args(segs, k, act, nb, epilogue=epi, residual=residual, use_pdl=pdl, act_tiled=tiled)
             cabi.check(lib.ggb_gemv_batch(C.byref(a), s), "gemv_batch")
 
-        def row_split(w, k):
-            """x += W h for a projection whose K is split across the ranks"""
-            if not tp:
-                return gemv([(w.ptr, w.type, w.rows, xp)], k, cabi.EPI_RESIDUAL, residual=xp)
-            gemv([(w.ptr, w.type, w.rows, self.y64.data_ptr())], k, cabi.EPI_STORE_F64)
-            e.dist.all_reduce(self.y64[:nb], op=e.dist.ReduceOp.SUM, group=e.pg)
-            cabi.check(lib.ggb_residual_add_f64(xp, self.y64.data_ptr(), nb * hp.d, 0, s), "residual_add_f64")
+        def row_split(x, w, k):
+            """x += W h for a projection whose K is split across the ranks.  More than 8 tokens of a long vector (ffn_down) go
+            through tiled activation images: one pass over the weights instead of two 8-token passes, same bits."""
+            epi = cabi.EPI_STORE_F64 if tp else cabi.EPI_RESIDUAL
+            y = self.y64.data_ptr() if tp else xp
+            probe = cabi.make_gemv_batch_args([(w.ptr, w.type, w.rows, y)], k, act, nb, epilogue=epi)
+            tiled = int(lib.ggb_gemv_batch_prefers_tiled(C.byref(probe)))
+            prep(x, None, k, w, tiled)
+            gemv([(w.ptr, w.type, w.rows, y)], k, epi, residual=0 if tp else xp, tiled=tiled)
+            if tp:
+                e.dist.all_reduce(self.y64[:nb], op=e.dist.ReduceOp.SUM, group=e.pg)
+                cabi.check(lib.ggb_residual_add_f64(xp, self.y64.data_ptr(), nb * hp.d, 0, s), "residual_add_f64")
 
         cabi.check(lib.ggb_embed_rows(e.emb_type, e.emb_canon.data_ptr(), hp.d, ids, nb, self.x.data_ptr(), s), "embed_rows")
         xp = self.x.data_ptr()
@@ -87,13 +95,11 @@ class BatchDecoder:
                                              self.nh, self.nkv, hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), kc, vc, s), "rope_kv_batch")
             cabi.check(lib.ggb_attn_decode_batch(self.q.data_ptr(), kc, vc, pos, slot, self.slot_stride, nb, self.nh, self.nkv,
                                                  hp.head_dim, e.n_ctx, self.att.data_ptr(), 0, s), "attn_decode_batch")
-            prep(self.att, None, qd, L["wo"])
-            row_split(L["wo"], qd)
+            row_split(self.att, L["wo"], qd)
             prep(self.x, L["ffn_norm"], hp.d, L["wg"])
             gemv([(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),
                   (L["wu"].ptr, L["wu"].type, L["wu"].rows, 0)], hp.d, cabi.EPI_SWIGLU)
-            prep(self.h, None, self.ffl, L["wd"])
-            row_split(L["wd"], self.ffl)
+            row_split(self.h, L["wd"], self.ffl)
         if not head:      # prompt tokens whose logits nobody reads: the pass only fills the KV cache
             return
         prep(self.x, e.out_norm, hp.d, e.w_out)

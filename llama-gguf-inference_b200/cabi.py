@@ -28,7 +28,7 @@ EXPORTS = [
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
     "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
-    "ggb_act_image_bytes", "ggb_act_prep", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows", "ggb_argmax_rows_key", "ggb_argmax_keys_unpack",
+    "ggb_act_image_bytes", "ggb_act_prep", "ggb_act_prep_tiled", "ggb_act_tiled_bytes", "ggb_gemv_batch_prefers_tiled", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows", "ggb_argmax_rows_key", "ggb_argmax_keys_unpack",
 ]
 
 
@@ -65,6 +65,7 @@ class GemvBatchArgs(C.Structure):
         ("epilogue", C.c_int32), ("nb", C.c_int32),
         ("act", C.c_void_p), ("residual", C.c_void_p),
         ("use_pdl", C.c_int32), ("grid", C.c_int32),
+        ("act_tiled", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -120,6 +121,9 @@ def lib() -> C.CDLL:
         "ggb_peer_reduce_residual": ([vp, vp, i32, i64, i64, i32, vp], i32),
         "ggb_act_image_bytes": ([i64], i64),
         "ggb_act_prep": ([vp, vp, f32, i64, i32, i32, vp, i32, vp], i32),
+        "ggb_act_prep_tiled": ([vp, vp, f32, i64, i32, vp, i32, vp], i32),
+        "ggb_act_tiled_bytes": ([i64, i32], i64),
+        "ggb_gemv_batch_prefers_tiled": ([C.POINTER(GemvBatchArgs)], i32),
         "ggb_gemv_batch": ([C.POINTER(GemvBatchArgs), vp], i32),
         "ggb_rope_kv_batch": ([vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp], i32),
         "ggb_attn_decode_batch": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, vp], i32),
@@ -176,13 +180,13 @@ def make_gemv_args(segs, k, x, *, prologue=PRO_PLAIN, epilogue=EPI_STORE, norm_w
     return a
 
 
-def make_gemv_batch_args(segs, k, act, nb, *, epilogue=EPI_STORE, residual=0, use_pdl=0, grid=0) -> GemvBatchArgs:
+def make_gemv_batch_args(segs, k, act, nb, *, epilogue=EPI_STORE, residual=0, use_pdl=0, grid=0, act_tiled=0) -> GemvBatchArgs:
     """segs: list of (w_ptr, type, rows, y_ptr); outputs are [nb][rows]."""
     a = GemvBatchArgs()
     a.n_seg, a.k = len(segs), k
     for i, (w, t, rows, y) in enumerate(segs):
         a.seg[i].w, a.seg[i].type, a.seg[i].rows, a.seg[i].y = w, t, rows, y
-    a.epilogue, a.nb, a.act, a.residual, a.use_pdl, a.grid = epilogue, nb, act, residual, use_pdl, grid
+    a.epilogue, a.nb, a.act, a.residual, a.use_pdl, a.grid, a.act_tiled = epilogue, nb, act, residual, use_pdl, grid, act_tiled
     return a
 
 

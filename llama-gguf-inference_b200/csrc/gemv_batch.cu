@@ -562,6 +562,12 @@ extern "C" int ggb_gemv_batch(const ggb_gemv_batch_args* a, void* stream) {
     // from 5 tokens up the integer dots of pure Q4_K / Q6_K launches go to the tensor cores (same arithmetic, half the
     // instructions); everything else stays on the dp4a kernel below
     static const int use_mma = env_int_b("GGB_BATCH_MMA", 1);
+    if (a->act_tiled) {   /* tiled activation images exist for the tensor-core kernel only */
+        if (mask != 1 && mask != 2 && mask != 3) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: tiled activation images need Q4_K / Q6_K segments");
+        const int rc = ggb_gemv_batch_mma(a, stream);
+        if (rc == 1) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: shape k=%d does not take tiled activation images", a->k);
+        return rc;
+    }
     if (use_mma && a->nb >= 5 && (mask == 1 || mask == 2 || mask == 3)) {
         const int rc = ggb_gemv_batch_mma(a, stream);
         if (rc != 1) return rc;

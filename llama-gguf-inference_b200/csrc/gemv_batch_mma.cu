@@ -18,9 +18,11 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include "actquant.cuh"
 #include "common.cuh"
 #include "layout.cuh"
 #include "gemv_common.cuh"
+#include "../../include/ggufb200.h"
 
 #define GBM_NW 8                      /* consumer warps */
 #define GBM_THREADS ((GBM_NW + 1) * 32)
@@ -59,6 +61,110 @@ __device__ __forceinline__ void mbar_arrive1(uint32_t bar) { asm volatile("mbarr
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GBM_NW * 32) : "memory"); }
 
 struct GbmCtx { int r0[GGB_MAX_SEG], cnt[GGB_MAX_SEG], ng[GGB_MAX_SEG], ngroups; };
+
+// One ring stage = K-tile t of a 16-row group: consumer warp `warp` applies super-block `warp` of the tile to every token.
+// The activation side is described by (act_s, imgp, bs_off, dsc_off, gsb0): whole-vector images (gsb0 = 8 t, offsets K and
+// K + K/8) or the K-tile slice of the tiled layout (gsb0 = 0, fixed offsets) -- the arithmetic is the same.
+template <int NT>
+__device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slotp, int nsb, int warp, int lane, uint32_t act_s, int imgp,
+                                              uint32_t bs_off, uint32_t dsc_off, int gsb0, double (&acc)[NT][4]) {
+    const int g = lane >> 2, t4 = lane & 3;
+    const uint32_t S = 64u * (uint32_t)nsb;                     /* bytes of a 16-byte-per-unit section */
+    if (warp < nsb) {
+        const int sb = warp;
+        const uint32_t rowA = stage + g * slotp, rowB = rowA + 8 * slotp;
+        const int gsb = gsb0 + sb;                              /* super-block index within the activation image */
+        const int chunk_sb = gsb * 16;                          /* first 16-element chunk of the super-block */
+        // block scales of my C-fragment tokens (2*t4, 2*t4+1 of every n-tile)
+        float dx[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            dx[nt][0] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4) * imgp + dsc_off + 4 * gsb));
+            dx[nt][1] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4 + 1) * imgp + dsc_off + 4 * gsb));
+        }
+        if (type == GGB_TYPE_Q4_K) {
+            const uint4 hA = lds128(rowA + 2 * S + 16 * sb), hB = lds128(rowB + 2 * S + 16 * sb);
+            const float dA = h2f((uint16_t)(hA.x & 0xFFFF)), mA = h2f((uint16_t)(hA.x >> 16));
+            const float dB = h2f((uint16_t)(hB.x & 0xFFFF)), mB = h2f((uint16_t)(hB.x >> 16));
+            const uint32_t hwA[4] = {hA.x, hA.y, hA.z, hA.w}, hwB[4] = {hB.x, hB.y, hB.z, hB.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int u = 4 * sb + j;
+                const uint32_t wA0 = lds32(rowA + 16 * u + 4 * t4), wA1 = lds32(rowA + S + 16 * u + 4 * t4);
+                const uint32_t wB0 = lds32(rowB + 16 * u + 4 * t4), wB1 = lds32(rowB + S + 16 * u + 4 * t4);
+                // field j (24 bits at header byte 4 + 3j): sc[2j] | sc[2j+1] << 6 | min[2j] << 12 | min[2j+1] << 18
+                const int bo = 4 + 3 * j;
+                const uint32_t fA = (uint32_t)((((uint64_t)hwA[bo >> 2] | ((uint64_t)hwA[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
+                const uint32_t fB = (uint32_t)((((uint64_t)hwB[bo >> 2] | ((uint64_t)hwB[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
+                const int chunk0 = chunk_sb + 4 * j;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    const uint32_t tb = act_s + (nt * 8 + g) * imgp + 4 * t4;      /* B fragment: token nt*8 + g */
+                    int clo[4] = {0, 0, 0, 0}, chi[4] = {0, 0, 0, 0};
+                    mma_u8s8_k32(clo, wA0 & 0x0F0F0F0Fu, wB0 & 0x0F0F0F0Fu, wA1 & 0x0F0F0F0Fu, wB1 & 0x0F0F0F0Fu,
+                                 lds32(tb + 16 * swz(chunk0)), lds32(tb + 16 * swz(chunk0 + 1)));
+                    mma_u8s8_k32(chi, (wA0 >> 4) & 0x0F0F0F0Fu, (wB0 >> 4) & 0x0F0F0F0Fu, (wA1 >> 4) & 0x0F0F0F0Fu, (wB1 >> 4) & 0x0F0F0F0Fu,
+                                 lds32(tb + 16 * swz(chunk0 + 2)), lds32(tb + 16 * swz(chunk0 + 3)));
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {                                     /* C-fragment tokens 2*t4 + q */
+                        const uint2 bs = lds64(act_s + (nt * 8 + 2 * t4 + q) * imgp + bs_off + 2 * chunk0);   /* four per-16 sums */
+                        const int blo = (int)(int16_t)(bs.x & 0xFFFF) + ((int)bs.x >> 16);
+                        const int bhi = (int)(int16_t)(bs.y & 0xFFFF) + ((int)bs.y >> 16);
+                        const float x = dx[nt][q];
+                        {
+                            const int isum = (int)(fA & 63) * clo[q] + (int)((fA >> 6) & 63) * chi[q];
+                            const int msum = (int)((fA >> 12) & 63) * blo + (int)((fA >> 18) & 63) * bhi;
+                            acc[nt][q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dA, x), (float)isum), __fmul_rn(__fmul_rn(mA, x), (float)msum));
+                        }
+                        {
+                            const int isum = (int)(fB & 63) * clo[2 + q] + (int)((fB >> 6) & 63) * chi[2 + q];
+                            const int msum = (int)((fB >> 12) & 63) * blo + (int)((fB >> 18) & 63) * bhi;
+                            acc[nt][2 + q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dB, x), (float)isum), __fmul_rn(__fmul_rn(mB, x), (float)msum));
+                        }
+                    }
+                }
+            }
+        } else {   /* Q6_K: unit (half n, column tt) = four 16-element groups r with their own int8 scale */
+            const uint4 scA = lds128(rowA + 3 * S + 16 * sb), scB = lds128(rowB + 3 * S + 16 * sb);
+            const float dA = h2f((uint16_t)lds16(rowA + 3 * S + 16 * nsb + 2 * sb)), dB = h2f((uint16_t)lds16(rowB + 3 * S + 16 * nsb + 2 * sb));
+            const uint32_t swA[4] = {scA.x, scA.y, scA.z, scA.w}, swB[4] = {scB.x, scB.y, scB.z, scB.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int n = j >> 1, tt = j & 1, u = 4 * sb + j;
+                const uint32_t laA = lds32(rowA + 16 * u + 4 * t4), lbA = lds32(rowA + S + 16 * u + 4 * t4), hqA = lds32(rowA + 2 * S + 16 * u + 4 * t4);
+                const uint32_t laB = lds32(rowB + 16 * u + 4 * t4), lbB = lds32(rowB + S + 16 * u + 4 * t4), hqB = lds32(rowB + 2 * S + 16 * u + 4 * t4);
+                const uint32_t cA[4] = {(laA & 0x0F0F0F0Fu) | ((hqA << 4) & 0x30303030u), (lbA & 0x0F0F0F0Fu) | ((hqA << 2) & 0x30303030u),
+                                        ((laA >> 4) & 0x0F0F0F0Fu) | (hqA & 0x30303030u), ((lbA >> 4) & 0x0F0F0F0Fu) | ((hqA >> 2) & 0x30303030u)};
+                const uint32_t cB[4] = {(laB & 0x0F0F0F0Fu) | ((hqB << 4) & 0x30303030u), (lbB & 0x0F0F0F0Fu) | ((hqB << 2) & 0x30303030u),
+                                        ((laB >> 4) & 0x0F0F0F0Fu) | (hqB & 0x30303030u), ((lbB >> 4) & 0x0F0F0F0Fu) | ((hqB >> 2) & 0x30303030u)};
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    const uint32_t tb = act_s + (nt * 8 + g) * imgp + 4 * t4;
+                    int isum[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const int chunk = chunk_sb + 8 * n + 2 * r + tt;
+                        int cc[4] = {0, 0, 0, 0};
+                        mma_u8s8_k16(cc, cA[r], cB[r], lds32(tb + 16 * swz(chunk)));
+                        const int si = 8 * n + 2 * r + tt;                           /* scale byte index */
+                        const int sA = (int)(int8_t)((swA[si >> 2] >> (8 * (si & 3))) & 0xFF), sB = (int)(int8_t)((swB[si >> 2] >> (8 * (si & 3))) & 0xFF);
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int b16 = 32 * (int)(int16_t)lds16(act_s + (nt * 8 + 2 * t4 + q) * imgp + bs_off + 2 * chunk);
+                            isum[q] += sA * (cc[q] - b16);
+                            isum[2 + q] += sB * (cc[2 + q] - b16);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        acc[nt][q] += (double)__fmul_rn(__fmul_rn(dA, dx[nt][q]), (float)isum[q]);
+                        acc[nt][2 + q] += (double)__fmul_rn(__fmul_rn(dB, dx[nt][q]), (float)isum[2 + q]);
+                    }
+                }
+            }
+        }
+    }
+}
 
 // NT = 8-token n-tiles per launch (1: <= 8 tokens, 2: <= 16)
 template <int NT>
@@ -154,102 +260,8 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
         for (int t = 0; t < T; t++, step++) {
             const int st = step % NS;
             const int nsb = (t == T - 1) ? nsb_last : GGB_TILE_SB;
-            const uint32_t S = 64u * (uint32_t)nsb;                     /* bytes of a 16-byte-per-unit section */
             mbar_wait(smem_u32(&s_full[st]), (step / NS) & 1);
-            if (warp < nsb) {
-                const int sb = warp;
-                const uint32_t rowA = ring + st * P.stage_bytes + g * P.slotp, rowB = rowA + 8 * P.slotp;
-                const int gsb = t * GGB_TILE_SB + sb;                   /* super-block index along K */
-                const int chunk_sb = gsb * 16;                          /* first 16-element chunk of the super-block */
-                // block scales of my C-fragment tokens (2*t4, 2*t4+1 of every n-tile)
-                float dx[NT][2];
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    dx[nt][0] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4) * P.imgp + dsc_off + 4 * gsb));
-                    dx[nt][1] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4 + 1) * P.imgp + dsc_off + 4 * gsb));
-                }
-                if (type == GGB_TYPE_Q4_K) {
-                    const uint4 hA = lds128(rowA + 2 * S + 16 * sb), hB = lds128(rowB + 2 * S + 16 * sb);
-                    const float dA = h2f((uint16_t)(hA.x & 0xFFFF)), mA = h2f((uint16_t)(hA.x >> 16));
-                    const float dB = h2f((uint16_t)(hB.x & 0xFFFF)), mB = h2f((uint16_t)(hB.x >> 16));
-                    const uint32_t hwA[4] = {hA.x, hA.y, hA.z, hA.w}, hwB[4] = {hB.x, hB.y, hB.z, hB.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int u = 4 * sb + j;
-                        const uint32_t wA0 = lds32(rowA + 16 * u + 4 * t4), wA1 = lds32(rowA + S + 16 * u + 4 * t4);
-                        const uint32_t wB0 = lds32(rowB + 16 * u + 4 * t4), wB1 = lds32(rowB + S + 16 * u + 4 * t4);
-                        // field j (24 bits at header byte 4 + 3j): sc[2j] | sc[2j+1] << 6 | min[2j] << 12 | min[2j+1] << 18
-                        const int bo = 4 + 3 * j;
-                        const uint32_t fA = (uint32_t)((((uint64_t)hwA[bo >> 2] | ((uint64_t)hwA[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
-                        const uint32_t fB = (uint32_t)((((uint64_t)hwB[bo >> 2] | ((uint64_t)hwB[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
-                        const int chunk0 = chunk_sb + 4 * j;
-#pragma unroll
-                        for (int nt = 0; nt < NT; nt++) {
-                            const uint32_t tb = act_s + (nt * 8 + g) * P.imgp + 4 * t4;      /* B fragment: token nt*8 + g */
-                            int clo[4] = {0, 0, 0, 0}, chi[4] = {0, 0, 0, 0};
-                            mma_u8s8_k32(clo, wA0 & 0x0F0F0F0Fu, wB0 & 0x0F0F0F0Fu, wA1 & 0x0F0F0F0Fu, wB1 & 0x0F0F0F0Fu,
-                                         lds32(tb + 16 * swz(chunk0)), lds32(tb + 16 * swz(chunk0 + 1)));
-                            mma_u8s8_k32(chi, (wA0 >> 4) & 0x0F0F0F0Fu, (wB0 >> 4) & 0x0F0F0F0Fu, (wA1 >> 4) & 0x0F0F0F0Fu, (wB1 >> 4) & 0x0F0F0F0Fu,
-                                         lds32(tb + 16 * swz(chunk0 + 2)), lds32(tb + 16 * swz(chunk0 + 3)));
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {                                     /* C-fragment tokens 2*t4 + q */
-                                const uint2 bs = lds64(act_s + (nt * 8 + 2 * t4 + q) * P.imgp + bs_off + 2 * chunk0);   /* four per-16 sums */
-                                const int blo = (int)(int16_t)(bs.x & 0xFFFF) + ((int)bs.x >> 16);
-                                const int bhi = (int)(int16_t)(bs.y & 0xFFFF) + ((int)bs.y >> 16);
-                                const float x = dx[nt][q];
-                                {
-                                    const int isum = (int)(fA & 63) * clo[q] + (int)((fA >> 6) & 63) * chi[q];
-                                    const int msum = (int)((fA >> 12) & 63) * blo + (int)((fA >> 18) & 63) * bhi;
-                                    acc[nt][q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dA, x), (float)isum), __fmul_rn(__fmul_rn(mA, x), (float)msum));
-                                }
-                                {
-                                    const int isum = (int)(fB & 63) * clo[2 + q] + (int)((fB >> 6) & 63) * chi[2 + q];
-                                    const int msum = (int)((fB >> 12) & 63) * blo + (int)((fB >> 18) & 63) * bhi;
-                                    acc[nt][2 + q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dB, x), (float)isum), __fmul_rn(__fmul_rn(mB, x), (float)msum));
-                                }
-                            }
-                        }
-                    }
-                } else {   /* Q6_K: unit (half n, column tt) = four 16-element groups r with their own int8 scale */
-                    const uint4 scA = lds128(rowA + 3 * S + 16 * sb), scB = lds128(rowB + 3 * S + 16 * sb);
-                    const float dA = h2f((uint16_t)lds16(rowA + 3 * S + 16 * nsb + 2 * sb)), dB = h2f((uint16_t)lds16(rowB + 3 * S + 16 * nsb + 2 * sb));
-                    const uint32_t swA[4] = {scA.x, scA.y, scA.z, scA.w}, swB[4] = {scB.x, scB.y, scB.z, scB.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int n = j >> 1, tt = j & 1, u = 4 * sb + j;
-                        const uint32_t laA = lds32(rowA + 16 * u + 4 * t4), lbA = lds32(rowA + S + 16 * u + 4 * t4), hqA = lds32(rowA + 2 * S + 16 * u + 4 * t4);
-                        const uint32_t laB = lds32(rowB + 16 * u + 4 * t4), lbB = lds32(rowB + S + 16 * u + 4 * t4), hqB = lds32(rowB + 2 * S + 16 * u + 4 * t4);
-                        const uint32_t cA[4] = {(laA & 0x0F0F0F0Fu) | ((hqA << 4) & 0x30303030u), (lbA & 0x0F0F0F0Fu) | ((hqA << 2) & 0x30303030u),
-                                                ((laA >> 4) & 0x0F0F0F0Fu) | (hqA & 0x30303030u), ((lbA >> 4) & 0x0F0F0F0Fu) | ((hqA >> 2) & 0x30303030u)};
-                        const uint32_t cB[4] = {(laB & 0x0F0F0F0Fu) | ((hqB << 4) & 0x30303030u), (lbB & 0x0F0F0F0Fu) | ((hqB << 2) & 0x30303030u),
-                                                ((laB >> 4) & 0x0F0F0F0Fu) | (hqB & 0x30303030u), ((lbB >> 4) & 0x0F0F0F0Fu) | ((hqB >> 2) & 0x30303030u)};
-#pragma unroll
-                        for (int nt = 0; nt < NT; nt++) {
-                            const uint32_t tb = act_s + (nt * 8 + g) * P.imgp + 4 * t4;
-                            int isum[4] = {0, 0, 0, 0};
-#pragma unroll
-                            for (int r = 0; r < 4; r++) {
-                                const int chunk = chunk_sb + 8 * n + 2 * r + tt;
-                                int cc[4] = {0, 0, 0, 0};
-                                mma_u8s8_k16(cc, cA[r], cB[r], lds32(tb + 16 * swz(chunk)));
-                                const int si = 8 * n + 2 * r + tt;                           /* scale byte index */
-                                const int sA = (int)(int8_t)((swA[si >> 2] >> (8 * (si & 3))) & 0xFF), sB = (int)(int8_t)((swB[si >> 2] >> (8 * (si & 3))) & 0xFF);
-#pragma unroll
-                                for (int q = 0; q < 2; q++) {
-                                    const int b16 = 32 * (int)(int16_t)lds16(act_s + (nt * 8 + 2 * t4 + q) * P.imgp + bs_off + 2 * chunk);
-                                    isum[q] += sA * (cc[q] - b16);
-                                    isum[2 + q] += sB * (cc[2 + q] - b16);
-                                }
-                            }
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                acc[nt][q] += (double)__fmul_rn(__fmul_rn(dA, dx[nt][q]), (float)isum[q]);
-                                acc[nt][2 + q] += (double)__fmul_rn(__fmul_rn(dB, dx[nt][q]), (float)isum[2 + q]);
-                            }
-                        }
-                    }
-                }
-            }
+            gbm_tile_step<NT>(type, ring + st * P.stage_bytes, P.slotp, nsb, warp, lane, act_s, P.imgp, bs_off, dsc_off, t * GGB_TILE_SB, acc);
             __syncwarp();
             if (lane == 0) mbar_arrive1(smem_u32(&s_empty[st]));
         }
@@ -290,6 +302,203 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
     }
 }
 
+// ------------------------------------------------------------------ tiled form: activation images streamed K-tile by K-tile
+// Sixteen images of a long vector (ffn_down: K = 14336 -> 16 x 17.9 KB) do not fit shared memory next to the ring, and two
+// 8-token passes stream the weights twice.  Here the CTA walks TILE-major -- for every K-tile, all of its (<= 4) row groups --
+// so that only the K-tile slice of the images is needed at a time: ggb_act_prep_tiled leaves the images as
+// [tile][token][GGB_ACT_TILE_STRIDE] (codes 2048 | per-16 sums 256 | block scales 32, padded so that the token stride is
+// 4 words mod 32 banks), one bulk copy per tile into one of two slice buffers.  The partial sums of a (group, warp, row,
+// token) live in shared memory between tiles (f64, each lane adds into its own words); what is summed is unchanged, so the
+// result is bit-identical with the one- and two-pass forms.
+#define GBM_TILED_MAX_GROUPS 4
+
+template <int NT>
+__global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_tiled_kernel(const __grid_constant__ GbmK P) {
+    constexpr int NBT = 8 * NT;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_full[GBM_MAX_STAGES], s_empty[GBM_MAX_STAGES], s_afull[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = P.k, T = P.T, NS = P.nstage;
+    const int G = gridDim.x, c = blockIdx.x;
+
+    // one segment: this CTA's rows (even-aligned), cut into groups of 16
+    const int q_ = P.rq[0], r_ = P.rr[0];
+    const int ra = (c * q_ + min(c, r_)) & ~1;
+    int rb_ = (c + 1) * q_ + min(c + 1, r_);
+    if (c + 1 != G) rb_ &= ~1;
+    const int cnt = rb_ - ra, ngroups = (cnt + GBM_ROWS - 1) / GBM_ROWS;
+    const int type = P.seg[0].type;
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), GBM_NW); }
+        mbar_init(smem_u32(&s_afull[0]), 1); mbar_init(smem_u32(&s_afull[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t ring = smem_u32(smem);
+    const int nsb_last = ggb_tile_nsb(K, T - 1);
+
+    if (warp == GBM_NW) {
+        // ===== producer: (tile, group) order; weights do not depend on the previous launch
+        if (lane == 0) {
+            const int sbb = ggb_sb_bytes(type);
+            const int tile = sbb * GGB_TILE_SB, last = (nsb_last * sbb + 15) & ~15;
+            int step = 0;
+            for (int t = 0; t < T; t++) {
+                const uint32_t bytes = (t == T - 1) ? (uint32_t)last : (uint32_t)tile;
+                for (int p = 0; p < ngroups; p++, step++) {
+                    const int nv = min(GBM_ROWS, cnt - GBM_ROWS * p);
+                    const uint8_t* src = P.seg[0].w + (int64_t)(ra + GBM_ROWS * p) * P.seg[0].stride + (int64_t)t * tile;
+                    const int st = step % NS;
+                    if (step >= NS) mbar_wait(smem_u32(&s_empty[st]), ((step / NS) - 1) & 1);
+                    const uint32_t bar = smem_u32(&s_full[st]);
+                    mbar_expect_tx(bar, (uint32_t)nv * bytes);
+                    for (int r = 0; r < nv; r++) bulk_g2s(ring + st * P.stage_bytes + r * P.slotp, src + (int64_t)r * P.seg[0].stride, bytes, bar);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers
+    uint8_t* abuf = smem + P.act_off;                               /* two slice buffers of NBT x imgp bytes */
+    double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [group][GBM_NW][16][NBT] */
+    const int abytes = NBT * P.imgp;
+    // rows of absent tokens: zero slices in both buffers (dx = 0 -> every term 0; the bulk copies never touch them)
+    for (int bsel = 0; bsel < 2; bsel++)
+        for (int i = tid * 16; i < (NBT - P.nb) * P.imgp; i += GBM_NW * 32 * 16)
+            *reinterpret_cast<uint4*>(abuf + bsel * abytes + P.nb * P.imgp + i) = make_uint4(0, 0, 0, 0);
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t abuf_s = smem_u32(abuf);
+    const uint32_t slice = (uint32_t)(P.nb * P.imgp);              /* bytes of one tile's slice in global memory: [nb][imgp] */
+    auto fetch_slice = [&](int t) {
+        const uint32_t bar = smem_u32(&s_afull[t & 1]);
+        mbar_expect_tx(bar, slice);
+        bulk_g2s(abuf_s + (t & 1) * abytes, P.act + (int64_t)t * slice, slice, bar);
+    };
+    if (tid == 0) {
+        fetch_slice(0);
+        if (T > 1) fetch_slice(1);
+    }
+
+    const int g = lane >> 2, t4 = lane & 3;
+    int step = 0;
+    for (int t = 0; t < T; t++) {
+        const int nsb = (t == T - 1) ? nsb_last : GGB_TILE_SB;
+        const uint32_t act_s = abuf_s + (t & 1) * abytes;
+        mbar_wait(smem_u32(&s_afull[t & 1]), (t >> 1) & 1);
+        for (int p = 0; p < ngroups; p++, step++) {
+            const int st = step % NS;
+            double acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0; }
+            mbar_wait(smem_u32(&s_full[st]), (step / NS) & 1);
+            gbm_tile_step<NT>(type, ring + st * P.stage_bytes, P.slotp, nsb, warp, lane, act_s, P.imgp, GGB_ACT_TILE_BS_OFF, GGB_ACT_TILE_DSC_OFF, 0, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(smem_u32(&s_empty[st]));
+            double* rb = red + (size_t)p * GBM_NW * GBM_ROWS * NBT;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    double* a0 = rb + (warp * GBM_ROWS + g) * NBT + nt * 8 + 2 * t4 + q;
+                    double* a1 = rb + (warp * GBM_ROWS + g + 8) * NBT + nt * 8 + 2 * t4 + q;
+                    if (t == 0) { *a0 = acc[nt][q]; *a1 = acc[nt][2 + q]; }
+                    else { *a0 += acc[nt][q]; *a1 += acc[nt][2 + q]; }
+                }
+        }
+        consumer_sync();                       /* every consumer is done with slice buffer t & 1 (and, after the last tile, with red) */
+        if (tid == 0 && t + 2 < T) fetch_slice(t + 2);
+    }
+    // ---- the 8 K-slices of every (row, token) meet here
+    for (int p = 0; p < ngroups; p++) {
+        const double* rb = red + (size_t)p * GBM_NW * GBM_ROWS * NBT;
+        const int nv = min(GBM_ROWS, cnt - GBM_ROWS * p), row0 = ra + GBM_ROWS * p;
+        for (int i = tid; i < GBM_ROWS * NBT; i += GBM_NW * 32) {
+            const int rl = i / NBT, b = i - rl * NBT;
+            if (rl < nv && b < P.nb) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < GBM_NW; w++) v += rb[(w * GBM_ROWS + rl) * NBT + b];
+                const int64_t o = (int64_t)b * P.seg[0].rows + row0 + rl;
+                if (P.epi == GGB_EPI_STORE) P.seg[0].y[o] = (float)v;
+                else if (P.epi == GGB_EPI_RESIDUAL) P.seg[0].y[o] = __fadd_rn(P.residual[o], (float)v);
+                else reinterpret_cast<double*>(P.seg[0].y)[o] = v;
+            }
+        }
+    }
+}
+
+// ggb_act_prep for the tiled form: token `blockIdx.x`, 256-blocks spread over gridDim.y CTAs; with RMSNorm every CTA first
+// takes the whole row's sum of squares (16-57 KB from L2: cheaper than a second launch).  Same quantiser, same codes.
+__global__ void __launch_bounds__(256) act_prep_tiled_kernel(const float* __restrict__ x, const float* __restrict__ norm_w, float eps, int K, int nb,
+                                                             uint8_t* __restrict__ out) {
+    __shared__ double red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* xr = x + (int64_t)blockIdx.x * K;
+    pdl_launch_dependents();
+    pdl_wait();
+    float scale = 1.f;
+    if (norm_w) {
+        double s = 0.0;
+        for (int i = tid; i < K; i += 256) { const float v = xr[i]; s += (double)__fmul_rn(v, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tot += red[i];
+        const float mean = (float)(tot / (double)K);
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(mean + eps));
+    }
+    const int nblk = K / 256;
+    for (int b = blockIdx.y * 8 + warp; b < nblk; b += gridDim.y * 8) {
+        const int e = b * 256 + lane * 8;
+        const float4 xa = *reinterpret_cast<const float4*>(xr + e), xb = *reinterpret_cast<const float4*>(xr + e + 4);
+        float v[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        if (norm_w) {
+            const float4 ga = *reinterpret_cast<const float4*>(norm_w + e), gb = *reinterpret_cast<const float4*>(norm_w + e + 4);
+            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(__fmul_rn(v[i], scale), gg[i]);
+        }
+        const int t = b / GGB_TILE_SB, sbr = b - t * GGB_TILE_SB;
+        uint8_t* base = out + ((int64_t)t * nb + blockIdx.x) * GGB_ACT_TILE_STRIDE;
+        const int chunk = (sbr * 256 + lane * 8) >> 4;                         /* chunk within the tile */
+        float dd;
+        const Q8Codes cq = warp_quantize_q8_K(v, lane, dd);
+        *reinterpret_cast<uint2*>(base + 16 * swz(chunk) + 8 * (lane & 1)) = cq.q;
+        const int s16 = cq.sum8 + __shfl_xor_sync(0xffffffffu, cq.sum8, 1);
+        if (!(lane & 1)) *reinterpret_cast<int16_t*>(base + GGB_ACT_TILE_BS_OFF + 2 * chunk) = (int16_t)s16;
+        if (lane == 0) *reinterpret_cast<float*>(base + GGB_ACT_TILE_DSC_OFF + 4 * sbr) = dd;
+    }
+}
+
+extern "C" int64_t ggb_act_tiled_bytes(int64_t k, int nb) {
+    return (k > 0 && k % 256 == 0 && nb >= 0) ? (int64_t)ggb_tiles_per_row((int)k) * nb * GGB_ACT_TILE_STRIDE : -1;
+}
+
+extern "C" int ggb_act_prep_tiled(const float* x, const float* norm_w, float eps, int64_t k, int nb, void* act, int use_pdl, void* stream) {
+    if (k <= 0 || (k % 256) || nb < 0) GGB_FAIL(GGB_ERR_ARG, "ggb_act_prep_tiled: k=%lld must be a positive multiple of 256, nb >= 0", (long long)k);
+    if (nb == 0) return GGB_OK;
+    if (!x || !act || ((uintptr_t)x & 15) || ((uintptr_t)act & 15) || (norm_w && ((uintptr_t)norm_w & 15)))
+        GGB_FAIL(GGB_ERR_ARG, "ggb_act_prep_tiled: null or misaligned pointer");
+    const int nblk = (int)(k / 256);
+    int splits = (nblk + 7) / 8;
+    if (norm_w && splits > 4) splits = 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nb, splits); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, act_prep_tiled_kernel, x, norm_w, eps, (int)k, nb, (uint8_t*)act));
+    return GGB_OK;
+}
+
 // ------------------------------------------------------------------ host side (called from ggb_gemv_batch)
 template <int NT>
 static int gbm_launch_nt(const GbmK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
@@ -306,6 +515,89 @@ static int gbm_launch_nt(const GbmK& P, int grid, size_t smem, int use_pdl, cuda
     cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
     GGB_CUDA(cudaLaunchKernelEx(&cfg, ggb_dq_gemv_batch_mma_kernel<NT>, P));
     return GGB_OK;
+}
+
+template <int NT>
+static int gbm_launch_tiled_nt(const GbmK& P, int grid, size_t smem, int use_pdl, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        GGB_CUDA(cudaFuncSetAttribute(ggb_dq_gemv_batch_mma_tiled_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBM_MAX_SMEM));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GBM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, ggb_dq_gemv_batch_mma_tiled_kernel<NT>, P));
+    return GGB_OK;
+}
+
+// whole-vector images: ring depth that fits next to `nbt` images (0 = does not fit)
+static int gbm_plan_whole(const ggb_gemv_batch_args* a, int nbt, int stage_bytes, int imgp, int64_t max_local) {
+    const size_t img = (size_t)nbt * imgp, red = (size_t)2 * GBM_NW * GBM_ROWS * nbt * 8;
+    const size_t rowv = a->epilogue == GGB_EPI_SWIGLU ? (size_t)max_local * nbt * 8 : 0;
+    const size_t fixed = ((img + 127) & ~(size_t)127) + red + rowv + 256;
+    int nstage = fixed < GBM_MAX_SMEM ? (int)((GBM_MAX_SMEM - fixed) / stage_bytes) : 0;
+    return nstage > GBM_MAX_STAGES ? GBM_MAX_STAGES : nstage;
+}
+
+// tiled images: one segment, no SWIGLU, at most GBM_TILED_MAX_GROUPS row groups per CTA; returns the ring depth (0 = no)
+static int gbm_plan_tiled(const ggb_gemv_batch_args* a, int nbt, int stage_bytes, int grid, int* groups_out) {
+    if (a->n_seg != 1 || a->epilogue == GGB_EPI_SWIGLU || a->k < GGB_TILE_ELEMS) return 0;
+    const int groups = (a->seg[0].rows / grid + 2 + GBM_ROWS - 1) / GBM_ROWS;
+    if (groups > GBM_TILED_MAX_GROUPS) return 0;
+    const size_t fixed = (size_t)2 * nbt * GGB_ACT_TILE_STRIDE + (size_t)groups * GBM_NW * GBM_ROWS * nbt * 8 + 256;
+    int nstage = fixed < GBM_MAX_SMEM ? (int)((GBM_MAX_SMEM - fixed) / stage_bytes) : 0;
+    if (groups_out) *groups_out = groups;
+    return nstage > GBM_MAX_STAGES ? GBM_MAX_STAGES : nstage;
+}
+
+static bool gbm_types_ok(const ggb_gemv_batch_args* a, int* max_tile) {
+    *max_tile = 0;
+    for (int s = 0; s < a->n_seg; s++) {
+        const ggb_gemv_seg& g = a->seg[s];
+        if (g.type != GGB_TYPE_Q4_K && g.type != GGB_TYPE_Q6_K) return false;
+        const int tile = ggb_sb_bytes(g.type) * GGB_TILE_SB;
+        if (tile > *max_tile) *max_tile = tile;
+    }
+    return a->k >= GGB_TILE_ELEMS && a->k % 256 == 0;
+}
+
+// 1 when a launch of this shape should be fed tiled images (ggb_act_prep_tiled + act_tiled = 1): more than 8 tokens whose
+// whole-vector images do not fit shared memory (the launch would otherwise run as two 8-token passes over the weights)
+extern "C" int ggb_gemv_batch_prefers_tiled(const ggb_gemv_batch_args* a) {
+    const char* ev = getenv("GGB_BATCH_TILED");   /* read per call: the tests switch it */
+    const int enabled = ev && *ev ? atoi(ev) : 1;
+    static const int use_mma = []() { const char* v = getenv("GGB_BATCH_MMA"); return v && *v ? atoi(v) : 1; }();
+    if (!a || !enabled || !use_mma || a->nb <= 8 || a->nb > 16 || a->n_seg < 1 || a->n_seg > GGB_MAX_SEG) return 0;
+    int max_tile;
+    if (!gbm_types_ok(a, &max_tile)) return 0;
+    const int grid = a->grid > 0 ? a->grid : ggb_num_sms();
+    const int stage_bytes = GBM_ROWS * (max_tile + 16);
+    const int image = a->k + a->k / 4, imgp = image + 4 * ((4 - (image / 4) % 32 + 32) % 32);
+    int64_t max_local = 0;
+    for (int s = 0; s < a->n_seg; s++) max_local += (a->seg[s].rows + grid - 1) / grid + 4;
+    if (enabled != 2 && gbm_plan_whole(a, 16, stage_bytes, imgp, max_local) >= 2) return 0;   /* GGB_BATCH_TILED=2: whenever possible (tests) */
+    return gbm_plan_tiled(a, 16, stage_bytes, grid, nullptr) >= 2 ? 1 : 0;
+}
+
+static int gbm_launch_tiled(const ggb_gemv_batch_args* a, GbmK P, int grid, void* stream) {
+    if (a->nb > 16) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: tiled activation images hold at most 16 tokens (nb=%d)", a->nb);
+    const int nbt = a->nb > 8 ? 16 : 8;
+    int groups = 0;
+    const int nstage = gbm_plan_tiled(a, nbt, P.stage_bytes, grid, &groups);
+    if (nstage < 2) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: shape k=%d rows=%d does not take tiled activation images", a->k, a->seg[0].rows);
+    P.nb = a->nb; P.act = (const uint8_t*)a->act; P.nstage = nstage;
+    P.image = P.imgp = GGB_ACT_TILE_STRIDE;
+    P.act_off = (nstage * P.stage_bytes + 127) & ~127;
+    P.red_off = P.act_off + 2 * nbt * GGB_ACT_TILE_STRIDE;
+    P.rowv_off = 0;
+    const size_t smem = (size_t)P.red_off + (size_t)groups * GBM_NW * GBM_ROWS * nbt * 8;
+    if (smem > GBM_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: tiled plan needs %zu bytes of shared memory", smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    return nbt == 16 ? gbm_launch_tiled_nt<2>(P, grid, smem, a->use_pdl, st) : gbm_launch_tiled_nt<1>(P, grid, smem, a->use_pdl, st);
 }
 
 // returns GGB_OK after launching, or 1 when the shape does not fit (the caller then uses the dp4a kernel)
@@ -330,6 +622,7 @@ int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream) {
     P.n_seg = a->n_seg; P.k = a->k; P.T = ggb_tiles_per_row(a->k); P.epi = a->epilogue; P.residual = a->residual;
     P.slotp = max_tile + 16;                        /* +16 B: rows g = 0..7 of a fragment fall into distinct banks */
     P.stage_bytes = GBM_ROWS * P.slotp;
+    if (a->act_tiled) return gbm_launch_tiled(a, P, grid, stream);
     P.image = a->k + a->k / 4;
     P.imgp = P.image + 4 * ((4 - (P.image / 4) % 32 + 32) % 32);   /* token stride == 4 words (mod 32 banks) */
     cudaStream_t st = (cudaStream_t)stream;

@@ -29,6 +29,11 @@
 
 #define GGB_TILE_ELEMS 2048
 #define GGB_TILE_SB 8 /* super-blocks per full tile */
+/* tiled activation images (ggb_act_prep_tiled): per (K-tile, token) codes 2048 | per-16 sums 256 | block scales 32, padded to a
+ * token stride of 4 words mod 32 banks */
+#define GGB_ACT_TILE_BS_OFF 2048
+#define GGB_ACT_TILE_DSC_OFF 2304
+#define GGB_ACT_TILE_STRIDE 2448
 
 #ifdef __CUDACC__
 #define GGB_HD __host__ __device__ __forceinline__

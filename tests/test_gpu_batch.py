@@ -228,3 +228,95 @@ def test_rope_kv_attn_argmax_batch(oracle, monkeypatch, gqa, n_head, n_kv, hd, n
     cabi.check(L.ggb_argmax_rows(U.to_dev(x).data_ptr(), 5000, 3, idx.data_ptr(), U.stream_ptr()))
     U.sync()
     assert idx.cpu().tolist() == [int(np.argmax(x[0])), 77, int(np.argmax(x[2]))]
+
+
+# ------------------------------------------------------------------ tiled activation images (one pass over the weights for 9..16 tokens of a long vector)
+TILE_STRIDE, TILE_BS, TILE_DSC = 2448, 2048, 2304
+
+
+def _prep_tiled(x: np.ndarray, k: int, norm_w=None, eps=0.0):
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    nb = x.shape[0]
+    size = L.ggb_act_tiled_bytes(k, nb)
+    assert size == -(-k // 2048) * nb * TILE_STRIDE
+    xd = U.to_dev(x.astype(np.float32))
+    act = torch.zeros(size, dtype=torch.uint8, device=U.DEV)
+    gd = U.to_dev(norm_w) if norm_w is not None else None
+    cabi.check(L.ggb_act_prep_tiled(xd.data_ptr(), gd.data_ptr() if gd is not None else 0, eps, k, nb, act.data_ptr(), 0, U.stream_ptr()))
+    U.sync()
+    return act
+
+
+@pytest.mark.parametrize("k,norm", [(2048, False), (5632, True), (14336, False), (4096, True)])
+def test_act_prep_tiled_bit_exact(oracle, k, norm):
+    rng = np.random.default_rng(k + 11)
+    nb, eps = 11, 1e-5
+    x = (rng.standard_normal((nb, k)) * np.exp(rng.uniform(-3, 3, (nb, 1)))).astype(np.float32)
+    x[0, :256] = 0.0
+    g = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32) if norm else None
+    T = -(-k // 2048)
+    img = _prep_tiled(x, k, norm_w=g, eps=eps).cpu().numpy().reshape(T, nb, TILE_STRIDE)
+    for b in range(nb):
+        h = oracle.rms_norm(x[b], g, eps) if norm else x[b]
+        rd, rq, rb = oracle.q8_K_fields(oracle.quantize_q8_K(h))
+        for t in range(T):
+            nsb = min(8, k // 256 - 8 * t)
+            sl = img[t, b]
+            assert np.array_equal(_unswizzle(sl[:2048].copy())[:256 * nsb].view(np.int8), rq[8 * t:8 * t + nsb].reshape(-1)), (b, t)
+            assert np.array_equal(sl[TILE_BS:TILE_BS + 32 * nsb].copy().view(np.int16), rb[8 * t:8 * t + nsb].reshape(-1))
+            assert np.array_equal(sl[TILE_DSC:TILE_DSC + 4 * nsb].copy().view(np.uint32), _bits(rd[8 * t:8 * t + nsb]))
+
+
+@pytest.mark.parametrize("name,qt", [("q4_k", 12), ("q6_k", 14)])
+@pytest.mark.parametrize("rows,k,nb", [(300, 14336, 11), (4096, 14336, 16), (600, 5632, 9), (100, 4096, 16), (2, 2048, 5), (8192, 8192, 13)])
+def test_gemv_batch_tiled_images_match_oracle_and_whole_images(oracle, name, qt, rows, k, nb):
+    """the tile-major walk over streamed image slices gives the bits of the whole-image kernel and of the oracle, for every epilogue"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    rng = np.random.default_rng(rows + k + nb + qt + 1)
+    be, _ = oracle.BLOCK[qt]
+    raw = rand_blocks(qt, rows * k // be, rng)
+    x = (rng.standard_normal((nb, k)) * np.exp(rng.uniform(-1, 1, (nb, 1)))).astype(np.float32)
+    w = U.gpu_repack(qt, raw, rows, k)
+    (whole,) = _batch_gemv([(w, qt, rows)], k, _prep(x, k), nb)
+    act = _prep_tiled(x, k)
+    (got,) = _batch_gemv([(w, qt, rows)], k, act, nb, act_tiled=1)
+    assert np.array_equal(_bits(got), _bits(whole))
+    for b in (0, nb - 1):
+        assert np.array_equal(_bits(got[b]), _bits(oracle.matmul(qt, raw, rows, k, x[b], mode="canon"))), f"token {b}"
+    # residual and unrounded-f64 epilogues
+    res = rng.standard_normal((nb, rows)).astype(np.float32)
+    y = U.to_dev(res.copy())
+    a = cabi.make_gemv_batch_args([(w.data_ptr(), qt, rows, y.data_ptr())], k, act.data_ptr(), nb, epilogue=cabi.EPI_RESIDUAL, residual=y.data_ptr(), act_tiled=1)
+    cabi.check(L.ggb_gemv_batch(C.byref(a), U.stream_ptr()), "residual")
+    U.sync()
+    assert np.array_equal(_bits(y.cpu().numpy()), _bits(res + whole))
+    y64 = torch.zeros(nb * rows, dtype=torch.float64, device=U.DEV)
+    a = cabi.make_gemv_batch_args([(w.data_ptr(), qt, rows, y64.data_ptr())], k, act.data_ptr(), nb, epilogue=cabi.EPI_STORE_F64, act_tiled=1)
+    cabi.check(L.ggb_gemv_batch(C.byref(a), U.stream_ptr()), "store_f64")
+    U.sync()
+    assert np.array_equal(_bits(y64.cpu().numpy().astype(np.float32).reshape(nb, rows)), _bits(whole))
+
+
+def test_gemv_batch_prefers_tiled_only_where_two_passes_would_run():
+    from ggufb200 import cabi
+    L = cabi.lib()
+
+    def pref(rows, k, nb, qt=12, nseg=1, epi=None):
+        a = cabi.make_gemv_batch_args([(16, qt, rows, 16)] * nseg, k, 16, nb, epilogue=cabi.EPI_STORE if epi is None else epi)
+        return L.ggb_gemv_batch_prefers_tiled(C.byref(a))
+
+    assert pref(4096, 14336, 16) == 1 and pref(4096, 14336, 16, qt=14) == 1 and pref(4096, 14336, 9) == 1      # ffn_down of Llama-3-8B
+    assert pref(4096, 14336, 8) == 0                 # one pass anyway
+    assert pref(4096, 4096, 16) == 0                 # sixteen whole images fit
+    assert pref(14336, 4096, 16, nseg=2, epi=cabi.EPI_SWIGLU) == 0
+    assert pref(4096, 14336, 16, qt=8) == 0          # Q8_0 stays on the dp4a kernel
+    assert pref(128256, 14336, 16) == 0              # too many row groups per CTA for the partial sums
+    # errors: tiled images with a shape / format the tiled kernel does not take
+    a = cabi.make_gemv_batch_args([(16, 8, 64, 16)], 4096, 16, 4, act_tiled=1)
+    assert L.ggb_gemv_batch(C.byref(a), 0) == -3    # GGB_ERR_UNSUPPORTED

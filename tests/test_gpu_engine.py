@@ -274,12 +274,15 @@ def test_gemm_prefill_matches_token_by_token_prefill_and_oracle(oracle, model_di
 
 # ----------------------------------------------------------------------------- batched decode (BASELINE.json config 5)
 @pytest.mark.parametrize("preset,ftype,n_seq", [("tiny", "Q4_K_M", 3), ("small", "Q4_K_M", 5), ("small", "Q5_K_M", 7), ("small", "Q8_0", 2), ("medium", "Q4_K_M", 11),
-                                                ("medium", "Q6_K", 16), ("gqa128", "Q4_K_M", 6)])
+                                                ("medium", "Q6_K", 16), ("gqa128", "Q4_K_M", 6), ("medium+tiled", "Q4_K_M", 13), ("medium+tiled", "Q6_K", 16)])
 def test_batched_decode_is_bit_identical_to_single_sequence_decode(oracle, model_dir, monkeypatch, preset, ftype, n_seq):
     """n_seq sequences with different prompts (so different positions) advance together through gemv_batch.cu;
     each must produce exactly the tokens and logits it produces alone -- and sequence 0 those of the canon oracle."""
     if preset == "gqa128":
         monkeypatch.setenv("GGB_ATTN_GQA", "2")     # the grouped-query attention kernel even for this small batch
+    if preset.endswith("+tiled"):                   # ffn_down through tiled activation images although sixteen whole images would fit
+        monkeypatch.setenv("GGB_BATCH_TILED", "2")
+        preset = preset[:-6]
     from ggufb200.model import Engine
     path = _model(model_dir, preset, ftype)
     n_new = 20
