@@ -558,6 +558,13 @@ static int env_int(const char* name, int dflt) {
 static int default_grid(const ggb_gemv_args* a) {
     if (a->grid > 0) return a->grid;
     static int per_sm = env_int("GGB_GEMV_CTAS_PER_SM", 1);
+    /* experiment: GGB_GEMV_GRID=n CTAs for every launch but the lm-head (read per call: tools/knob_sweep.py switches it) */
+    const int forced = env_int("GGB_GEMV_GRID", 0);
+    if (forced > 0 && forced <= 2 * ggb_num_sms()) {
+        int64_t rows = 0;
+        for (int s = 0; s < a->n_seg && s < GGB_MAX_SEG; s++) rows += a->seg[s].rows;
+        if (rows < 100000) return forced;
+    }
     return ggb_num_sms() * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
 }
 

@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ggb_dq_gemv_batch_kernel(const 
 // ------------------------------------------------------------------ activation images
 // One token's image = what the batch-1 GEMV prologue leaves in shared memory: K int8 codes in bank-swizzled 16-byte
 // chunks | K/16 int16 group sums | block scales (Q8_K: K/256 floats; Q8_0: K/32 floats), padded to 1.25 K bytes.
-// grid (nb, splits): with RMSNorm one CTA per token (it needs the whole row's sum of squares first); without it the
-// 256-blocks of a token are spread over `splits` CTAs.
+// grid (nb, splits): the 256-blocks of a token are spread over `splits` CTAs; with RMSNorm each of them first takes the
+// whole row's sum of squares (same order of additions in every CTA: same scale).
 __global__ void __launch_bounds__(GB_THREADS) act_prep_kernel(const float* __restrict__ x, const float* __restrict__ norm_w, float eps, int K,
                                                             int q8_0, uint8_t* __restrict__ out, int image) {
     __shared__ double red[GB_NW];
@@ -454,7 +454,10 @@ extern "C" int ggb_act_prep(const float* x, const float* norm_w, float eps, int6
     if (!x || !act || ((uintptr_t)x & 15) || ((uintptr_t)act & 15) || (norm_w && ((uintptr_t)norm_w & 15)))
         GGB_FAIL(GGB_ERR_ARG, "ggb_act_prep: null or misaligned pointer");
     const int nblk = (int)(k / 256);
-    const int splits = norm_w ? 1 : (nblk + GB_NW - 1) / GB_NW;
+    /* with RMSNorm every CTA of a token takes the whole row's sum of squares itself (<= 57 KB from L2), so the 256-blocks can
+     * still be spread: up to 4 CTAs per token */
+    int splits = (nblk + GB_NW - 1) / GB_NW;
+    if (norm_w && splits > 4) splits = 4;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     launch_cfg(cfg, at, dim3(nb, splits), dim3(GB_THREADS), 0, use_pdl, (cudaStream_t)stream);

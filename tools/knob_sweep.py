@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from ggufb200.model import Engine  # noqa: E402
 
-KNOBS = ("GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM", "GGB_LIB_PATH")
+KNOBS = ("GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM", "GGB_LIB_PATH", "GGB_GEMV_GRID")
 
 
 def run(path, steps, warm):
