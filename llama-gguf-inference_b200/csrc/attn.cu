@@ -767,7 +767,14 @@ extern "C" int ggb_attn_decode(const float* q, const uint16_t* kcache, const uin
         if (!ws || ((uintptr_t)ws & 255)) GGB_FAIL(GGB_ERR_ARG, "ggb_attn_decode: the long-sequence path needs the 256-byte aligned workspace of ggb_attn_decode_ws_bytes_ctx()");
         return launch_attn_split(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, ws, out, use_pdl, st);
     }
-    static const int cl1 = []() { const char* v = getenv("GGB_ATTN_CL"); return v && *v ? atoi(v) : 0; }();
+    /* experiment knobs, read per call (tools/knob_sweep.py switches them): CTAs per head, warps per CTA */
+    const char* cl_s = getenv("GGB_ATTN_CL");
+    const char* nw_s = getenv("GGB_ATTN_NW");
+    const int cl1 = cl_s && *cl_s ? atoi(cl_s) : 0, nw1 = nw_s && *nw_s ? atoi(nw_s) : 0;
+    if (head_dim == 128 && nw1 == 16 && n_ctx <= 16384) {
+        if (cl1 == 2) return launch_attn<128, 2, 16>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+        if (cl1 == 4) return launch_attn<128, 4, 16>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
+    }
     if (head_dim == 128 && cl1 == 4) return launch_attn<128, 4, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     if (head_dim == 128 && cl1 == 2) return launch_attn<128, 2, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);
     if (head_dim == 128) return launch_attn<128, ATTN_CL, ATTN_WARPS>(q, kcache, vcache, pos_dev, n_head, n_kv, n_ctx, out, use_pdl, st);

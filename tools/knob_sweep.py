@@ -11,14 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from ggufb200.model import Engine  # noqa: E402
 
-KNOBS = ("GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM", "GGB_LIB_PATH", "GGB_GEMV_GRID")
+KNOBS = ("GGB_ATTN_CL", "GGB_GEMV_CTAS_PER_SM", "GGB_LIB_PATH", "GGB_GEMV_GRID", "GGB_ATTN_NW")
 
 
 def run(path, steps, warm):
     eng = Engine(path, n_ctx=1024)
     eng.warmup()
     eng.reset()
-    eng.prefill([1] + list(range(300, 555)))
+    eng.prefill([1] + list(range(300, 300 + int(os.environ.get('SWEEP_PROMPT', '256')) - 1)))
     eng.decode(warm)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     best = 1e9
