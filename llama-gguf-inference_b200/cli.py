@@ -166,6 +166,8 @@ def main(argv=None, engine_factory=None) -> int:
                          use_pdl=not args.no_pdl, n_slots=max(1, args.parallel), verbose=args.verbose,
                          tp_rank=rank if world > 1 else 0, tp_size=world)
         eng.warmup()
+        if world == 1 and len(eng.slots) > 1 and os.environ.get("GGB_WARM_BATCH", "1") != "0" and hasattr(getattr(eng, "batch", None), "warmup"):
+            eng.batch.warmup()      # every batch size's graph now, not under the first burst of requests
         info.update({"n_layer": eng.hp.n_layer, "n_embd": eng.hp.d, "weights_gb": round(eng.weight_bytes / 1e9, 3)})
         log(f"main: model loaded in {time.time() - t0:.2f} s ({eng.weight_bytes / 1e9:.2f} GB of weights in HBM, "
             f"{len(eng.slots)} slot(s), context {args.ctx_size})")

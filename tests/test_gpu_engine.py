@@ -521,3 +521,30 @@ def test_embeddings_match_the_oracle_hidden_states(oracle, model_dir, pooling):
     assert float(got @ want) > 0.999, float(got @ want)
     assert eng.generate(prompt, 4) == m.greedy(prompt, 4)        # the slot is usable for generation afterwards
     eng.close()
+
+
+def test_batch_warmup_captures_every_shape_and_leaves_the_slots_clean(oracle, model_dir):
+    """llama-server start-up: BatchDecoder.warmup() captures the graphs of all batch shapes; decoding afterwards is what it is without"""
+    from ggufb200.model import Engine
+    path = _model(model_dir, "small", "Q4_K_M")
+    eng = Engine(path, n_ctx=96, n_slots=4)
+    eng.warmup()
+    eng.batch.warmup()
+    keys = set(eng.batch._graphs)
+    assert {(nb, True, c) for nb in (2, 3, 4) for c in (False, True)} <= keys
+    assert {(nb, False, False) for nb in range(1, 17)} <= keys
+    assert all(s.n_past == 0 for s in eng.slots)
+    prompts = [[1, 300 + s, 310 + s, 320 + s] for s in range(3)]
+    for s, p in enumerate(prompts):
+        eng.slots[s].prefill(p)
+    last = [eng.slots[s].read_last_token() for s in range(3)]
+    got = [[t] for t in last]
+    for _ in range(11):
+        last = eng.batch.step([(s, last[s], eng.slots[s].n_past) for s in range(3)])
+        for s in range(3):
+            got[s].append(last[s])
+    assert len(eng.batch._graphs) == len(keys)          # nothing was captured under load
+    ref = oracle.OracleLlama(path, n_ctx=96, mode="canon")
+    for s in range(3):
+        assert got[s] == ref.greedy(prompts[s], 12), f"sequence {s}"
+    eng.close()
