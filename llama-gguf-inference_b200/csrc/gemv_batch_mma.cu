@@ -74,7 +74,6 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
         const int sb = warp;
         const uint32_t rowA = stage + g * slotp, rowB = rowA + 8 * slotp;
         const int gsb = gsb0 + sb;                              /* super-block index within the activation image */
-        const int chunk_sb = gsb * 16;                          /* first 16-element chunk of the super-block */
         // block scales of my C-fragment tokens (2*t4, 2*t4+1 of every n-tile)
         float dx[NT][2];
 #pragma unroll
@@ -82,6 +81,20 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
             dx[nt][0] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4) * imgp + dsc_off + 4 * gsb));
             dx[nt][1] = __uint_as_float(lds32(act_s + (nt * 8 + 2 * t4 + 1) * imgp + dsc_off + 4 * gsb));
         }
+        // Activation addresses without per-access arithmetic.  Chunk c of the image sits at swz(c) = c ^ ((c >> 2) & 7); inside my
+        // super-block c = 16 gsb + l (l = 0..15), so swz(c) = 16 gsb + (l ^ x ^ 4 par) with x = (l >> 2) + (constant of the unit) known
+        // at compile time and par = gsb & 1: the parity moves the chunk by +-64 bytes, the sign given by bit 2 of l ^ x.  Two base
+        // registers per n-tile (plus / minus) and immediates replace a LOP3 + IMAD / LEA per load.
+        const int par = gsb & 1;
+        uint32_t bp[NT], bm[NT], bq[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            const uint32_t tb = act_s + (nt * 8 + g) * imgp + 4 * t4 + 256 * gsb;     /* B fragment: token nt*8 + g */
+            bp[nt] = tb + 64 * par; bm[nt] = tb - 64 * par;
+#pragma unroll
+            for (int q = 0; q < 2; q++) bq[nt][q] = act_s + (nt * 8 + 2 * t4 + q) * imgp + bs_off + 32 * gsb;   /* per-16 sums of C token 2*t4 + q */
+        }
+#define GBM_BADDR(nt, l, x) ((((((l) ^ (x)) >> 2) & 1) ? bm[nt] : bp[nt]) + 16 * ((l) ^ (x)))
         if (type == GGB_TYPE_Q4_K) {
             const uint4 hA = lds128(rowA + 2 * S + 16 * sb), hB = lds128(rowB + 2 * S + 16 * sb);
             const float dA = h2f((uint16_t)(hA.x & 0xFFFF)), mA = h2f((uint16_t)(hA.x >> 16));
@@ -96,18 +109,16 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
                 const int bo = 4 + 3 * j;
                 const uint32_t fA = (uint32_t)((((uint64_t)hwA[bo >> 2] | ((uint64_t)hwA[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
                 const uint32_t fB = (uint32_t)((((uint64_t)hwB[bo >> 2] | ((uint64_t)hwB[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
-                const int chunk0 = chunk_sb + 4 * j;
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) {
-                    const uint32_t tb = act_s + (nt * 8 + g) * imgp + 4 * t4;      /* B fragment: token nt*8 + g */
-                    int clo[4] = {0, 0, 0, 0}, chi[4] = {0, 0, 0, 0};
+                    int clo[4] = {0, 0, 0, 0}, chi[4] = {0, 0, 0, 0};              /* chunks 4j .. 4j+3 of the super-block: l = 4j + c, x = j */
                     mma_u8s8_k32(clo, wA0 & 0x0F0F0F0Fu, wB0 & 0x0F0F0F0Fu, wA1 & 0x0F0F0F0Fu, wB1 & 0x0F0F0F0Fu,
-                                 lds32(tb + 16 * swz(chunk0)), lds32(tb + 16 * swz(chunk0 + 1)));
+                                 lds32(GBM_BADDR(nt, 4 * j, j)), lds32(GBM_BADDR(nt, 4 * j + 1, j)));
                     mma_u8s8_k32(chi, (wA0 >> 4) & 0x0F0F0F0Fu, (wB0 >> 4) & 0x0F0F0F0Fu, (wA1 >> 4) & 0x0F0F0F0Fu, (wB1 >> 4) & 0x0F0F0F0Fu,
-                                 lds32(tb + 16 * swz(chunk0 + 2)), lds32(tb + 16 * swz(chunk0 + 3)));
+                                 lds32(GBM_BADDR(nt, 4 * j + 2, j)), lds32(GBM_BADDR(nt, 4 * j + 3, j)));
 #pragma unroll
                     for (int q = 0; q < 2; q++) {                                     /* C-fragment tokens 2*t4 + q */
-                        const uint2 bs = lds64(act_s + (nt * 8 + 2 * t4 + q) * imgp + bs_off + 2 * chunk0);   /* four per-16 sums */
+                        const uint2 bs = lds64(bq[nt][q] + 8 * j);                    /* four per-16 sums */
                         const int blo = (int)(int16_t)(bs.x & 0xFFFF) + ((int)bs.x >> 16);
                         const int bhi = (int)(int16_t)(bs.y & 0xFFFF) + ((int)bs.y >> 16);
                         const float x = dx[nt][q];
@@ -139,18 +150,17 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
                                         ((laB >> 4) & 0x0F0F0F0Fu) | (hqB & 0x30303030u), ((lbB >> 4) & 0x0F0F0F0Fu) | ((hqB >> 2) & 0x30303030u)};
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) {
-                    const uint32_t tb = act_s + (nt * 8 + g) * imgp + 4 * t4;
                     int isum[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
-                        const int chunk = chunk_sb + 8 * n + 2 * r + tt;
+                        const int l = 8 * n + 2 * r + tt;                             /* chunk within the super-block; x = l >> 2 */
                         int cc[4] = {0, 0, 0, 0};
-                        mma_u8s8_k16(cc, cA[r], cB[r], lds32(tb + 16 * swz(chunk)));
+                        mma_u8s8_k16(cc, cA[r], cB[r], lds32(GBM_BADDR(nt, l, l >> 2)));
                         const int si = 8 * n + 2 * r + tt;                           /* scale byte index */
                         const int sA = (int)(int8_t)((swA[si >> 2] >> (8 * (si & 3))) & 0xFF), sB = (int)(int8_t)((swB[si >> 2] >> (8 * (si & 3))) & 0xFF);
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
-                            const int b16 = 32 * (int)(int16_t)lds16(act_s + (nt * 8 + 2 * t4 + q) * imgp + bs_off + 2 * chunk);
+                            const int b16 = 32 * (int)(int16_t)lds16(bq[nt][q] + 2 * l);
                             isum[q] += sA * (cc[q] - b16);
                             isum[2 + q] += sB * (cc[2 + q] - b16);
                         }
@@ -163,6 +173,7 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
                 }
             }
         }
+#undef GBM_BADDR
     }
 }
 
