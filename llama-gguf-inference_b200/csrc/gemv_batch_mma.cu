@@ -109,6 +109,8 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
                 const int bo = 4 + 3 * j;
                 const uint32_t fA = (uint32_t)((((uint64_t)hwA[bo >> 2] | ((uint64_t)hwA[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
                 const uint32_t fB = (uint32_t)((((uint64_t)hwB[bo >> 2] | ((uint64_t)hwB[(bo >> 2) + ((bo >> 2) < 3 ? 1 : 0)] << 32)) >> (8 * (bo & 3))) & 0xFFFFFFu);
+                const int mmA0 = (int)(((fA >> 12) & 63) * 0x0101u), mmA1 = (int)(((fA >> 18) & 63) * 0x0101u);   /* (m, m) byte pairs */
+                const int mmB0 = (int)(((fB >> 12) & 63) * 0x0101u), mmB1 = (int)(((fB >> 18) & 63) * 0x0101u);
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) {
                     int clo[4] = {0, 0, 0, 0}, chi[4] = {0, 0, 0, 0};              /* chunks 4j .. 4j+3 of the super-block: l = 4j + c, x = j */
@@ -118,18 +120,16 @@ __device__ __forceinline__ void gbm_tile_step(int type, uint32_t stage, int slot
                                  lds32(GBM_BADDR(nt, 4 * j + 2, j)), lds32(GBM_BADDR(nt, 4 * j + 3, j)));
 #pragma unroll
                     for (int q = 0; q < 2; q++) {                                     /* C-fragment tokens 2*t4 + q */
-                        const uint2 bs = lds64(bq[nt][q] + 8 * j);                    /* four per-16 sums */
-                        const int blo = (int)(int16_t)(bs.x & 0xFFFF) + ((int)bs.x >> 16);
-                        const int bhi = (int)(int16_t)(bs.y & 0xFFFF) + ((int)bs.y >> 16);
+                        const uint2 bs = lds64(bq[nt][q] + 8 * j);                    /* four per-16 sums (int16): sub-block 2j in .x, 2j+1 in .y */
                         const float x = dx[nt][q];
-                        {
+                        {   /* min[2j] * (s0 + s1) + min[2j+1] * (s2 + s3) as two 2-way dots of the int16 pairs with the byte pairs (m, m) */
                             const int isum = (int)(fA & 63) * clo[q] + (int)((fA >> 6) & 63) * chi[q];
-                            const int msum = (int)((fA >> 12) & 63) * blo + (int)((fA >> 18) & 63) * bhi;
+                            const int msum = __dp2a_lo((int)bs.y, mmA1, __dp2a_lo((int)bs.x, mmA0, 0));
                             acc[nt][q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dA, x), (float)isum), __fmul_rn(__fmul_rn(mA, x), (float)msum));
                         }
                         {
                             const int isum = (int)(fB & 63) * clo[2 + q] + (int)((fB >> 6) & 63) * chi[2 + q];
-                            const int msum = (int)((fB >> 12) & 63) * blo + (int)((fB >> 18) & 63) * bhi;
+                            const int msum = __dp2a_lo((int)bs.y, mmB1, __dp2a_lo((int)bs.x, mmB0, 0));
                             acc[nt][2 + q] += (double)__fsub_rn(__fmul_rn(__fmul_rn(dB, x), (float)isum), __fmul_rn(__fmul_rn(mB, x), (float)msum));
                         }
                     }
