@@ -27,6 +27,8 @@
 #define GBM_NW 8                      /* consumer warps */
 #define GBM_THREADS ((GBM_NW + 1) * 32)
 #define GBM_ROWS 16
+#define GBM_RS 18                     /* doubles per (super-block, token) row of the partial-sum buffer: 16 rows + 2, so that the 16 lanes of a
+                                       * half-warp -- rows g = 0..3, tokens 2*t4 + q, i.e. words 36 t4 + g -- hit 16 different 8-byte banks */
 #define GBM_MAX_STAGES 6
 #define GBM_MAX_SMEM (226 * 1024)
 
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
 
     // ===== consumers
     uint8_t* act = smem + P.act_off;
-    double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [2][GBM_NW][16][NBT] */
+    double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [2][GBM_NW][NBT][GBM_RS] */
     double* rowv = reinterpret_cast<double*>(smem + P.rowv_off);   /* SWIGLU only: [local row][NBT] */
     // rows of absent tokens: zero images (dx = 0 -> every term 0)
     for (int i = tid * 16; i < (NBT - P.nb) * P.imgp; i += GBM_NW * 32 * 16) *reinterpret_cast<uint4*>(act + P.nb * P.imgp + i) = make_uint4(0, 0, 0, 0);
@@ -277,21 +279,21 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
             if (lane == 0) mbar_arrive1(smem_u32(&s_empty[st]));
         }
         // ---- the 8 K-slices of every (row, token) meet here
-        double* rb = red + (size_t)(p & 1) * GBM_NW * GBM_ROWS * NBT;
+        double* rb = red + (size_t)(p & 1) * GBM_NW * GBM_RS * NBT;   /* [super-block][token][GBM_RS rows] */
 #pragma unroll
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                rb[(warp * GBM_ROWS + g) * NBT + nt * 8 + 2 * t4 + q] = acc[nt][q];
-                rb[(warp * GBM_ROWS + g + 8) * NBT + nt * 8 + 2 * t4 + q] = acc[nt][2 + q];
+                rb[(warp * NBT + nt * 8 + 2 * t4 + q) * GBM_RS + g] = acc[nt][q];
+                rb[(warp * NBT + nt * 8 + 2 * t4 + q) * GBM_RS + g + 8] = acc[nt][2 + q];
             }
         consumer_sync();
         for (int i = tid; i < GBM_ROWS * NBT; i += GBM_NW * 32) {
-            const int rl = i / NBT, b = i - rl * NBT;
+            const int rl = i & (GBM_ROWS - 1), b = i / GBM_ROWS;         /* consecutive threads: consecutive rows (banks, and the stores below) */
             if (rl < nv && b < P.nb) {
                 double v = 0.0;
 #pragma unroll
-                for (int w = 0; w < GBM_NW; w++) v += rb[(w * GBM_ROWS + rl) * NBT + b];
+                for (int w = 0; w < GBM_NW; w++) v += rb[(w * NBT + b) * GBM_RS + rl];
                 const int row = row0 + rl;
                 if (P.epi == GGB_EPI_STORE) P.seg[s].y[(int64_t)b * P.seg[s].rows + row] = (float)v;
                 else if (P.epi == GGB_EPI_RESIDUAL) {
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_tiled_ke
 
     // ===== consumers
     uint8_t* abuf = smem + P.act_off;                               /* two slice buffers of NBT x imgp bytes */
-    double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [group][GBM_NW][16][NBT] */
+    double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [group][GBM_NW][NBT][GBM_RS] */
     const int abytes = NBT * P.imgp;
     // rows of absent tokens: zero slices in both buffers (dx = 0 -> every term 0; the bulk copies never touch them)
     for (int bsel = 0; bsel < 2; bsel++)
@@ -409,13 +411,13 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_tiled_ke
             gbm_tile_step<NT>(type, ring + st * P.stage_bytes, P.slotp, nsb, warp, lane, act_s, P.imgp, GGB_ACT_TILE_BS_OFF, GGB_ACT_TILE_DSC_OFF, 0, acc);
             __syncwarp();
             if (lane == 0) mbar_arrive1(smem_u32(&s_empty[st]));
-            double* rb = red + (size_t)p * GBM_NW * GBM_ROWS * NBT;
+            double* rb = red + (size_t)p * GBM_NW * GBM_RS * NBT;
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
-                    double* a0 = rb + (warp * GBM_ROWS + g) * NBT + nt * 8 + 2 * t4 + q;
-                    double* a1 = rb + (warp * GBM_ROWS + g + 8) * NBT + nt * 8 + 2 * t4 + q;
+                    double* a0 = rb + (warp * NBT + nt * 8 + 2 * t4 + q) * GBM_RS + g;
+                    double* a1 = a0 + 8;
                     if (t == 0) { *a0 = acc[nt][q]; *a1 = acc[nt][2 + q]; }
                     else { *a0 += acc[nt][q]; *a1 += acc[nt][2 + q]; }
                 }
@@ -425,14 +427,14 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_tiled_ke
     }
     // ---- the 8 K-slices of every (row, token) meet here
     for (int p = 0; p < ngroups; p++) {
-        const double* rb = red + (size_t)p * GBM_NW * GBM_ROWS * NBT;
+        const double* rb = red + (size_t)p * GBM_NW * GBM_RS * NBT;
         const int nv = min(GBM_ROWS, cnt - GBM_ROWS * p), row0 = ra + GBM_ROWS * p;
         for (int i = tid; i < GBM_ROWS * NBT; i += GBM_NW * 32) {
-            const int rl = i / NBT, b = i - rl * NBT;
+            const int rl = i & (GBM_ROWS - 1), b = i / GBM_ROWS;
             if (rl < nv && b < P.nb) {
                 double v = 0.0;
 #pragma unroll
-                for (int w = 0; w < GBM_NW; w++) v += rb[(w * GBM_ROWS + rl) * NBT + b];
+                for (int w = 0; w < GBM_NW; w++) v += rb[(w * NBT + b) * GBM_RS + rl];
                 const int64_t o = (int64_t)b * P.seg[0].rows + row0 + rl;
                 if (P.epi == GGB_EPI_STORE) P.seg[0].y[o] = (float)v;
                 else if (P.epi == GGB_EPI_RESIDUAL) P.seg[0].y[o] = __fadd_rn(P.residual[o], (float)v);
@@ -547,7 +549,7 @@ static int gbm_launch_tiled_nt(const GbmK& P, int grid, size_t smem, int use_pdl
 
 // whole-vector images: ring depth that fits next to `nbt` images (0 = does not fit)
 static int gbm_plan_whole(const ggb_gemv_batch_args* a, int nbt, int stage_bytes, int imgp, int64_t max_local) {
-    const size_t img = (size_t)nbt * imgp, red = (size_t)2 * GBM_NW * GBM_ROWS * nbt * 8;
+    const size_t img = (size_t)nbt * imgp, red = (size_t)2 * GBM_NW * GBM_RS * nbt * 8;
     const size_t rowv = a->epilogue == GGB_EPI_SWIGLU ? (size_t)max_local * nbt * 8 : 0;
     const size_t fixed = ((img + 127) & ~(size_t)127) + red + rowv + 256;
     int nstage = fixed < GBM_MAX_SMEM ? (int)((GBM_MAX_SMEM - fixed) / stage_bytes) : 0;
@@ -559,7 +561,7 @@ static int gbm_plan_tiled(const ggb_gemv_batch_args* a, int nbt, int stage_bytes
     if (a->n_seg != 1 || a->epilogue == GGB_EPI_SWIGLU || a->k < GGB_TILE_ELEMS) return 0;
     const int groups = (a->seg[0].rows / grid + 2 + GBM_ROWS - 1) / GBM_ROWS;
     if (groups > GBM_TILED_MAX_GROUPS) return 0;
-    const size_t fixed = (size_t)2 * nbt * GGB_ACT_TILE_STRIDE + (size_t)groups * GBM_NW * GBM_ROWS * nbt * 8 + 256;
+    const size_t fixed = (size_t)2 * nbt * GGB_ACT_TILE_STRIDE + (size_t)groups * GBM_NW * GBM_RS * nbt * 8 + 256;
     int nstage = fixed < GBM_MAX_SMEM ? (int)((GBM_MAX_SMEM - fixed) / stage_bytes) : 0;
     if (groups_out) *groups_out = groups;
     return nstage > GBM_MAX_STAGES ? GBM_MAX_STAGES : nstage;
@@ -586,7 +588,7 @@ extern "C" int ggb_gemv_batch_prefers_tiled(const ggb_gemv_batch_args* a) {
     int max_tile;
     if (!gbm_types_ok(a, &max_tile)) return 0;
     const int grid = a->grid > 0 ? a->grid : ggb_num_sms();
-    const int stage_bytes = GBM_ROWS * (max_tile + 16);
+    const int stage_bytes = GBM_ROWS * (max_tile + (16 - max_tile % 128 + 128) % 128);
     const int image = a->k + a->k / 4, imgp = image + 4 * ((4 - (image / 4) % 32 + 32) % 32);
     int64_t max_local = 0;
     for (int s = 0; s < a->n_seg; s++) max_local += (a->seg[s].rows + grid - 1) / grid + 4;
@@ -605,7 +607,7 @@ static int gbm_launch_tiled(const ggb_gemv_batch_args* a, GbmK P, int grid, void
     P.act_off = (nstage * P.stage_bytes + 127) & ~127;
     P.red_off = P.act_off + 2 * nbt * GGB_ACT_TILE_STRIDE;
     P.rowv_off = 0;
-    const size_t smem = (size_t)P.red_off + (size_t)groups * GBM_NW * GBM_ROWS * nbt * 8;
+    const size_t smem = (size_t)P.red_off + (size_t)groups * GBM_NW * GBM_RS * nbt * 8;
     if (smem > GBM_MAX_SMEM) GGB_FAIL(GGB_ERR_UNSUPPORTED, "ggb_gemv_batch: tiled plan needs %zu bytes of shared memory", smem);
     cudaStream_t st = (cudaStream_t)stream;
     return nbt == 16 ? gbm_launch_tiled_nt<2>(P, grid, smem, a->use_pdl, st) : gbm_launch_tiled_nt<1>(P, grid, smem, a->use_pdl, st);
@@ -631,7 +633,7 @@ int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream) {
         max_local += (a->seg[s].rows + grid - 1) / grid + 4;
     }
     P.n_seg = a->n_seg; P.k = a->k; P.T = ggb_tiles_per_row(a->k); P.epi = a->epilogue; P.residual = a->residual;
-    P.slotp = max_tile + 16;                        /* +16 B: rows g = 0..7 of a fragment fall into distinct banks */
+    P.slotp = max_tile + (16 - max_tile % 128 + 128) % 128;   /* slot stride == 16 B mod 128: rows g = 0..7 of a fragment fall into distinct banks (Q4_K: + 16, Q6_K: + 0) */
     P.stage_bytes = GBM_ROWS * P.slotp;
     if (a->act_tiled) return gbm_launch_tiled(a, P, grid, stream);
     P.image = a->k + a->k / 4;
@@ -642,7 +644,7 @@ int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream) {
         size_t smem = 0;
         int nstage = 0;
         for (;;) {   /* shared memory: [ring][images][red x2][rowv (SWIGLU)] */
-            const size_t img = (size_t)nbt * P.imgp, red = (size_t)2 * GBM_NW * GBM_ROWS * nbt * 8;
+            const size_t img = (size_t)nbt * P.imgp, red = (size_t)2 * GBM_NW * GBM_RS * nbt * 8;
             const size_t rowv = a->epilogue == GGB_EPI_SWIGLU ? (size_t)max_local * nbt * 8 : 0;
             const size_t fixed = ((img + 127) & ~(size_t)127) + red + rowv + 256;
             nstage = fixed < GBM_MAX_SMEM ? (int)((GBM_MAX_SMEM - fixed) / P.stage_bytes) : 0;
