@@ -45,7 +45,7 @@ struct GbmK {
     int n_seg, k, T, epi, nb;
     int slotp, stage_bytes, nstage;     /* padded tile slot, 16 slots, ring depth */
     int image, imgp;                    /* activation image bytes / padded token stride */
-    int act_off, red_off, rowv_off;
+    int act_off, red_off, rowv_off, rowv_ld;   /* rowv_ld: local rows per token of the SWIGLU row buffer */
     int rq[GGB_MAX_SEG], rr[GGB_MAX_SEG];
     const uint8_t* act;
     const float* residual;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
     // ===== consumers
     uint8_t* act = smem + P.act_off;
     double* red = reinterpret_cast<double*>(smem + P.red_off);     /* [2][GBM_NW][NBT][GBM_RS] */
-    double* rowv = reinterpret_cast<double*>(smem + P.rowv_off);   /* SWIGLU only: [local row][NBT] */
+    double* rowv = reinterpret_cast<double*>(smem + P.rowv_off);   /* SWIGLU only: [token][rowv_ld local rows] */
     // rows of absent tokens: zero images (dx = 0 -> every term 0)
     for (int i = tid * 16; i < (NBT - P.nb) * P.imgp; i += GBM_NW * 32 * 16) *reinterpret_cast<uint4*>(act + P.nb * P.imgp + i) = make_uint4(0, 0, 0, 0);
     pdl_launch_dependents();
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
                     const int64_t o = (int64_t)b * P.seg[0].rows + row;
                     P.seg[0].y[o] = __fadd_rn(P.residual[o], (float)v);
                 } else if (P.epi == GGB_EPI_STORE_F64) reinterpret_cast<double*>(P.seg[0].y)[(int64_t)b * P.seg[0].rows + row] = v;
-                else rowv[(lr + rl) * NBT + b] = v;
+                else rowv[b * P.rowv_ld + lr + rl] = v;
             }
         }
         /* the other half of `red` is used by the next group; the sync of the group after that orders its reuse */
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(GBM_THREADS, 1) ggb_dq_gemv_batch_mma_kernel(c
         const int cnt0 = X.cnt[0];
         for (int i = tid; i < cnt0 * P.nb; i += GBM_NW * 32) {
             const int b = i / cnt0, l = i - b * cnt0;
-            P.seg[0].y[(int64_t)b * P.seg[0].rows + X.r0[0] + l] = silu_mul_ref((float)rowv[l * NBT + b], (float)rowv[(cnt0 + l) * NBT + b]);
+            P.seg[0].y[(int64_t)b * P.seg[0].rows + X.r0[0] + l] = silu_mul_ref((float)rowv[b * P.rowv_ld + l], (float)rowv[b * P.rowv_ld + cnt0 + l]);
         }
     }
 }
@@ -655,6 +655,7 @@ int ggb_gemv_batch_mma(const ggb_gemv_batch_args* a, void* stream) {
                 P.act_off = (P.act_off + 127) & ~127;
                 P.red_off = P.act_off + (int)((img + 127) & ~(size_t)127);
                 P.rowv_off = P.red_off + (int)red;
+                P.rowv_ld = (int)max_local;
                 smem = (size_t)P.rowv_off + rowv;
                 break;
             }
