@@ -271,6 +271,11 @@ int ggb_attn_decode_batch(const float* q, const uint16_t* kcache, const uint16_t
                           const int32_t* slot_dev, int64_t slot_stride, int nb, int n_head, int n_kv, int head_dim,
                           int n_ctx, float* out, int use_pdl, void* stream);
 int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_idx, void* stream);
+/* Sampler candidates (sampled requests: temperature > 0 with top-k): for every row of x [nb][n] the elements >= the k-th largest
+ * value -- k of them, more on ties -- unordered, as (value, index) pairs in out_val / out_idx [nb][cap]; out_cnt[b] = how many
+ * row b has (> cap: ties overflowed, read the row instead).  Exact; the host sorts them and runs top-p / min-p / temperature on
+ * k numbers instead of reading back and partitioning n (llama.cpp's top-k sampler, [UPSTREAM-MEM: llama-sampling.cpp]). */
+int ggb_topk_rows(const float* x, int64_t n, int nb, int k, int cap, float* out_val, int32_t* out_idx, int32_t* out_cnt, void* stream);
 /* Tensor-parallel batch: x [nb][n] is this rank's vocabulary shard starting at global row row_offset.  ggb_argmax_rows_key
  * packs (maximum, global index) of every row into one sortable signed 64-bit key (larger value, then smaller index);
  * after a MAX all-reduce of the keys ggb_argmax_keys_unpack yields the global first-maximum index of every row. */

@@ -231,6 +231,29 @@ class BatchDecoder:
             sl.reset()
         self._last = None
 
+    def candidates(self, nb: int, k: int, cap: int = 256):
+        """per row of the last step's logits: (token ids, logits) of every logit >= the k-th largest, or None for a row whose ties
+        overflowed the buffer; None altogether when the vocabulary is sharded.  One launch and one copy for all rows."""
+        e, torch = self.eng, self.torch
+        if self.tp > 1 or not (0 < nb <= self.nb_max and 0 < k <= min(cap, self.vl)):
+            return None
+        if getattr(self, "_cand_dev", None) is None or self._cand_cap != cap:
+            self._cand_cap = cap
+            self._cand_dev = torch.zeros(self.nb_max * (2 * cap + 1), dtype=torch.int32, device=e.dev)   # values | indices | counts
+            self._cand_host = torch.zeros(self.nb_max * (2 * cap + 1), dtype=torch.int32).pin_memory()
+        d, NB = self._cand_dev, self.nb_max
+        with torch.cuda.stream(self.stream):
+            cabi.check(self.lib.ggb_topk_rows(self.logits.data_ptr(), self.vl, nb, k, cap, d.data_ptr(), d.data_ptr() + 4 * NB * cap,
+                                              d.data_ptr() + 8 * NB * cap, self.stream.cuda_stream), "topk_rows")
+            self._cand_host.copy_(d, non_blocking=True)
+        self.stream.synchronize()
+        h = self._cand_host.numpy()
+        out = []
+        for b in range(nb):
+            c = int(h[2 * NB * cap + b])
+            out.append(None if c > cap else (h[NB * cap + b * cap:NB * cap + b * cap + c].copy(), h[b * cap:b * cap + c].copy().view(np.float32)))
+        return out
+
     def logits_row_tensor(self, b: int):
         """row b of this rank's logits (its vocabulary shard under tensor parallelism), on the device, stream drained"""
         self.stream.synchronize()

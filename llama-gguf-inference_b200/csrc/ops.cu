@@ -375,3 +375,77 @@ extern "C" int ggb_argmax_unpack_next(const int64_t* key, int32_t* tok_dev, int3
     if (token_embd) return ggb_embed_row(emb_type, token_embd, k, tok_dev, x, stream);
     return GGB_OK;
 }
+
+// ------------------------------------------------------------------ sampler candidates: the k largest logits of every row
+// A sampled request (temperature > 0, top-k) needs the k best logits of a 128 K row, not the row: reading it back and
+// partitioning it on the host costs ~1.5 ms per token and sequence -- more than the whole decode step.  One CTA per row finds the
+// k-th largest value EXACTLY by building its order-preserving 32-bit key two bits per pass (16 passes over the L2-resident row,
+// three nested thresholds counted per pass), then emits every element >= that value (k of them, more on ties, at most `cap`).
+// The host sorts the few candidates and runs the unchanged top-p / min-p / temperature / multinomial chain on them.
+__device__ __forceinline__ uint32_t topk_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);      /* unsigned order == float order (-0 < +0, NaN above +Inf) */
+}
+
+#define TOPK_THREADS 1024
+__global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __restrict__ x, int64_t n, int k, int cap, float* __restrict__ out_val,
+                                                                 int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cnt) {
+    __shared__ int s_c[3][TOPK_THREADS / 32];
+    __shared__ int s_tot[3];
+    __shared__ int s_n;
+    const float* xr = x + (int64_t)blockIdx.x * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n4 = ((uintptr_t)xr & 15) ? 0 : n / 4;     /* float4 body (rows of a [nb][n] matrix with n % 4 == 0 are aligned) */
+    uint32_t T = 0;
+    for (int bit = 30; bit >= 0; bit -= 2) {
+        const uint32_t t1 = T | (1u << bit), t2 = T | (2u << bit), t3 = T | (3u << bit);
+        int c1 = 0, c2 = 0, c3 = 0;
+        for (int64_t i = tid; i < n4; i += TOPK_THREADS) {
+            const float4 v = reinterpret_cast<const float4*>(xr)[i];
+            const uint32_t ka = topk_key(v.x), kb = topk_key(v.y), kc = topk_key(v.z), kd = topk_key(v.w);
+            c1 += (ka >= t1) + (kb >= t1) + (kc >= t1) + (kd >= t1);
+            c2 += (ka >= t2) + (kb >= t2) + (kc >= t2) + (kd >= t2);
+            c3 += (ka >= t3) + (kb >= t3) + (kc >= t3) + (kd >= t3);
+        }
+        for (int64_t i = 4 * n4 + tid; i < n; i += TOPK_THREADS) {
+            const uint32_t ka = topk_key(xr[i]);
+            c1 += ka >= t1; c2 += ka >= t2; c3 += ka >= t3;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+        }
+        if (lane == 0) { s_c[0][warp] = c1; s_c[1][warp] = c2; s_c[2][warp] = c3; }
+        __syncthreads();
+        if (warp < 3) {
+            int v = s_c[warp][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_tot[warp] = v;
+        }
+        __syncthreads();
+        if (s_tot[2] >= k) T = t3; else if (s_tot[1] >= k) T = t2; else if (s_tot[0] >= k) T = t1;
+        __syncthreads();
+    }
+    // T is the key of the k-th largest element (count(key >= T) >= k, count(key > T) < k): emit everything >= T
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += TOPK_THREADS) {
+        const float v = xr[i];
+        if (topk_key(v) >= T) {
+            const int p = atomicAdd(&s_n, 1);
+            if (p < cap) { out_val[(int64_t)blockIdx.x * cap + p] = v; out_idx[(int64_t)blockIdx.x * cap + p] = (int32_t)i; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) out_cnt[blockIdx.x] = s_n;      /* may exceed cap (ties at the k-th value): the caller then falls back to the whole row */
+}
+
+extern "C" int ggb_topk_rows(const float* x, int64_t n, int nb, int k, int cap, float* out_val, int32_t* out_idx, int32_t* out_cnt, void* stream) {
+    if (n <= 0 || nb < 0 || k <= 0 || k > n || cap < k || (nb && (!x || !out_val || !out_idx || !out_cnt)))
+        GGB_FAIL(GGB_ERR_ARG, "ggb_topk_rows: bad argument (n=%lld nb=%d k=%d cap=%d)", (long long)n, nb, k, cap);
+    if (nb == 0) return GGB_OK;
+    topk_rows_kernel<<<nb, TOPK_THREADS, 0, (cudaStream_t)stream>>>(x, n, k, cap, out_val, out_idx, out_cnt);
+    GGB_CHECK_LAUNCH("ggb_topk_rows");
+    return GGB_OK;
+}

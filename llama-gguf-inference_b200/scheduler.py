@@ -13,6 +13,7 @@ boundary can be tested on a CPU box with a stand-in engine.
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 import time
@@ -88,6 +89,38 @@ def _lcp(a, b) -> int:
     return n
 
 
+TOPK_CAP = 256      # candidates per row the device hands back (ggb_topk_rows); top_k above TOPK_CAP - 16 reads the whole row
+
+
+def _chain(idx: np.ndarray, xs: np.ndarray, sp: SamplingParams, rng: np.random.Generator) -> int:
+    """top-p -> min-p -> temperature -> multinomial on the top-k logits xs (float64, descending) with token ids idx"""
+    p = np.exp(xs - xs[0])
+    p /= p.sum()
+    if 0.0 < sp.top_p < 1.0:
+        keep = int(np.searchsorted(np.cumsum(p), sp.top_p) + 1)
+        idx, xs, p = idx[:keep], xs[:keep], p[:keep] / p[:keep].sum()
+    if 0.0 < sp.min_p < 1.0:
+        keep = max(1, int((p >= sp.min_p * p[0]).sum()))          # p is sorted, p[0] is the maximum
+        idx, xs = idx[:keep], xs[:keep]
+    xt = xs / max(sp.temperature, 1e-6)
+    p = np.exp(xt - xt[0])
+    p /= p.sum()
+    return int(idx[rng.choice(len(idx), p=p)])
+
+
+def device_topk_ok(sp: SamplingParams) -> bool:
+    """the request can be sampled from the device's top-k candidates: no penalties (they change logits outside the top-k too),
+    a top_k that fits the candidate buffer"""
+    return not sp.arg_max and not sp.penalised and 0 < sp.top_k <= TOPK_CAP - 16 and os.environ.get("GGB_DEVICE_TOPK", "1") != "0"
+
+
+def sample_from_candidates(idx: np.ndarray, vals: np.ndarray, sp: SamplingParams, rng: np.random.Generator) -> int:
+    """sample_token() on what ggb_topk_rows returned: every logit >= the k-th largest, unordered (ties: lower token id first)"""
+    xs = vals.astype(np.float64)
+    order = np.lexsort((idx, -xs))[: sp.top_k]
+    return _chain(idx[order].astype(np.int64), xs[order], sp, rng)
+
+
 def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generator, history=None) -> int:
     """penalties -> top-k -> top-p -> min-p -> temperature -> multinomial: the order of upstream's default sampler chain
     [UPSTREAM-MEM: common/sampling.cpp; the reference documents the parameters in docs/API_REFERENCE.md:369-379].
@@ -98,20 +131,9 @@ def sample_token(logits: np.ndarray, sp: SamplingParams, rng: np.random.Generato
         return int(np.argmax(logits))
     x = logits.astype(np.float64)
     k = sp.top_k if 0 < sp.top_k < x.size else x.size
-    idx = np.argpartition(x, -k)[-k:]
-    idx = idx[np.argsort(-x[idx], kind="stable")]
-    p = np.exp(x[idx] - x[idx[0]])
-    p /= p.sum()
-    if 0.0 < sp.top_p < 1.0:
-        keep = int(np.searchsorted(np.cumsum(p), sp.top_p) + 1)
-        idx, p = idx[:keep], p[:keep] / p[:keep].sum()
-    if 0.0 < sp.min_p < 1.0:
-        keep = max(1, int((p >= sp.min_p * p[0]).sum()))          # p is sorted, p[0] is the maximum
-        idx = idx[:keep]
-    xt = x[idx] / max(sp.temperature, 1e-6)
-    p = np.exp(xt - xt[0])
-    p /= p.sum()
-    return int(idx[rng.choice(len(idx), p=p)])
+    idx = np.flatnonzero(x >= np.partition(x, -k)[-k]) if k < x.size else np.arange(x.size)
+    idx = idx[np.lexsort((idx, -x[idx]))][:k]                    # descending; ties: lower token id first
+    return _chain(idx, x[idx], sp, rng)
 
 
 class _Active:
@@ -306,7 +328,13 @@ class Scheduler(threading.Thread):
         """token produced by the step that just ran"""
         if a.req.sampling.greedy:
             return a.slot.read_last_token()
-        return sample_token(a.slot.read_logits(), a.req.sampling, a.rng, a.history)
+        sp = a.req.sampling
+        if device_topk_ok(sp) and hasattr(a.slot, "read_candidates"):
+            cand = a.slot.read_candidates(sp.top_k, TOPK_CAP)          # k numbers instead of the vocabulary
+            if cand is not None:
+                self.stats["device_topk_tokens"] = self.stats.get("device_topk_tokens", 0) + 1
+                return sample_from_candidates(cand[0], cand[1], sp, a.rng)
+        return sample_token(a.slot.read_logits(), sp, a.rng, a.history)
 
     def _step(self, i: int):
         a = self.active.get(i)
@@ -348,24 +376,34 @@ class Scheduler(threading.Thread):
             self.stats["batched_steps"] = self.stats.get("batched_steps", 0) + 1
             self.stats["batched_tokens"] = self.stats.get("batched_tokens", 0) + len(live)
             pairs = list(zip(live, acts))
-            if hasattr(bd, "launch") and all(a.req.sampling.greedy for a in acts):
+            if hasattr(bd, "launch"):
                 self._inflight = (bd.launch(entries), pairs)           # collected by the next round, after its own launch
             else:
                 self._deliver(bd.step(entries), pairs)
             return
         handle, pairs = inf
         nxt = None
+        all_greedy = all(a.req.sampling.greedy for _, a in pairs)
+        go_on = False
         if ([i for i, _ in pairs] == list(self.active) and all(self.active[i] is a for i, a in pairs)
                 and all(a.n_gen + 1 < a.req.max_tokens for _, a in pairs)):
             with self.cv:
                 waiting = bool(self.pending) and len(self.active) < len(self.engine.slots)
-            if not waiting:
-                nxt = bd.launch_chained()                               # step k+1 from device state; None at the context end
+            go_on = not waiting
+        if go_on and all_greedy:
+            nxt = bd.launch_chained()                                   # step k+1 from device state; None at the context end
         self._inflight = None
         t0 = time.time()
         toks = bd.collect(handle)
         self.stats["gpu_wait_seconds"] = self.stats.get("gpu_wait_seconds", 0.0) + time.time() - t0
-        self._deliver(toks, pairs)
+        decided = self._decide(toks, pairs)
+        if go_on and not all_greedy and len(decided) == len(pairs) and all(a.slot.n_past + 1 < a.slot.n_ctx for _, a, _ in decided):
+            # sampled sequences: the tokens are chosen (k candidates per row came off the GPU), so step k+1 is fed by the host and
+            # enqueued BEFORE the tokens of step k are detokenised and streamed -- that work overlaps the GPU like the greedy chain's
+            nxt = bd.launch([(a.slot.index, tok, a.slot.n_past) for _, a, tok in decided])
+        for i, a, tok in decided:
+            if self.active.get(i) is a:
+                self._emit(i, tok)
         if nxt is not None:
             for i, a in pairs:
                 if self.active.get(i) is a:
@@ -376,11 +414,32 @@ class Scheduler(threading.Thread):
             self._inflight = (nxt, pairs)
 
     def _deliver(self, toks, pairs):
+        for i, a, tok in self._decide(toks, pairs):
+            if self.active.get(i) is a:
+                self._emit(i, tok)
+
+    def _decide(self, toks, pairs):
+        """[(slot index, sequence, token)] of the step that was just collected, for the sequences still running: the device's
+        arg-max for greedy ones, the host sampler (on the device's top-k candidates where the request allows) for the others"""
         bd = self.engine.batch
+        out = []
+        cands = None
+        ks = [a.req.sampling.top_k for i, a in pairs if self.active.get(i) is a and device_topk_ok(a.req.sampling)]
+        if ks and hasattr(bd, "candidates"):
+            cands = bd.candidates(len(pairs), max(ks), TOPK_CAP)        # one launch + one small copy for every sampled row of the step
         for b, (i, a) in enumerate(pairs):
             if self.active.get(i) is not a:
                 continue                                                # ended or cancelled while the step was in flight
-            self._emit(i, toks[b] if a.req.sampling.greedy else sample_token(bd.logits_row(b), a.req.sampling, a.rng, a.history))
+            sp = a.req.sampling
+            if sp.greedy:
+                tok = toks[b]
+            elif cands is not None and device_topk_ok(sp) and cands[b] is not None:
+                self.stats["device_topk_tokens"] = self.stats.get("device_topk_tokens", 0) + 1
+                tok = sample_from_candidates(cands[b][0], cands[b][1], sp, a.rng)
+            else:
+                tok = sample_token(bd.logits_row(b), sp, a.rng, a.history)
+            out.append((i, a, tok))
+        return out
 
     def _drain(self):
         """wait for the step in flight (if any) and deliver its tokens"""

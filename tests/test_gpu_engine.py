@@ -548,3 +548,34 @@ def test_batch_warmup_captures_every_shape_and_leaves_the_slots_clean(oracle, mo
     for s in range(3):
         assert got[s] == ref.greedy(prompts[s], 12), f"sequence {s}"
     eng.close()
+
+
+def test_device_candidates_equal_the_rows_top_k(oracle, model_dir):
+    """Slot.read_candidates / BatchDecoder.candidates (sampled requests: k numbers leave the GPU instead of the vocabulary) hold exactly
+    the logits a host-side top-k of the same row holds, and the scheduler's sampler picks the same token from either"""
+    from ggufb200.model import Engine
+    from ggufb200.scheduler import SamplingParams, sample_from_candidates, sample_token
+    path = _model(model_dir, "small", "Q4_K_M")
+    eng = Engine(path, n_ctx=64, n_slots=3)
+    eng.warmup()
+    sp = SamplingParams(temperature=0.9, top_k=40, top_p=0.95, seed=5)
+    s0 = eng.slots[0]
+    s0.prefill(PROMPT)
+    s0.decode(3)
+    row = s0.read_logits().copy()
+    idx, val = s0.read_candidates(sp.top_k)
+    assert set(idx.tolist()) == set(np.flatnonzero(row >= np.sort(row)[-sp.top_k]).tolist())
+    assert np.array_equal(_bits(val), _bits(row[idx]))
+    assert sample_from_candidates(idx, val, sp, np.random.default_rng(5)) == sample_token(row, sp, np.random.default_rng(5))
+    for s in range(3):
+        eng.slots[s].reset()
+        eng.slots[s].prefill([1, 300 + s, 310 + s])
+    last = [eng.slots[s].read_last_token() for s in range(3)]
+    eng.batch.step([(s, last[s], eng.slots[s].n_past) for s in range(3)])
+    cands = eng.batch.candidates(3, sp.top_k)
+    for s in range(3):
+        row = eng.batch.logits_row(s).copy()
+        idx, val = cands[s]
+        assert set(idx.tolist()) == set(np.flatnonzero(row >= np.sort(row)[-sp.top_k]).tolist())
+        assert sample_from_candidates(idx, val, sp, np.random.default_rng(s)) == sample_token(row, sp, np.random.default_rng(s))
+    eng.close()

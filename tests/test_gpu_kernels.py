@@ -446,3 +446,39 @@ def test_rms_norm_swiglu_argmax_embed(oracle):
         U.sync()
         rb = k // be * bb
         assert np.array_equal(_bits(oracle.dequantize(raw.reshape(-1)[6 * rb:7 * rb], qt, k)), _bits(xo.cpu().numpy()))
+
+
+@pytest.mark.parametrize("n,nb,k", [(128256, 3, 40), (32000, 16, 1), (5000, 2, 240), (1001, 1, 7), (256, 4, 256)])
+def test_topk_rows_returns_exactly_the_logits_from_the_kth_largest_up(n, nb, k):
+    """ggb_topk_rows: per row the set {x >= k-th largest x} (unordered), incl. ties, negatives, -0.0 / +0.0 and a row of equal values"""
+    import torch
+    import gpu_util as U
+    from ggufb200 import cabi
+    L = cabi.lib()
+    cap = 256
+    rng = np.random.default_rng(n + k)
+    x = (rng.standard_normal((nb, n)) * 4).astype(np.float32)
+    x[0, rng.integers(0, n, 30)] = x[0].max()                     # ties at the top of row 0
+    if nb > 1:
+        x[1, :] = np.where(rng.random(n) < 0.5, -0.0, 0.0).astype(np.float32)   # row 1: only zeros of both signs
+        x[1, rng.integers(0, n, max(1, k // 2))] = 1.5
+    xd = U.to_dev(x)
+    out = torch.zeros(nb * (2 * cap + 1), dtype=torch.int32, device=U.DEV)
+    cabi.check(L.ggb_topk_rows(xd.data_ptr(), n, nb, k, cap, out.data_ptr(), out.data_ptr() + 4 * nb * cap, out.data_ptr() + 8 * nb * cap,
+                               U.stream_ptr()), "topk_rows")
+    U.sync()
+    h = out.cpu().numpy()
+    for b in range(nb):
+        c = int(h[2 * nb * cap + b])
+        key = x[b].view(np.int32).astype(np.int64)
+        key = np.where(key < 0, -(key & 0x7FFFFFFF) - 1, key)     # the kernel's order: -0.0 below +0.0
+        kth = np.sort(key)[-k]
+        want = np.flatnonzero(key >= kth)
+        assert c == want.size, (b, c, want.size)
+        if c <= cap:
+            idx = h[nb * cap + b * cap:nb * cap + b * cap + c]
+            val = h[b * cap:b * cap + c].view(np.float32)
+            assert np.array_equal(np.sort(idx), want)
+            assert np.array_equal(val.view(np.uint32), x[b][idx].view(np.uint32))
+    assert L.ggb_topk_rows(xd.data_ptr(), n, nb, 0, cap, out.data_ptr(), out.data_ptr(), out.data_ptr(), 0) == -1
+    assert L.ggb_topk_rows(xd.data_ptr(), n, nb, cap + 1, cap, out.data_ptr(), out.data_ptr(), out.data_ptr(), 0) == -1

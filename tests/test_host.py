@@ -325,3 +325,27 @@ def test_sampler_min_p_and_penalties():
     assert SamplingParams(temperature=0.0).greedy
     # ids outside the vocabulary in the history are ignored
     assert np.array_equal(apply_penalties(logits, sp, [99, -1]), logits)
+
+
+def test_sampling_from_device_candidates_equals_sampling_from_the_row():
+    """scheduler.sample_from_candidates on {logits >= the k-th largest} (what ggb_topk_rows hands back, unordered) picks the token
+    sample_token picks from the whole row, for the same seed: top-k / top-p / min-p / temperature see the same sorted k numbers"""
+    from ggufb200.scheduler import SamplingParams, device_topk_ok, sample_from_candidates, sample_token
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        n = int(rng.integers(300, 5000))
+        logits = (rng.standard_normal(n) * 3).astype(np.float32)
+        if trial % 5 == 0:
+            logits[rng.integers(0, n, 40)] = logits.max()          # ties at the top
+        sp = SamplingParams(temperature=float(rng.uniform(0.2, 1.5)), top_k=int(rng.integers(2, 100)), top_p=float(rng.choice([1.0, 0.95, 0.5])),
+                            min_p=float(rng.choice([0.0, 0.05])), seed=trial)
+        assert device_topk_ok(sp)
+        kth = np.sort(logits)[-sp.top_k]
+        idx = np.flatnonzero(logits >= kth).astype(np.int32)
+        rng.shuffle(idx)
+        a = sample_token(logits, sp, np.random.default_rng(trial))
+        b = sample_from_candidates(idx, logits[idx], sp, np.random.default_rng(trial))
+        assert a == b, trial
+    assert not device_topk_ok(SamplingParams(temperature=0.0))                       # greedy: the arg-max kernel
+    assert not device_topk_ok(SamplingParams(repeat_penalty=1.1))                    # penalties reach below the top-k
+    assert not device_topk_ok(SamplingParams(top_k=0)) and not device_topk_ok(SamplingParams(top_k=1000))

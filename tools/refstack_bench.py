@@ -60,6 +60,7 @@ def main() -> int:
     ap.add_argument("--stage", action="store_true", help="copy /root/reference/scripts to baseline/_ref/scripts and exit")
     ap.add_argument("--requests", type=int, default=0)
     ap.add_argument("--max-tokens", type=int, default=128)
+    ap.add_argument("--temp", type=float, default=0.0, help="server default temperature (0 = greedy; 0.8 = llama-server's default sampling chain)")
     args = ap.parse_args()
     if args.stage:
         dst = os.path.join(ROOT, "baseline", "_ref", "scripts")
@@ -87,7 +88,7 @@ def main() -> int:
     ctx = 1024 * conc          # llama-server divides -c by --parallel: 1024 positions per slot
     env = {**os.environ, "DATA_DIR": data, "MODEL_NAME": "model.gguf", "PORT": str(gport), "PORT_BACKEND": str(bport),
            "PORT_HEALTH": str(hport), "NGL": "99", "CTX": str(ctx), "THREADS": "4",
-           "EXTRA_ARGS": f"--parallel {conc} --temp 0 --ignore-eos", "AUTH_ENABLED": "true", "INSTANCE_ID": f"refstack-{os.getpid()}",
+           "EXTRA_ARGS": f"--parallel {conc} --temp {args.temp:g} --ignore-eos", "AUTH_ENABLED": "true", "INSTANCE_ID": f"refstack-{os.getpid()}",
            "MAX_CONCURRENT_REQUESTS": str(conc), "MAX_QUEUE_SIZE": "64", "MAX_REQUESTS_PER_MINUTE": "100000"}
     t_start = time.time()
     proc = subprocess.Popen(["bash", "-s"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
