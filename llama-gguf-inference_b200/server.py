@@ -108,7 +108,8 @@ class Handler(BaseHTTPRequestHandler):
                     f"llamacpp:predicted_tokens_seconds {tps:.3f}\nllamacpp:requests_processing {len(st.sched.active)}\n"
                     f"llamacpp:requests_deferred {len(st.sched.pending)}\n"
                     f"ggufb200:batched_steps_total {s.get('batched_steps', 0)}\nggufb200:chained_steps_total {s.get('chained_steps', 0)}\n"
-                    f"ggufb200:gpu_wait_seconds_total {s.get('gpu_wait_seconds', 0.0):.4f}\n")
+                    f"ggufb200:gpu_wait_seconds_total {s.get('gpu_wait_seconds', 0.0):.4f}\n"
+                    f"ggufb200:device_topk_tokens_total {s.get('device_topk_tokens', 0)}\n")
             return self._send(200, body.encode(), "text/plain; version=0.0.4")
         if p == "/":
             return self._send(200, b'{"status":"ok","server":"ggufb200"}')

@@ -153,3 +153,58 @@ def test_tensor_parallel_llama_server_under_torchrun(oracle, model_dir, tmp_path
                 proc.wait(timeout=60)
             except subprocess.TimeoutExpired:
                 os.killpg(proc.pid, signal.SIGKILL)
+
+
+def test_concurrent_sampled_requests_are_seeded_pipelined_and_sampled_from_device_candidates(model_dir, tmp_path):
+    """four concurrent requests with llama-server's default chain (temp 0.8, top-k 40, top-p 0.95), different lengths so that
+    sequences end while a pipelined step is in flight: every request returns its own max_tokens, the same seeds give the same
+    texts on a second round (batched logits are bit-identical whatever the batch composition), and the tokens were sampled from
+    the device's top-k candidates (/metrics)"""
+    import threading
+    from ggufb200 import synth
+    path = os.path.join(model_dir, "proc-small.gguf")
+    if not os.path.exists(path):
+        synth.write_gguf(path, "small", "Q4_K_M", seed=0xB200)
+    keyfile = tmp_path / "backend.key"
+    keyfile.write_text(KEY + "\n")
+    port = free_port()
+    argv = [os.path.join(ROOT, "bin", "llama-server"), "-m", path, "--host", "127.0.0.1", "--port", str(port), "-c", "256",
+            "--api-key-file", str(keyfile), "--parallel", "4", "--ignore-eos"]
+    proc = subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, GGB_GEMM_PREFILL_MIN="1000000"))
+    try:
+        for _ in range(120):
+            try:
+                if call(port, "GET", "/health", key=None)[0] == 200:
+                    break
+            except OSError:
+                pass
+            assert proc.poll() is None, proc.stdout.read()
+            time.sleep(0.25)
+        lens = [9, 23, 40, 31]
+
+        def round_():
+            out = [None] * 4
+
+            def one(j):
+                msg = [{"role": "user", "content": f"Tell me about topic number {j}"}]
+                out[j] = call(port, "POST", "/v1/chat/completions", {"messages": msg, "max_tokens": lens[j], "seed": 100 + j, "cache_prompt": False})
+            th = [threading.Thread(target=one, args=(j,)) for j in range(4)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+            return out
+        a, b = round_(), round_()
+        for j in range(4):
+            assert a[j][0] == 200 and a[j][1]["usage"]["completion_tokens"] == lens[j]
+            assert a[j][1]["choices"][0]["message"]["content"] == b[j][1]["choices"][0]["message"]["content"], j
+        assert len({a[j][1]["choices"][0]["message"]["content"][:20] for j in range(4)}) > 1      # sampled, different prompts / seeds
+        c = http.client.HTTPConnection("127.0.0.1", port, timeout=30)
+        c.request("GET", "/metrics", headers={"Authorization": f"Bearer {KEY}"})
+        metrics = c.getresponse().read().decode()
+        c.close()
+        topk = [float(l.split()[1]) for l in metrics.splitlines() if l.startswith("ggufb200:device_topk_tokens_total")][0]
+        assert topk >= 2 * sum(lens) - 8, metrics          # (the first token of a request comes from its prompt pass)
+        proc.send_signal(signal.SIGTERM)
+        assert proc.wait(timeout=30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
