@@ -276,6 +276,9 @@ int ggb_argmax_rows(const float* x, int64_t n, int nb, int32_t* out_idx, void* s
  * row b has (> cap: ties overflowed, read the row instead).  Exact; the host sorts them and runs top-p / min-p / temperature on
  * k numbers instead of reading back and partitioning n (llama.cpp's top-k sampler, [UPSTREAM-MEM: llama-sampling.cpp]). */
 int ggb_topk_rows(const float* x, int64_t n, int nb, int k, int cap, float* out_val, int32_t* out_idx, int32_t* out_cnt, void* stream);
+/* out[b][j] = x[b][idx[b][j]] (0 for an index outside 0..n-1): the raw logits of the tokens in a request's penalty window, which
+ * together with the top-(k + window) candidates determine the penalised top-k exactly (penalties only touch window tokens). */
+int ggb_gather_rows(const float* x, int64_t n, int nb, const int32_t* idx, int m, float* out, void* stream);
 /* Tensor-parallel batch: x [nb][n] is this rank's vocabulary shard starting at global row row_offset.  ggb_argmax_rows_key
  * packs (maximum, global index) of every row into one sortable signed 64-bit key (larger value, then smaller index);
  * after a MAX all-reduce of the keys ggb_argmax_keys_unpack yields the global first-maximum index of every row. */

@@ -231,27 +231,44 @@ class BatchDecoder:
             sl.reset()
         self._last = None
 
-    def candidates(self, nb: int, k: int, cap: int = 256):
-        """per row of the last step's logits: (token ids, logits) of every logit >= the k-th largest, or None for a row whose ties
-        overflowed the buffer; None altogether when the vocabulary is sharded.  One launch and one copy for all rows."""
+    def candidates(self, nb: int, k: int, cap: int = 256, extra=None):
+        """per row of the last step's logits: (token ids, logits, logits of extra[b]) -- every logit >= the k-th largest, plus the raw
+        logits of the tokens named in extra = {row: [ids]} (penalty windows) -- or None for a row whose ties overflowed the buffer;
+        None altogether when the vocabulary is sharded.  One top-k launch, one gather launch when asked, one copy for all rows."""
         e, torch = self.eng, self.torch
-        if self.tp > 1 or not (0 < nb <= self.nb_max and 0 < k <= min(cap, self.vl)):
+        m = max((len(v) for v in extra.values()), default=0) if extra else 0
+        if self.tp > 1 or not (0 < nb <= self.nb_max and 0 < k <= min(cap, self.vl)) or m > cap:
             return None
+        NB = self.nb_max
         if getattr(self, "_cand_dev", None) is None or self._cand_cap != cap:
             self._cand_cap = cap
-            self._cand_dev = torch.zeros(self.nb_max * (2 * cap + 1), dtype=torch.int32, device=e.dev)   # values | indices | counts
-            self._cand_host = torch.zeros(self.nb_max * (2 * cap + 1), dtype=torch.int32).pin_memory()
-        d, NB = self._cand_dev, self.nb_max
+            self._cand_dev = torch.zeros(NB * (4 * cap + 1), dtype=torch.int32, device=e.dev)   # values | indices | extra values | extra ids | counts
+            self._cand_host = torch.zeros(NB * (4 * cap + 1), dtype=torch.int32).pin_memory()
+            self._cand_ids = torch.zeros(NB * cap, dtype=torch.int32).pin_memory()
+        d = self._cand_dev
+        p0 = d.data_ptr()
         with torch.cuda.stream(self.stream):
-            cabi.check(self.lib.ggb_topk_rows(self.logits.data_ptr(), self.vl, nb, k, cap, d.data_ptr(), d.data_ptr() + 4 * NB * cap,
-                                              d.data_ptr() + 8 * NB * cap, self.stream.cuda_stream), "topk_rows")
+            cabi.check(self.lib.ggb_topk_rows(self.logits.data_ptr(), self.vl, nb, k, cap, p0, p0 + 4 * NB * cap, p0 + 16 * NB * cap,
+                                              self.stream.cuda_stream), "topk_rows")
+            if m:
+                ids = self._cand_ids.numpy()[:nb * m].reshape(nb, m)
+                ids[:] = -1
+                for b, v in extra.items():
+                    ids[b, :len(v)] = np.asarray(v, dtype=np.int32)
+                d[3 * NB * cap:3 * NB * cap + nb * m].copy_(self._cand_ids[:nb * m], non_blocking=True)
+                cabi.check(self.lib.ggb_gather_rows(self.logits.data_ptr(), self.vl, nb, p0 + 12 * NB * cap, m, p0 + 8 * NB * cap,
+                                                    self.stream.cuda_stream), "gather_rows")
             self._cand_host.copy_(d, non_blocking=True)
         self.stream.synchronize()
         h = self._cand_host.numpy()
         out = []
         for b in range(nb):
-            c = int(h[2 * NB * cap + b])
-            out.append(None if c > cap else (h[NB * cap + b * cap:NB * cap + b * cap + c].copy(), h[b * cap:b * cap + c].copy().view(np.float32)))
+            c = int(h[4 * NB * cap + b])
+            if c > cap:
+                out.append(None)
+                continue
+            ex = h[2 * NB * cap + b * m:2 * NB * cap + b * m + (len(extra.get(b, ())) if extra else 0)].copy().view(np.float32)
+            out.append((h[NB * cap + b * cap:NB * cap + b * cap + c].copy(), h[b * cap:b * cap + c].copy().view(np.float32), ex))
         return out
 
     def logits_row_tensor(self, b: int):

@@ -28,7 +28,7 @@ EXPORTS = [
     "ggb_residual_add_f64", "ggb_argmax_pack", "ggb_argmax_unpack_next",
     "ggb_embed_rows", "ggb_rope_kv_prefill", "ggb_attn_prefill", "ggb_add_f32",
     "ggb_peer_region_bytes", "ggb_peer_alloc", "ggb_peer_open", "ggb_peer_close", "ggb_peer_free", "ggb_peer_reduce_residual",
-    "ggb_act_image_bytes", "ggb_act_prep", "ggb_act_prep_tiled", "ggb_act_tiled_bytes", "ggb_gemv_batch_prefers_tiled", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows", "ggb_topk_rows", "ggb_argmax_rows_key", "ggb_argmax_keys_unpack",
+    "ggb_act_image_bytes", "ggb_act_prep", "ggb_act_prep_tiled", "ggb_act_tiled_bytes", "ggb_gemv_batch_prefers_tiled", "ggb_gemv_batch", "ggb_rope_kv_batch", "ggb_attn_decode_batch", "ggb_argmax_rows", "ggb_topk_rows", "ggb_gather_rows", "ggb_argmax_rows_key", "ggb_argmax_keys_unpack",
 ]
 
 
@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
         "ggb_attn_decode_batch": ([vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, vp], i32),
         "ggb_argmax_rows": ([vp, i64, i32, vp, vp], i32),
         "ggb_topk_rows": ([vp, i64, i32, i32, i32, vp, vp, vp, vp], i32),
+        "ggb_gather_rows": ([vp, i64, i32, vp, i32, vp, vp], i32),
         "ggb_argmax_rows_key": ([vp, i64, i32, i32, vp, vp], i32),
         "ggb_argmax_keys_unpack": ([vp, i32, vp, vp], i32),
         "ggb_argmax_pack": ([vp, vp, i32, i32, vp, vp], i32),

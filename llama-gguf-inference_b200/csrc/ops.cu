@@ -449,3 +449,20 @@ extern "C" int ggb_topk_rows(const float* x, int64_t n, int nb, int k, int cap, 
     GGB_CHECK_LAUNCH("ggb_topk_rows");
     return GGB_OK;
 }
+
+// x[b][idx[b][j]] for a few indices per row (the logits of the tokens in a request's penalty window); idx < 0 or >= n yields 0
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t n, const int32_t* __restrict__ idx, int m, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int32_t i = idx[(int64_t)b * m + j];
+        out[(int64_t)b * m + j] = (i >= 0 && i < n) ? x[(int64_t)b * n + i] : 0.f;
+    }
+}
+
+extern "C" int ggb_gather_rows(const float* x, int64_t n, int nb, const int32_t* idx, int m, float* out, void* stream) {
+    if (n <= 0 || nb < 0 || m < 0 || (nb && m && (!x || !idx || !out))) GGB_FAIL(GGB_ERR_ARG, "ggb_gather_rows: bad argument");
+    if (nb == 0 || m == 0) return GGB_OK;
+    gather_rows_kernel<<<nb, 128, 0, (cudaStream_t)stream>>>(x, n, idx, m, out);
+    GGB_CHECK_LAUNCH("ggb_gather_rows");
+    return GGB_OK;
+}

@@ -454,28 +454,35 @@ class Slot:
         self.stream.synchronize()
         return self.host_logits.numpy()
 
-    def read_candidates(self, k: int, cap: int = 256):
-        """(token ids, logits) of every logit >= the k-th largest (k of them, more on ties; unordered) -- what a top-k sampler needs
-        instead of the whole row: one ggb_topk_rows launch and a copy of cap pairs.  None when the vocabulary is sharded (tensor
+    def read_candidates(self, k: int, cap: int = 256, extra_ids=None):
+        """(token ids, logits, logits of extra_ids) -- every logit >= the k-th largest (k of them, more on ties; unordered), which is
+        what a top-k sampler needs instead of the whole row, plus the raw logits of a few named tokens (a penalty window): one
+        ggb_topk_rows launch, one ggb_gather_rows launch when asked, one copy.  None when the vocabulary is sharded (tensor
         parallelism) or ties overflowed the buffer: the caller then reads the row."""
         e, torch = self.eng, self.torch
-        if e.tp_size > 1 or not 0 < k <= min(cap, self.vl):
+        m = len(extra_ids) if extra_ids else 0
+        if e.tp_size > 1 or not 0 < k <= min(cap, self.vl) or m > cap:
             return None
         if getattr(self, "_cand_dev", None) is None or self._cand_cap != cap:
             self._cand_cap = cap
-            self._cand_dev = torch.zeros(2 * cap + 1, dtype=torch.int32, device=e.dev)      # values (f32 bits) | indices | count
-            self._cand_host = torch.zeros(2 * cap + 1, dtype=torch.int32).pin_memory()
+            self._cand_dev = torch.zeros(4 * cap + 1, dtype=torch.int32, device=e.dev)   # values (f32 bits) | indices | extra values | extra ids | count
+            self._cand_host = torch.zeros(4 * cap + 1, dtype=torch.int32).pin_memory()
+            self._cand_ids = torch.zeros(cap, dtype=torch.int32).pin_memory()
         d = self._cand_dev
+        p0 = d.data_ptr()
         with torch.cuda.stream(self.stream):
-            cabi.check(e.lib.ggb_topk_rows(self.logits.data_ptr(), self.vl, 1, k, cap, d.data_ptr(), d.data_ptr() + 4 * cap,
-                                           d.data_ptr() + 8 * cap, self.stream.cuda_stream), "topk_rows")
+            cabi.check(e.lib.ggb_topk_rows(self.logits.data_ptr(), self.vl, 1, k, cap, p0, p0 + 4 * cap, p0 + 16 * cap, self.stream.cuda_stream), "topk_rows")
+            if m:
+                self._cand_ids.numpy()[:m] = np.asarray(extra_ids, dtype=np.int32)
+                d[3 * cap:3 * cap + m].copy_(self._cand_ids[:m], non_blocking=True)
+                cabi.check(e.lib.ggb_gather_rows(self.logits.data_ptr(), self.vl, 1, p0 + 12 * cap, m, p0 + 8 * cap, self.stream.cuda_stream), "gather_rows")
             self._cand_host.copy_(d, non_blocking=True)
         self.stream.synchronize()
         h = self._cand_host.numpy()
-        c = int(h[2 * cap])
+        c = int(h[4 * cap])
         if c > cap:
             return None
-        return h[cap:cap + c].copy(), h[:c].copy().view(np.float32)
+        return h[cap:cap + c].copy(), h[:c].copy().view(np.float32), h[2 * cap:2 * cap + m].copy().view(np.float32)
 
     def logits_tensor(self):
         """this rank's (vocabulary-sharded under tensor parallelism) logits, on the device, after the stream has drained"""

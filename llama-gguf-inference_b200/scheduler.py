@@ -108,10 +108,42 @@ def _chain(idx: np.ndarray, xs: np.ndarray, sp: SamplingParams, rng: np.random.G
     return int(idx[rng.choice(len(idx), p=p)])
 
 
-def device_topk_ok(sp: SamplingParams) -> bool:
-    """the request can be sampled from the device's top-k candidates: no penalties (they change logits outside the top-k too),
-    a top_k that fits the candidate buffer"""
-    return not sp.arg_max and not sp.penalised and 0 < sp.top_k <= TOPK_CAP - 16 and os.environ.get("GGB_DEVICE_TOPK", "1") != "0"
+PENALTY_WINDOW_MAX = 128     # distinct window tokens whose logits the device gathers for a penalised request
+
+
+def penalty_window(sp: SamplingParams, history) -> list:
+    """the distinct token ids the penalties of this request touch (its last repeat_last_n tokens)"""
+    if not sp.penalised or not history:
+        return []
+    win = list(history)[-sp.repeat_last_n:] if sp.repeat_last_n > 0 else list(history)
+    return sorted(set(int(t) for t in win))
+
+
+def device_topk_ok(sp: SamplingParams, history=None) -> bool:
+    """the request can be sampled from what the device hands back -- the top-k candidates; with penalties the top-(k + window)
+    candidates plus the logits of the window tokens, which determine the penalised top-k exactly (a token outside the window keeps
+    its logit, so at most `window` of the tokens ranked above it can drop below it) -- when that fits the candidate buffer"""
+    if sp.arg_max and not sp.penalised:
+        return False
+    if os.environ.get("GGB_DEVICE_TOPK", "1") == "0":
+        return False
+    k = 1 if sp.arg_max else sp.top_k
+    w = len(penalty_window(sp, history)) if sp.penalised else 0
+    return 0 < k and k + w <= TOPK_CAP - 16 and w <= PENALTY_WINDOW_MAX
+
+
+def sample_from_candidates_penalised(idx, vals, win_ids, win_vals, sp: SamplingParams, rng, history) -> int:
+    """sample_token() for a penalised request on the union of the top-(k + window) candidates and the window tokens: the same
+    float32 penalty arithmetic on the same raw logits, the same top-k of the result (ties: lower token id first)"""
+    raw = {int(i): np.float32(v) for i, v in zip(idx, vals)}
+    raw.update({int(i): np.float32(v) for i, v in zip(win_ids, win_vals)})
+    ids = np.array(sorted(raw), dtype=np.int64)
+    small = np.array([raw[int(i)] for i in ids], dtype=np.float32)
+    pos = {int(t): j for j, t in enumerate(ids)}
+    win = (list(history)[-sp.repeat_last_n:] if sp.repeat_last_n > 0 else list(history)) if history else []
+    win = [pos[int(t)] for t in win if int(t) in pos]                          # (ids outside the vocabulary were never gathered)
+    sp_small = SamplingParams(**{**sp.__dict__, "repeat_last_n": 0})          # the window is already cut; ids are positions now
+    return int(ids[sample_token(small, sp_small, rng, win)])
 
 
 def sample_from_candidates(idx: np.ndarray, vals: np.ndarray, sp: SamplingParams, rng: np.random.Generator) -> int:
@@ -329,10 +361,13 @@ class Scheduler(threading.Thread):
         if a.req.sampling.greedy:
             return a.slot.read_last_token()
         sp = a.req.sampling
-        if device_topk_ok(sp) and hasattr(a.slot, "read_candidates"):
-            cand = a.slot.read_candidates(sp.top_k, TOPK_CAP)          # k numbers instead of the vocabulary
+        if device_topk_ok(sp, a.history) and hasattr(a.slot, "read_candidates"):
+            win = penalty_window(sp, a.history)
+            cand = a.slot.read_candidates((1 if sp.arg_max else sp.top_k) + len(win), TOPK_CAP, win)   # k numbers instead of the vocabulary
             if cand is not None:
                 self.stats["device_topk_tokens"] = self.stats.get("device_topk_tokens", 0) + 1
+                if sp.penalised:
+                    return sample_from_candidates_penalised(cand[0], cand[1], win, cand[2], sp, a.rng, a.history)
                 return sample_from_candidates(cand[0], cand[1], sp, a.rng)
         return sample_token(a.slot.read_logits(), sp, a.rng, a.history)
 
@@ -424,18 +459,23 @@ class Scheduler(threading.Thread):
         bd = self.engine.batch
         out = []
         cands = None
-        ks = [a.req.sampling.top_k for i, a in pairs if self.active.get(i) is a and device_topk_ok(a.req.sampling)]
-        if ks and hasattr(bd, "candidates"):
-            cands = bd.candidates(len(pairs), max(ks), TOPK_CAP)        # one launch + one small copy for every sampled row of the step
+        wins = {b: penalty_window(a.req.sampling, a.history) for b, (i, a) in enumerate(pairs)
+                if self.active.get(i) is a and device_topk_ok(a.req.sampling, a.history)}
+        if wins and hasattr(bd, "candidates"):
+            k = max((1 if pairs[b][1].req.sampling.arg_max else pairs[b][1].req.sampling.top_k) + len(w) for b, w in wins.items())
+            cands = bd.candidates(len(pairs), k, TOPK_CAP, wins)        # one launch + one small copy for every sampled row of the step
         for b, (i, a) in enumerate(pairs):
             if self.active.get(i) is not a:
                 continue                                                # ended or cancelled while the step was in flight
             sp = a.req.sampling
             if sp.greedy:
                 tok = toks[b]
-            elif cands is not None and device_topk_ok(sp) and cands[b] is not None:
+            elif cands is not None and b in wins and cands[b] is not None:
                 self.stats["device_topk_tokens"] = self.stats.get("device_topk_tokens", 0) + 1
-                tok = sample_from_candidates(cands[b][0], cands[b][1], sp, a.rng)
+                if sp.penalised:
+                    tok = sample_from_candidates_penalised(cands[b][0], cands[b][1], wins[b], cands[b][2], sp, a.rng, a.history)
+                else:
+                    tok = sample_from_candidates(cands[b][0], cands[b][1], sp, a.rng)
             else:
                 tok = sample_token(bd.logits_row(b), sp, a.rng, a.history)
             out.append((i, a, tok))

@@ -563,7 +563,7 @@ def test_device_candidates_equal_the_rows_top_k(oracle, model_dir):
     s0.prefill(PROMPT)
     s0.decode(3)
     row = s0.read_logits().copy()
-    idx, val = s0.read_candidates(sp.top_k)
+    idx, val, _ = s0.read_candidates(sp.top_k)
     assert set(idx.tolist()) == set(np.flatnonzero(row >= np.sort(row)[-sp.top_k]).tolist())
     assert np.array_equal(_bits(val), _bits(row[idx]))
     assert sample_from_candidates(idx, val, sp, np.random.default_rng(5)) == sample_token(row, sp, np.random.default_rng(5))
@@ -575,7 +575,16 @@ def test_device_candidates_equal_the_rows_top_k(oracle, model_dir):
     cands = eng.batch.candidates(3, sp.top_k)
     for s in range(3):
         row = eng.batch.logits_row(s).copy()
-        idx, val = cands[s]
+        idx, val, _ = cands[s]
         assert set(idx.tolist()) == set(np.flatnonzero(row >= np.sort(row)[-sp.top_k]).tolist())
         assert sample_from_candidates(idx, val, sp, np.random.default_rng(s)) == sample_token(row, sp, np.random.default_rng(s))
+    # a penalised request: top-(k + window) candidates + the window's raw logits decide exactly like the whole row
+    from ggufb200.scheduler import penalty_window, sample_from_candidates_penalised
+    spp = SamplingParams(temperature=0.7, top_k=20, top_p=0.9, repeat_penalty=1.3, presence_penalty=0.4, frequency_penalty=0.2, seed=1)
+    row = eng.batch.logits_row(1).copy()
+    hist = [int(t) for t in np.argsort(-row)[:12]] * 2 + [5, 5, 7]
+    win = penalty_window(spp, hist)
+    c = eng.batch.candidates(3, spp.top_k + len(win), 256, {1: win})[1]
+    assert np.array_equal(_bits(c[2]), _bits(row[win]))
+    assert sample_from_candidates_penalised(c[0], c[1], win, c[2], spp, np.random.default_rng(1), hist) == sample_token(row, spp, np.random.default_rng(1), hist)
     eng.close()

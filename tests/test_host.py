@@ -347,5 +347,34 @@ def test_sampling_from_device_candidates_equals_sampling_from_the_row():
         b = sample_from_candidates(idx, logits[idx], sp, np.random.default_rng(trial))
         assert a == b, trial
     assert not device_topk_ok(SamplingParams(temperature=0.0))                       # greedy: the arg-max kernel
-    assert not device_topk_ok(SamplingParams(repeat_penalty=1.1))                    # penalties reach below the top-k
+    assert device_topk_ok(SamplingParams(repeat_penalty=1.1), [3, 4, 5])             # penalised: candidates + the window's logits
+    assert not device_topk_ok(SamplingParams(repeat_penalty=1.1, repeat_last_n=0), list(range(300)))   # window too wide for the buffer
     assert not device_topk_ok(SamplingParams(top_k=0)) and not device_topk_ok(SamplingParams(top_k=1000))
+
+
+def test_penalised_sampling_from_candidates_and_window_logits_equals_sampling_from_the_row():
+    """penalties only touch the window tokens, so the top-(k + window) raw candidates plus the window's raw logits contain the
+    penalised top-k: scheduler.sample_from_candidates_penalised picks sample_token's token, greedy-with-penalties included"""
+    from ggufb200.scheduler import SamplingParams, device_topk_ok, penalty_window, sample_from_candidates_penalised, sample_token
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(400, 4000))
+        logits = (rng.standard_normal(n) * 3).astype(np.float32)
+        top = np.argsort(-logits)
+        hist = [int(t) for t in rng.choice(top[:30], size=int(rng.integers(1, 50)))] + [int(t) for t in rng.integers(0, n, 10)] + [n + 5]
+        sp = SamplingParams(temperature=0.0 if trial % 7 == 0 else float(rng.uniform(0.3, 1.2)), top_k=int(rng.integers(2, 60)),
+                            top_p=float(rng.choice([1.0, 0.9])), repeat_penalty=float(rng.choice([1.0, 1.1, 1.5])),
+                            presence_penalty=float(rng.choice([0.0, 0.5])), frequency_penalty=float(rng.choice([0.0, 0.3])),
+                            repeat_last_n=int(rng.choice([64, 16, 0])), seed=trial)
+        if not sp.penalised:
+            continue
+        assert device_topk_ok(sp, hist)
+        win = penalty_window(sp, hist)
+        k = (1 if sp.arg_max else sp.top_k) + len(win)
+        kth = np.sort(logits)[-min(k, n)]
+        idx = np.flatnonzero(logits >= kth).astype(np.int32)
+        rng.shuffle(idx)
+        win_vals = np.array([logits[t] if 0 <= t < n else 0.0 for t in win], dtype=np.float32)   # what ggb_gather_rows returns
+        a = sample_token(logits, sp, np.random.default_rng(trial), hist)
+        b = sample_from_candidates_penalised(idx, logits[idx], win, win_vals, sp, np.random.default_rng(trial), hist)
+        assert a == b, trial
