@@ -13,6 +13,7 @@ sampled requests, logits rows) are read back.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -58,6 +59,7 @@ class BatchDecoder:
         ids, pos, slot = (self.meta[i].data_ptr() for i in range(3))
         act = self.act.data_ptr()
         tp = self.tp > 1
+        apdl = int(pdl and os.environ.get("GGB_BATCH_PDL", "0") != "0")    # RoPE / KV write and attention launched programmatically too
 
         def prep(x, norm, k, w, tiled=0):
             if tiled:
@@ -94,7 +96,7 @@ class BatchDecoder:
             cabi.check(lib.ggb_rope_kv_batch(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), nb, pos, slot, self.slot_stride,
                                              self.nh, self.nkv, hp.head_dim, hp.n_rot, e.rope_tab.data_ptr(), kc, vc, s), "rope_kv_batch")
             cabi.check(lib.ggb_attn_decode_batch(self.q.data_ptr(), kc, vc, pos, slot, self.slot_stride, nb, self.nh, self.nkv,
-                                                 hp.head_dim, e.n_ctx, self.att.data_ptr(), 0, s), "attn_decode_batch")
+                                                 hp.head_dim, e.n_ctx, self.att.data_ptr(), apdl, s), "attn_decode_batch")
             row_split(self.att, L["wo"], qd)
             prep(self.x, L["ffn_norm"], hp.d, L["wg"])
             gemv([(L["wg"].ptr, L["wg"].type, L["wg"].rows, self.h.data_ptr()),

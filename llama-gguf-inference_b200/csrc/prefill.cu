@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 __global__ void add_f32_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n) {
@@ -77,6 +79,8 @@ __global__ void rope_kv_batch_kernel(float* __restrict__ q, const float* __restr
     const int qd = n_head * hd, kvd = n_kv * hd;
     const int pairs_per_tok = (qd + 2 * kvd) / 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();      /* programmatic launch (use_pdl): the attention behind may become resident; it waits for this grid */
+    pdl_wait();                   /* q, k, v come from the launch in front */
     if (idx >= nb * pairs_per_tok) return;
     const int t = idx / pairs_per_tok, p = idx - t * pairs_per_tok;
     const int pos = pos_dev[t];
@@ -116,9 +120,15 @@ extern "C" int ggb_rope_kv_batch(float* q, const float* k, const float* v, int n
     if (nb == 0) return GGB_OK;
     if (!q || !k || !v || !pos_dev || !slot_dev || !rope_tab || !kcache || !vcache) GGB_FAIL(GGB_ERR_ARG, "ggb_rope_kv_batch: null pointer");
     const int64_t total = (int64_t)nb * ((n_head + 2 * n_kv) * head_dim / 2);
-    rope_kv_batch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, k, v, nb, pos_dev, slot_dev, slot_stride, n_head, n_kv,
-                                                                                          head_dim, n_rot, rope_tab, kcache, vcache);
-    GGB_CHECK_LAUNCH("ggb_rope_kv_batch");
+    // GGB_BATCH_PDL=1 (read per call; the launches are captured into graphs): programmatic dependent launch, like the kernels either side
+    const char* pe = getenv("GGB_BATCH_PDL");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((total + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pe && *pe && atoi(pe) != 0) ? 1 : 0;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, rope_kv_batch_kernel, q, k, v, nb, pos_dev, slot_dev, slot_stride, n_head, n_kv, head_dim, n_rot, rope_tab, kcache, vcache));
     return GGB_OK;
 }
 
