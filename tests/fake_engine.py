@@ -42,6 +42,19 @@ class OracleSlot:
     def read_logits(self):
         return self.logits
 
+    def read_candidates(self, k, cap=256, extra_ids=None):
+        """what Slot.read_candidates takes off the GPU (ggb_topk_rows + ggb_gather_rows), restated with numpy"""
+        return _candidates(np.asarray(self.logits, dtype=np.float32), k, cap, extra_ids)
+
+
+def _candidates(row, k, cap, extra_ids):
+    idx = np.flatnonzero(row >= np.sort(row)[-k]).astype(np.int32)
+    if idx.size > cap:
+        return None
+    np.random.default_rng(int(idx.sum())).shuffle(idx)          # the device emits them unordered
+    ex = np.array([row[t] if 0 <= t < row.size else 0.0 for t in (extra_ids or [])], dtype=np.float32)
+    return idx, row[idx], ex
+
 
 class OracleEngine:
     def __init__(self, path, n_ctx=128, n_slots=1):
@@ -118,3 +131,6 @@ class OracleBatch:
 
     def logits_row(self, b):
         return self.rows[b]
+
+    def candidates(self, nb, k, cap=256, extra=None):
+        return [_candidates(np.asarray(self.rows[b], dtype=np.float32), k, cap, (extra or {}).get(b)) for b in range(nb)]

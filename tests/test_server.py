@@ -425,3 +425,33 @@ def test_prompt_cache_reuses_the_common_prefix(oracle, backend):
     r3 = call(p, "POST", "/v1/chat/completions", {"messages": follow, "max_tokens": 10, "temperature": 0, "cache_prompt": False})[1]
     assert sched.stats.get("prompt_tokens_cached", 0) == before
     assert r3["choices"][0]["message"]["content"] == want
+
+
+def test_sampled_requests_use_device_candidates_and_give_the_whole_row_tokens(oracle, backend, monkeypatch):
+    """the scheduler's candidate path (top-k candidates + penalty-window logits instead of whole rows; sampled batches pipelined):
+    the same seeded requests -- plain chain, penalised, greedy-with-penalties, alone and two at a time -- return the texts the
+    whole-row path returns (GGB_DEVICE_TOPK=0), and the candidate path is what ran"""
+    p, st = backend["port"], backend["state"]
+    bodies = [{"messages": MSG, "max_tokens": 14, "temperature": 0.9, "top_k": 30, "top_p": 0.9, "seed": 11},
+              {"messages": MSG, "max_tokens": 9, "temperature": 0.7, "top_k": 20, "repeat_penalty": 1.3, "presence_penalty": 0.3, "seed": 12},
+              {"messages": MSG, "max_tokens": 11, "temperature": 0.0, "frequency_penalty": 0.5, "repeat_penalty": 1.2}]
+
+    def run_all():
+        out = [call(p, "POST", "/v1/chat/completions", b) for b in bodies]                  # one at a time
+        res = {}
+        ts = [threading.Thread(target=lambda j=j: res.__setitem__(j, call(p, "POST", "/v1/chat/completions", bodies[j]))) for j in (0, 1)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return out + [res[0], res[1]]
+
+    before = st.sched.stats.get("device_topk_tokens", 0)
+    fast = run_all()
+    used = st.sched.stats.get("device_topk_tokens", 0) - before
+    monkeypatch.setenv("GGB_DEVICE_TOPK", "0")
+    slow = run_all()
+    assert st.sched.stats.get("device_topk_tokens", 0) - before == used                    # the whole-row path did not count
+    for a, b in zip(fast, slow):
+        assert a[0] == 200 and b[0] == 200
+        assert a[1]["choices"][0]["message"]["content"] == b[1]["choices"][0]["message"]["content"]
+    assert fast[0][1]["choices"][0]["message"]["content"] == fast[3][1]["choices"][0]["message"]["content"]   # alone == in a batch
+    assert used >= 14 + 9 + 11 + 14 + 9 - 5
