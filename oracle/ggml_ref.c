@@ -8,11 +8,12 @@
  * (llama-gguf-inference_b200/) never links, imports or calls anything in oracle/.
  *
  * PARITY PINNING STATUS
- *   - dequantize_row_{q8_0,q4_K,q5_K,q6_K}: PINNED bit-exact against gguf-py 0.19.0
- *     (`gguf.quants.dequantize`, site-packages/gguf/quants.py:396-401, 475-522, 525-549, 552-572 --
- *     the python package published from the llama.cpp tree) through tests/golden/dequant_*.npz.
+ *   - dequantize_row_{q8_0,q4_K,q5_K,q6_K,q4_0,q5_0}: PINNED bit-exact against gguf-py 0.19.0
+ *     (`gguf.quants.dequantize`, site-packages/gguf/quants.py:396-401, 475-522, 525-549, 552-572; Q4_0 / Q5_0
+ *     classes of the same file -- the python package published from the llama.cpp tree) through
+ *     tests/golden/dequant_*.npz.
  *   - quantize_row_q8_0: PINNED bit-exact against gguf-py `Q8_0.quantize_blocks` (quants.py:378-394).
- *   - quantize_row_q8_K, vec_dot_*_q8_K, rms_norm, rope, soft_max, silu, graph order:
+ *   - quantize_row_q8_K, vec_dot_*_q8_K, vec_dot_{q4_0,q5_0}_q8_0, rms_norm, rope, soft_max, silu, graph order:
  *     PARITY UNPINNED. The upstream sources (ggml/src/ggml-quants.c, ggml/src/ggml-cpu/quants.c,
  *     ggml/src/ggml-cpu/ops.cpp, src/llama-model.cpp) are not vendored by the reference (it pulls a
  *     prebuilt, unpinned `ghcr.io/ggml-org/llama.cpp:server` image) and are not on this machine, and
